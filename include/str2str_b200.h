@@ -1,0 +1,117 @@
+/*
+ * str2str_b200 — C ABI of the B200-native Str2Str denoising hot path.
+ *
+ * The reference (lujiarui/Str2Str) is pure Python: it has no FFI.  Its "operator interface" for this path is a
+ * set of Python call signatures.  This header is the boundary those signatures are re-implemented
+ * on: plain device pointers, sizes and a cudaStream_t (passed as void*), no torch types.  The Python host mirror
+ * (str2str_b200/net, str2str_b200/score) binds it with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.  Every entry point returns 0 on success and a non-zero code on failure, in which case
+ * s2s_last_error() describes the problem; nothing aborts and nothing falls back to the CPU.
+ *
+ * All tensors are contiguous, row-major, on the current device.  fp32 unless noted; residue indices and
+ * residue types are int64 as in the reference batch dict.  B = decoys in flight, L = residues.
+ */
+#ifndef STR2STR_B200_H
+#define STR2STR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s2s_ctx s2s_ctx;
+
+#define S2S_ABI_VERSION 1
+
+int s2s_abi_version(void);
+const char* s2s_last_error(void);
+
+/* ---- context: weights + workspace ------------------------------------------------------------------------
+ * Replaces DenoisingNet.__init__ + load_state_dict (reference src/models/net/denoising_ipa.py:162-169,
+ * src/utils/checkpoint_utils.py:16-20).  Host tables (all host pointers, copied):
+ *   tfreq[16]      exp(-k ln(1e4)/15)                 denoising_ipa.py:39-41
+ *   pdenom[16]     2056^(2k/32)                        denoising_ipa.py:26-30
+ *   bin_lower[22]  linspace(1e-5, 20, 22)              geo_utils.py:49-53
+ *   backbone[21*33] ideal backbone geometry per residue type (str2str_b200/backbone_constants.py)
+ */
+s2s_ctx* s2s_create(const float* tfreq, const float* pdenom, const float* bin_lower, const float* backbone);
+void s2s_destroy(s2s_ctx* ctx);
+/* Register one tensor of the reference state dict by its key (e.g. "translator.trunk.ipa_0.linear_q.weight").
+ * `data` is a DEVICE pointer to fp32 that must stay alive until s2s_destroy. */
+int s2s_set_param(s2s_ctx* ctx, const char* name, const float* data, int64_t numel);
+/* Check that all 274 tensors are present with the right sizes and build the derived device tensors
+ * (bf16 / split / transposed weight images, concatenated projections, softplus head weights). */
+int s2s_finalize(s2s_ctx* ctx, void* stream);
+/* Options: "pair_kernels" 0 = SIMT cross-check kernels, 1 = tcgen05 kernels (default);
+ *          "node_gemm"    0 = exact fp32 FFMA everywhere, 1 = tensor-core GEMMs where the parity budget allows. */
+int s2s_set_option(s2s_ctx* ctx, const char* key, int value);
+/* Size the workspace for (B, L) and build the relative-position table for residue-index offsets in
+ * [d_min, d_max] (= min/max of residue_idx[i] - residue_idx[j]).  Must be called before s2s_net_forward and
+ * outside CUDA-graph capture; calling it again with a larger shape re-allocates. */
+int s2s_reserve(s2s_ctx* ctx, int B, int L, int d_min, int d_max, void* stream);
+
+/* ---- score network ------------------------------------------------------------------------------------------
+ * DenoisingNet.forward (denoising_ipa.py:171-211) without the backbone build:
+ *   rigids_t [B,L,7] (quat wxyz + trans in Angstrom), sc_ca [B,L,3], t [B], residue_idx [B,L] int64,
+ *   residue_mask / fixed_mask [B,L], gt_psi [B,L,2] (torsion_angles_sin_cos[..., 2, :])
+ *   -> out_rigids [B,L,7], out_psi [B,L,2]. */
+int s2s_net_forward(s2s_ctx* ctx, int B, int L, const float* rigids_t, const float* sc_ca, const float* t,
+                    const int64_t* residue_idx, const float* residue_mask, const float* fixed_mask,
+                    const float* gt_psi, float* out_rigids, float* out_psi, void* stream);
+
+/* Stage entry points (the same code s2s_net_forward runs), exposed for module-level parity tests.
+ * EmbeddingModule.forward (denoising_ipa.py:107-159) followed by the mask multiply (:186-187):
+ *   node_out [B,L,256] fp32, z_out [B,L,L,128] bf16. */
+int s2s_embed(s2s_ctx* ctx, int B, int L, const float* t, const int64_t* residue_idx, const float* fixed_mask,
+              const float* sc_ca, const float* residue_mask, float* node_out, void* z_out, void* stream);
+/* TranslationIPA.forward (ipa.py:331-387) on given embeddings: node_embed [B,L,256] fp32 and z [B,L,L,128] bf16,
+ * both already multiplied by their masks.  gt_psi may be NULL: out_psi is then the raw torsion head output. */
+int s2s_trunk(s2s_ctx* ctx, int B, int L, const float* node_embed, const void* z, const float* rigids_t,
+              const float* residue_mask, const float* fixed_mask, const float* gt_psi, float* out_rigids,
+              float* out_psi, void* stream);
+/* InvariantPointAttention.forward of trunk block `blk` (ipa.py:100-268): quat [B,L,4] (not normalised),
+ * trans_nm [B,L,3] (already x0.1), z [B,L,L,128] bf16 -> out [B,L,256] (before the mask multiply of ipa.py:350). */
+int s2s_ipa(s2s_ctx* ctx, int blk, int B, int L, const float* node, const void* z, const float* quat,
+            const float* trans_nm, const float* residue_mask, float* out, void* stream);
+/* EdgeTransition.forward of block `blk` followed by the edge-mask multiply (layers.py:170-185, ipa.py:371-372);
+ * z_out may alias z_in. */
+int s2s_edge_transition(s2s_ctx* ctx, int blk, int B, int L, const float* node, const void* z_in,
+                        const float* residue_mask, void* z_out, void* stream);
+
+/* ---- SE(3) diffusion step ------------------------------------------------------------------------------------
+ * FrameDiffuser.score + FrameDiffuser.reverse (reference src/models/score/frame.py:109-210).
+ * Per-decoy schedule scalars are computed by the host exactly as the reference computes them (same torch ops,
+ * so the integer sigma bucket is bit-identical) and passed in:
+ *   sched_f [B][8] = t, sigma_q = discrete_sigma[bucket], g_rot(t), g_rot(t)^2, exp(-beta(t)/2), 1-exp(-beta(t)),
+ *                    b(t), sqrt(b(t))          (so3.py:205-234, r3.py:26-41)
+ *   sched_d [B][2] = dt, sqrt(dt)              (double)
+ * mode 0: fused score + reverse (scores optional outputs); 1: scores only; 2: reverse from given scores.
+ * Scores are fp64 like the reference's (its fp64 masks promote them, frame.py:137-138).
+ * rot_noise / trans_noise [B,L,3]: N(0,1) draws, required when probability_flow == 0. */
+int s2s_se3_step(int B, int L, const float* rigids_t, const float* rigids_0, const float* residue_mask,
+                 const float* diffuse_mask, const float* sched_f, const double* sched_d, const float* rot_noise,
+                 const float* trans_noise, float noise_scale, int probability_flow, int mode, double* rot_score,
+                 double* trans_score, float* rigids_out, void* stream);
+/* FrameDiffuser.forward_marginal (frame.py:36-107) with the three random draws supplied by the caller:
+ *   rot0 [B,L,3,3], trans0 [B,L,3], sched_f [B][2] = exp(-beta/2), sqrt(1-exp(-beta)), cdf [B][1000] fp64 row of
+ *   SO3Diffuser._cdf for each decoy's sigma bucket, omega_grid [1000]. */
+int s2s_se3_perturb(int B, int L, const float* rot0, const float* trans0, const float* diffuse_mask,
+                    const float* sched_f, const double* cdf, const float* omega_grid, const float* axis_noise,
+                    const float* u_noise, const float* trans_noise, float* rigids_out, void* stream);
+/* compute_backbone (reference src/common/all_atom.py:141-173): atom37 [B,L,37,3], atom14 [B,L,14,3] (nullable).
+ * aatype may be NULL (all alanine, as the reference does for aatype=None). */
+int s2s_backbone_atoms(s2s_ctx* ctx, int rows, const float* rigids, const float* psi, const int64_t* aatype,
+                       float* atom37, float* atom14, void* stream);
+
+/* Exact-fp32 GEMM  C[M,N] = A[M,K] W[N,K]^T + bias  (unit test hook for the node-track GEMM). */
+int s2s_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
+                   void* stream);
+
+/* number of kernels launched by this library since load (for bench.py's gpu_launches) */
+int64_t s2s_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STR2STR_B200_H */

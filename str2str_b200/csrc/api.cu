@@ -1,0 +1,588 @@
+// C ABI (include/str2str_b200.h): context, weight preparation, workspace, and the network forward that
+// strings the kernels together.  Host-side only orchestration; every arithmetic op is a kernel of this library.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/str2str_b200.h"
+#include "s2s_internal.cuh"
+
+namespace s2s {
+
+long long g_launch_count = 0;
+static thread_local std::string g_error;
+
+namespace {
+
+// ---- weight preparation kernels ----------------------------------------------------------------------
+// dst[c][r] = bf16(src[r][c0 + c]) : transposed bf16 image of a weight sub-block
+__global__ void prep_bf16_t_kernel(const float* __restrict__ src, long ld, int rows, int c0, int cols, bf16* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  dst[(long)c * rows + r] = __float2bfloat16_rn(src[(long)r * ld + c0 + c]);
+}
+// hi[r][c] = bf16(src[r][c0+c]); lo = bf16(src - hi)   (lo may be null)
+__global__ void prep_bf16_split_kernel(const float* __restrict__ src, long ld, int rows, int c0, int cols,
+                                       bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  const float v = src[(long)r * ld + c0 + c];
+  const bf16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+// dst[c][r] = src[r][c0 + c]  (fp32 transpose of a sub-block)
+__global__ void prep_f32_t_kernel(const float* __restrict__ src, long ld, int rows, int c0, int cols, float* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  dst[(long)c * rows + r] = src[(long)r * ld + c0 + c];
+}
+
+struct Slab {  // bump allocator over one cudaMalloc
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = off = 0;
+  }
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    S2S_CHECK(off <= cap, "workspace overflow");
+    return p;
+  }
+};
+
+struct IpaW {
+  float *proj_w, *proj_b;  // [6816][256], [6816]: q | kv | q_points | kv_points
+  bf16 *Wb_hi, *Wb_lo;
+  float *Wdz_t, *pt_w;
+};
+struct EtW {
+  bf16 *W1z, *W2, *Wfh, *Wfz, *W1zt, *W2t, *Wft, *Wfzt;
+};
+
+}  // namespace
+}  // namespace s2s
+
+using namespace s2s;
+
+struct s2s_ctx {
+  std::map<std::string, std::pair<const float*, int64_t>> params;
+  bool finalized = false;
+  int opt_pair = 1, opt_node = 0;
+  float *tfreq = nullptr, *pdenom = nullptr, *bin_lower = nullptr, *backbone = nullptr;
+  Slab wslab;  // derived weights
+  IpaW ipa[N_BLK];
+  EtW et[N_BLK - 1];
+  bf16 *ee_W2, *ee_W3, *ee_W2t, *ee_W3t;
+  float* ee_Wd;
+  // workspace
+  Slab ws;
+  int cap_B = 0, cap_L = 0, d_min = 0, n_off = 0;
+  float *feat65, *tf33, *node, *init_node, *a256, *b256, *proj, *feats, *q_pts, *k_pts, *v_pts, *S, *opt;
+  float *skip64, *x320, *t320, *y320, *qkv, *nprime, *u384, *v384, *p128, *q128, *Ti, *Tj, *Tpos, *relfeat;
+  float *quat, *trans, *upd6, *psi_u, *diffuse, *keybias;
+  bf16* z;
+
+  const float* P(const std::string& n) const {
+    auto it = params.find(n);
+    S2S_CHECK(it != params.end(), "missing parameter " + n);
+    return it->second.first;
+  }
+};
+
+namespace {
+
+void linear(const s2s_ctx* c, const float* x, long ldx, const float* W, long ldw, const float* bias, float* y, long ldy,
+            int M, int N, int K, cudaStream_t st, int relu = 0, const float* res = nullptr, long ldres = 0,
+            const float* row_pre = nullptr, const float* row_post = nullptr) {
+  (void)c;
+  GemmArgs g;
+  g.A = x; g.lda = ldx; g.B = W; g.ldb = ldw; g.C = y; g.ldc = ldy;
+  g.bias = bias; g.res = res; g.ldres = ldres; g.row_pre = row_pre; g.row_post = row_post;
+  g.M = M; g.N = N; g.K = K; g.relu = relu;
+  gemm_f32(g, st);
+}
+
+struct ParamSpec { std::string name; int64_t numel; };
+
+std::vector<ParamSpec> expected_params() {
+  std::vector<ParamSpec> v;
+  auto lin = [&](const std::string& n, int o, int i) { v.push_back({n + ".weight", (int64_t)o * i}); v.push_back({n + ".bias", o}); };
+  auto ln = [&](const std::string& n, int d) { v.push_back({n + ".weight", d}); v.push_back({n + ".bias", d}); };
+  lin("embedder.node_embed.0", 256, 65); lin("embedder.node_embed.2", 256, 256); lin("embedder.node_embed.4", 256, 256); ln("embedder.node_embed.5", 256);
+  lin("embedder.edge_embed.0", 128, 120); lin("embedder.edge_embed.2", 128, 128); lin("embedder.edge_embed.4", 128, 128); ln("embedder.edge_embed.5", 128);
+  for (int b = 0; b < N_BLK; ++b) {
+    const std::string t = "translator.trunk.", s = std::to_string(b);
+    v.push_back({t + "ipa_" + s + ".head_weights", 8});
+    lin(t + "ipa_" + s + ".linear_q", 2048, 256); lin(t + "ipa_" + s + ".linear_kv", 4096, 256);
+    lin(t + "ipa_" + s + ".linear_q_points", 192, 256); lin(t + "ipa_" + s + ".linear_kv_points", 480, 256);
+    lin(t + "ipa_" + s + ".linear_b", 8, 128); lin(t + "ipa_" + s + ".down_z", 32, 128);
+    lin(t + "ipa_" + s + ".linear_out", 256, IPA_FEAT);
+    ln(t + "ipa_ln_" + s, 256); lin(t + "skip_embed_" + s, 64, 256);
+    for (int l = 0; l < 2; ++l) {
+      const std::string tl = t + "transformer_" + s + ".layers." + std::to_string(l) + ".";
+      v.push_back({tl + "self_attn.in_proj_weight", 960 * 320}); v.push_back({tl + "self_attn.in_proj_bias", 960});
+      lin(tl + "self_attn.out_proj", 320, 320); lin(tl + "linear1", 320, 320); lin(tl + "linear2", 320, 320);
+      ln(tl + "norm1", 320); ln(tl + "norm2", 320);
+    }
+    lin(t + "linear_" + s, 256, 320);
+    lin(t + "node_transition_" + s + ".linear_1", 256, 256); lin(t + "node_transition_" + s + ".linear_2", 256, 256);
+    lin(t + "node_transition_" + s + ".linear_3", 256, 256); ln(t + "node_transition_" + s + ".ln", 256);
+    lin(t + "bb_update_" + s + ".linear", 6, 256);
+    if (b < N_BLK - 1) {
+      const std::string e = t + "edge_transition_" + s + ".";
+      lin(e + "initial_embed", 128, 256); lin(e + "trunk.0", 384, 384); lin(e + "trunk.2", 384, 384);
+      lin(e + "final_layer", 128, 384); ln(e + "layer_norm", 128);
+    }
+  }
+  lin("translator.torsion_pred.linear_1", 256, 256); lin("translator.torsion_pred.linear_2", 256, 256);
+  lin("translator.torsion_pred.linear_3", 256, 256); lin("translator.torsion_pred.linear_final", 2, 256);
+  return v;
+}
+
+void prep_t_bf16(const float* src, long ld, int rows, int c0, int cols, bf16* dst, cudaStream_t st) {
+  prep_bf16_t_kernel<<<ceil_div((long)rows * cols, 256), 256, 0, st>>>(src, ld, rows, c0, cols, dst);
+  S2S_LAUNCH_CHECK();
+}
+void prep_split(const float* src, long ld, int rows, int c0, int cols, bf16* hi, bf16* lo, cudaStream_t st) {
+  prep_bf16_split_kernel<<<ceil_div((long)rows * cols, 256), 256, 0, st>>>(src, ld, rows, c0, cols, hi, lo);
+  S2S_LAUNCH_CHECK();
+}
+void prep_t_f32(const float* src, long ld, int rows, int c0, int cols, float* dst, cudaStream_t st) {
+  prep_f32_t_kernel<<<ceil_div((long)rows * cols, 256), 256, 0, st>>>(src, ld, rows, c0, cols, dst);
+  S2S_LAUNCH_CHECK();
+}
+
+void do_finalize(s2s_ctx* c, cudaStream_t st) {
+  for (const auto& ps : expected_params()) {
+    auto it = c->params.find(ps.name);
+    S2S_CHECK(it != c->params.end(), "missing parameter " + ps.name);
+    S2S_CHECK(it->second.second == ps.numel, "parameter " + ps.name + " has " + std::to_string(it->second.second) +
+                                                 " elements, expected " + std::to_string(ps.numel));
+  }
+  c->wslab.release();
+  c->wslab.cap = 64u << 20;
+  S2S_CUDA(cudaMalloc(&c->wslab.base, c->wslab.cap));
+  const std::string t = "translator.trunk.";
+  for (int b = 0; b < N_BLK; ++b) {
+    const std::string ip = t + "ipa_" + std::to_string(b) + ".";
+    IpaW& w = c->ipa[b];
+    w.proj_w = c->wslab.take<float>(6816 * 256);
+    w.proj_b = c->wslab.take<float>(6816);
+    const struct { const char* n; int rows; int off; } parts[4] = {
+        {"linear_q", 2048, 0}, {"linear_kv", 4096, 2048}, {"linear_q_points", 192, 6144}, {"linear_kv_points", 480, 6336}};
+    for (const auto& p : parts) {
+      S2S_CUDA(cudaMemcpyAsync(w.proj_w + (size_t)p.off * 256, c->P(ip + p.n + ".weight"), (size_t)p.rows * 256 * 4, cudaMemcpyDeviceToDevice, st));
+      S2S_CUDA(cudaMemcpyAsync(w.proj_b + p.off, c->P(ip + p.n + ".bias"), (size_t)p.rows * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    w.Wb_hi = c->wslab.take<bf16>(8 * 128);
+    w.Wb_lo = c->wslab.take<bf16>(8 * 128);
+    prep_split(c->P(ip + "linear_b.weight"), 128, 8, 0, 128, w.Wb_hi, w.Wb_lo, st);
+    w.Wdz_t = c->wslab.take<float>(128 * 32);
+    prep_t_f32(c->P(ip + "down_z.weight"), 128, 32, 0, 128, w.Wdz_t, st);
+    w.pt_w = c->wslab.take<float>(8);
+    softplus_point_weights(c->P(ip + "head_weights"), w.pt_w, st);
+    if (b < N_BLK - 1) {
+      const std::string e = t + "edge_transition_" + std::to_string(b) + ".";
+      EtW& x = c->et[b];
+      const float *W1 = c->P(e + "trunk.0.weight"), *W2 = c->P(e + "trunk.2.weight"), *Wf = c->P(e + "final_layer.weight");
+      x.W1z = c->wslab.take<bf16>(384 * 128); x.W1zt = c->wslab.take<bf16>(384 * 128);
+      x.W2 = c->wslab.take<bf16>(384 * 384);  x.W2t = c->wslab.take<bf16>(384 * 384);
+      x.Wfh = c->wslab.take<bf16>(128 * 384); x.Wft = c->wslab.take<bf16>(128 * 384);
+      x.Wfz = c->wslab.take<bf16>(128 * 128); x.Wfzt = c->wslab.take<bf16>(128 * 128);
+      prep_split(W1, 384, 384, 0, 128, x.W1z, nullptr, st);  prep_t_bf16(W1, 384, 384, 0, 128, x.W1zt, st);
+      prep_split(W2, 384, 384, 0, 384, x.W2, nullptr, st);   prep_t_bf16(W2, 384, 384, 0, 384, x.W2t, st);
+      prep_split(Wf, 384, 128, 0, 384, x.Wfh, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 384, x.Wft, st);
+      prep_split(Wf, 384, 128, 0, 128, x.Wfz, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 128, x.Wfzt, st);
+    }
+  }
+  {
+    const float *W1 = c->P("embedder.edge_embed.0.weight"), *W2 = c->P("embedder.edge_embed.2.weight"),
+                *W3 = c->P("embedder.edge_embed.4.weight");
+    c->ee_W2 = c->wslab.take<bf16>(128 * 128); c->ee_W2t = c->wslab.take<bf16>(128 * 128);
+    c->ee_W3 = c->wslab.take<bf16>(128 * 128); c->ee_W3t = c->wslab.take<bf16>(128 * 128);
+    c->ee_Wd = c->wslab.take<float>(N_BINS * 128);
+    prep_split(W2, 128, 128, 0, 128, c->ee_W2, nullptr, st); prep_t_bf16(W2, 128, 128, 0, 128, c->ee_W2t, st);
+    prep_split(W3, 128, 128, 0, 128, c->ee_W3, nullptr, st); prep_t_bf16(W3, 128, 128, 0, 128, c->ee_W3t, st);
+    prep_t_f32(W1, 120, 128, 98, N_BINS, c->ee_Wd, st);
+  }
+  // Wfh above holds the full [128][384] final-layer image; only its action on h2 (all 384 inputs) is used:
+  // final_layer(h2 + x) = Wf h2 + Wf[:, :128] z + Wf[:,128:256] n_i + Wf[:,256:] n_j.
+  c->finalized = true;
+}
+
+void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st) {
+  S2S_CHECK(c->finalized, "s2s_finalize must run before s2s_reserve");
+  S2S_CHECK(B > 0 && L > 0 && d_max >= d_min, "reserve: bad shape");
+  const int n_off = d_max - d_min + 1;
+  if (!(B <= c->cap_B && L <= c->cap_L && c->d_min == d_min && c->n_off == n_off && c->ws.base)) {
+    if (c->ws.base) S2S_CUDA(cudaDeviceSynchronize());
+    c->ws.release();
+    const size_t R = (size_t)B * L;
+    size_t bytes = 0;
+    auto add = [&](size_t n, size_t sz) { bytes += ((n * sz + 255) & ~size_t(255)) + 256; };
+    add(R * 65, 4); add(R * 33, 4); for (int k = 0; k < 4; ++k) add(R * 256, 4);
+    add(R * 6816, 4); add(R * IPA_FEAT, 4); add(R * 192, 4); add(R * 192, 4); add(R * 288, 4);
+    add((size_t)B * N_H * L * L, 4); add(R * 288, 4);
+    add(R * 64, 4); for (int k = 0; k < 3; ++k) add(R * 320, 4); add(R * 960, 4);
+    add(R * 128, 4); add(R * 384, 4); add(R * 384, 4); add(R * 128, 4); add(R * 128, 4); add(R * 128, 4); add(R * 128, 4);
+    add((size_t)n_off * 128, 4); add((size_t)n_off * 32, 4);
+    add(R * 4, 4); add(R * 3, 4); add(R * 6, 4); add(R * 2, 4); add(R, 4); add(R, 4);
+    add(R * L * C_Z, 2);
+    c->ws.cap = bytes + 4096;
+    S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
+    Slab& w = c->ws;
+    c->feat65 = w.take<float>(R * 65); c->tf33 = w.take<float>(R * 33);
+    c->node = w.take<float>(R * 256); c->init_node = w.take<float>(R * 256); c->a256 = w.take<float>(R * 256); c->b256 = w.take<float>(R * 256);
+    c->proj = w.take<float>(R * 6816); c->feats = w.take<float>(R * IPA_FEAT);
+    c->q_pts = w.take<float>(R * 192); c->k_pts = w.take<float>(R * 192); c->v_pts = w.take<float>(R * 288);
+    c->S = w.take<float>((size_t)B * N_H * L * L); c->opt = w.take<float>(R * 288);
+    c->skip64 = w.take<float>(R * 64); c->x320 = w.take<float>(R * 320); c->t320 = w.take<float>(R * 320); c->y320 = w.take<float>(R * 320);
+    c->qkv = w.take<float>(R * 960);
+    c->nprime = w.take<float>(R * 128); c->u384 = w.take<float>(R * 384); c->v384 = w.take<float>(R * 384);
+    c->p128 = w.take<float>(R * 128); c->q128 = w.take<float>(R * 128); c->Ti = w.take<float>(R * 128); c->Tj = w.take<float>(R * 128);
+    c->Tpos = w.take<float>((size_t)n_off * 128); c->relfeat = w.take<float>((size_t)n_off * 32);
+    c->quat = w.take<float>(R * 4); c->trans = w.take<float>(R * 3); c->upd6 = w.take<float>(R * 6); c->psi_u = w.take<float>(R * 2);
+    c->diffuse = w.take<float>(R); c->keybias = w.take<float>(R);
+    c->z = w.take<bf16>(R * L * C_Z);
+    c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
+  }
+  // relative-position table: Tpos[r] = W1[:,66:98] pos(d_min + r)   (denoising_ipa.py:144-149)
+  relpos_features(c->pdenom, c->relfeat, d_min, n_off, st);
+  linear(c, c->relfeat, 32, c->P("embedder.edge_embed.0.weight") + 66, 120, nullptr, c->Tpos, 128, n_off, 128, 32, st);
+}
+
+void check_shape(const s2s_ctx* c, int B, int L) {
+  S2S_CHECK(c->finalized, "context not finalized");
+  S2S_CHECK(c->ws.base && B <= c->cap_B && L <= c->cap_L && B > 0 && L > 0,
+            "workspace too small: call s2s_reserve(B, L, ...) first");
+}
+
+// EmbeddingModule.forward + mask multiply
+void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, const float* fixed, const float* sc_ca,
+              const float* rmask, float* node_out, bf16* z_out, cudaStream_t st) {
+  const int R = B * L;
+  node_features(t, ridx, fixed, c->tfreq, c->pdenom, c->feat65, c->tf33, B, L, st);
+  const std::string ne = "embedder.node_embed.", ee = "embedder.edge_embed.";
+  linear(c, c->feat65, 65, c->P(ne + "0.weight"), 65, c->P(ne + "0.bias"), c->a256, 256, R, 256, 65, st, 1);
+  linear(c, c->a256, 256, c->P(ne + "2.weight"), 256, c->P(ne + "2.bias"), c->b256, 256, R, 256, 256, st, 1);
+  linear(c, c->b256, 256, c->P(ne + "4.weight"), 256, c->P(ne + "4.bias"), c->a256, 256, R, 256, 256, st);
+  layernorm(c->a256, nullptr, c->P(ne + "5.weight"), c->P(ne + "5.bias"), rmask, node_out, R, 256, st);
+  const float* W1 = c->P(ee + "0.weight");
+  linear(c, c->tf33, 33, W1, 120, c->P(ee + "0.bias"), c->Ti, 128, R, 128, 33, st);
+  linear(c, c->tf33, 33, W1 + 33, 120, nullptr, c->Tj, 128, R, 128, 33, st);
+  EdgeEmbedArgs a;
+  a.B = B; a.L = L; a.d_min = c->d_min;
+  a.Ti = c->Ti; a.Tj = c->Tj; a.Tpos = c->Tpos; a.Wd = c->ee_Wd; a.bin_lower = c->bin_lower;
+  a.sc_ca = sc_ca; a.ridx = ridx; a.mask = rmask;
+  a.W2 = c->ee_W2; a.W3 = c->ee_W3; a.W2t = c->ee_W2t; a.W3t = c->ee_W3t;
+  a.b2 = c->P(ee + "2.bias"); a.b3 = c->P(ee + "4.bias"); a.ln_w = c->P(ee + "5.weight"); a.ln_b = c->P(ee + "5.bias");
+  a.z_out = z_out;
+  if (c->opt_pair == 1) edge_embed_tc(a, st); else edge_embed_simt(a, st);
+}
+
+// InvariantPointAttention.forward of block blk -> out (linear_out result; not yet masked)
+void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z, const float* quat, const float* trans,
+            const float* rmask, float* out, const float* res, const float* row_post, cudaStream_t st) {
+  const int R = B * L;
+  const IpaW& w = c->ipa[blk];
+  const std::string ip = "translator.trunk.ipa_" + std::to_string(blk) + ".";
+  linear(c, node, 256, w.proj_w, 256, w.proj_b, c->proj, 6816, R, 6816, 256, st);
+  ipa_points(c->proj + 6144, 6816, c->proj + 6336, 6816, quat, trans, c->q_pts, c->k_pts, c->v_pts, R, st);
+  {  // S = sqrt(1/(3*256)) q.k     (ipa.py:183-187)
+    GemmArgs g;
+    g.A = c->proj; g.lda = 6816; g.sAb = (long)L * 6816; g.sAh = 256;
+    g.B = c->proj + 2048; g.ldb = 6816; g.sBb = (long)L * 6816; g.sBh = 512;
+    g.C = c->S; g.ldc = L; g.sCb = (long)N_H * L * L; g.sCh = (long)L * L;
+    g.M = L; g.N = L; g.K = 256; g.nb = B; g.nh = N_H; g.alpha = 0.03608439182435161f;
+    gemm_f32(g, st);
+  }
+  ipa_point_logits(c->S, c->q_pts, c->k_pts, w.pt_w, B, L, st);
+  IpaPairArgs p;
+  p.B = B; p.L = L; p.z = z; p.S = c->S; p.mask = rmask;
+  p.Wb_hi = w.Wb_hi; p.Wb_lo = w.Wb_lo; p.bb = c->P(ip + "linear_b.bias");
+  p.Wdz_t = w.Wdz_t; p.bdz = c->P(ip + "down_z.bias");
+  p.o_pair = c->feats + (N_H * C_H + 4 * N_H * P_V); p.ld_opair = IPA_FEAT;
+  ipa_pair_attention(p, st);
+  {  // o = P v  -> feats[:, h*256 + c]
+    GemmArgs g;
+    g.A = c->S; g.lda = L; g.sAb = (long)N_H * L * L; g.sAh = (long)L * L;
+    g.B = c->proj + 2048 + 256; g.ldb = 6816; g.sBb = (long)L * 6816; g.sBh = 512; g.b_kn = 1;
+    g.C = c->feats; g.ldc = IPA_FEAT; g.sCb = (long)L * IPA_FEAT; g.sCh = 256;
+    g.M = L; g.N = 256; g.K = L; g.nb = B; g.nh = N_H;
+    gemm_f32(g, st);
+    // o_pt (global frame) = P v_pts
+    g.B = c->v_pts; g.ldb = N_H * P_V * 3; g.sBb = (long)L * N_H * P_V * 3; g.sBh = P_V * 3;
+    g.C = c->opt; g.ldc = N_H * P_V * 3; g.sCb = (long)L * N_H * P_V * 3; g.sCh = P_V * 3;
+    g.N = P_V * 3;
+    gemm_f32(g, st);
+  }
+  ipa_finalize_points(c->opt, quat, trans, c->feats, R, st);
+  linear(c, c->feats, IPA_FEAT, c->P(ip + "linear_out.weight"), IPA_FEAT, c->P(ip + "linear_out.bias"), out, 256, R, 256,
+         IPA_FEAT, st, 0, res, 256, nullptr, row_post);
+}
+
+void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z_in, const float* rmask,
+                        bf16* z_out, cudaStream_t st) {
+  const int R = B * L;
+  const std::string e = "translator.trunk.edge_transition_" + std::to_string(blk) + ".";
+  const float *W1 = c->P(e + "trunk.0.weight"), *Wf = c->P(e + "final_layer.weight");
+  linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st);
+  linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st);
+  linear(c, c->nprime, 128, W1 + 256, 384, nullptr, c->v384, 384, R, 384, 128, st);
+  linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st);
+  linear(c, c->nprime, 128, Wf + 256, 384, nullptr, c->q128, 128, R, 128, 128, st);
+  EdgeTransitionArgs a;
+  a.B = B; a.L = L; a.z_in = z_in; a.u = c->u384; a.v = c->v384; a.p = c->p128; a.q = c->q128; a.mask = rmask;
+  const EtW& w = c->et[blk];
+  a.W1z = w.W1z; a.W2 = w.W2; a.Wfh = w.Wfh; a.Wfz = w.Wfz;
+  a.W1zt = w.W1zt; a.W2t = w.W2t; a.Wft = w.Wft; a.Wfzt = w.Wfzt;
+  a.b2 = c->P(e + "trunk.2.bias"); a.ln_w = c->P(e + "layer_norm.weight"); a.ln_b = c->P(e + "layer_norm.bias");
+  a.z_out = z_out;
+  if (c->opt_pair == 1) edge_transition_tc(a, st); else edge_transition_simt(a, st);
+}
+
+void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {
+  const int R = B * L;
+  linear(c, c->x320, 320, c->P(tl + "self_attn.in_proj_weight"), 320, c->P(tl + "self_attn.in_proj_bias"), c->qkv, 960, R, 960, 320, st);
+  GemmArgs g;
+  g.A = c->qkv; g.lda = 960; g.sAb = (long)L * 960; g.sAh = TFM_HD;
+  g.B = c->qkv + 320; g.ldb = 960; g.sBb = (long)L * 960; g.sBh = TFM_HD;
+  g.C = c->S; g.ldc = L; g.sCb = (long)TFM_H * L * L; g.sCh = (long)L * L;
+  g.M = L; g.N = L; g.K = TFM_HD; g.nb = B; g.nh = TFM_H; g.alpha = 0.11180339887498948f;  // 1/sqrt(80)
+  gemm_f32(g, st);
+  softmax_keybias(c->S, c->keybias, B, TFM_H, L, st);
+  GemmArgs h;
+  h.A = c->S; h.lda = L; h.sAb = (long)TFM_H * L * L; h.sAh = (long)L * L;
+  h.B = c->qkv + 640; h.ldb = 960; h.sBb = (long)L * 960; h.sBh = TFM_HD; h.b_kn = 1;
+  h.C = c->y320; h.ldc = 320; h.sCb = (long)L * 320; h.sCh = TFM_HD;
+  h.M = L; h.N = TFM_HD; h.K = L; h.nb = B; h.nh = TFM_H;
+  gemm_f32(h, st);
+  linear(c, c->y320, 320, c->P(tl + "self_attn.out_proj.weight"), 320, c->P(tl + "self_attn.out_proj.bias"), c->t320, 320, R, 320, 320, st, 0, c->x320, 320);
+  layernorm(c->t320, nullptr, c->P(tl + "norm1.weight"), c->P(tl + "norm1.bias"), nullptr, c->x320, R, 320, st);
+  linear(c, c->x320, 320, c->P(tl + "linear1.weight"), 320, c->P(tl + "linear1.bias"), c->t320, 320, R, 320, 320, st, 1);
+  linear(c, c->t320, 320, c->P(tl + "linear2.weight"), 320, c->P(tl + "linear2.bias"), c->y320, 320, R, 320, 320, st, 0, c->x320, 320);
+  layernorm(c->y320, nullptr, c->P(tl + "norm2.weight"), c->P(tl + "norm2.bias"), nullptr, c->x320, R, 320, st);
+}
+
+// TranslationIPA.forward (ipa.py:331-387) on the node / pair embeddings already in c->node / c->z
+void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmask, const float* fixed,
+              const float* gt_psi, float* out_rigids, float* out_psi, cudaStream_t st) {
+  const int R = B * L;
+  const std::string tk = "translator.trunk.";
+  make_masks(rmask, fixed, c->diffuse, c->keybias, R, st);
+  S2S_CUDA(cudaMemcpyAsync(c->init_node, c->node, (size_t)R * 256 * 4, cudaMemcpyDeviceToDevice, st));
+  split_rigids(rigids_t, c->quat, c->trans, R, st);
+  for (int b = 0; b < N_BLK; ++b) {
+    const std::string s = std::to_string(b);
+    // node = LN(node + ipa(node, z, T) * mask)          (ipa.py:344-351)
+    do_ipa(c, b, B, L, c->node, c->z, c->quat, c->trans, rmask, c->a256, c->node, rmask, st);
+    layernorm(c->a256, nullptr, c->P(tk + "ipa_ln_" + s + ".weight"), c->P(tk + "ipa_ln_" + s + ".bias"), nullptr, c->node, R, 256, st);
+    // sequence transformer on [node | skip(init_node)]   (ipa.py:353-360)
+    linear(c, c->init_node, 256, c->P(tk + "skip_embed_" + s + ".weight"), 256, c->P(tk + "skip_embed_" + s + ".bias"), c->skip64, 64, R, 64, 256, st);
+    concat_skip(c->node, c->skip64, c->x320, R, st);
+    for (int l = 0; l < 2; ++l) do_transformer_layer(c, tk + "transformer_" + s + ".layers." + std::to_string(l) + ".", B, L, st);
+    linear(c, c->x320, 320, c->P(tk + "linear_" + s + ".weight"), 320, c->P(tk + "linear_" + s + ".bias"), c->node, 256, R, 256, 320, st, 0, c->node, 256);
+    // node transition + mask                              (layers.py:138-145, ipa.py:363-365)
+    const std::string nt = tk + "node_transition_" + s + ".";
+    linear(c, c->node, 256, c->P(nt + "linear_1.weight"), 256, c->P(nt + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1);
+    linear(c, c->a256, 256, c->P(nt + "linear_2.weight"), 256, c->P(nt + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 1);
+    linear(c, c->b256, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), c->a256, 256, R, 256, 256, st, 0, c->node, 256);
+    layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, R, 256, st);
+    // backbone update on node * diffuse_mask, exact fp32    (ipa.py:367-369)
+    linear(c, c->node, 256, c->P(tk + "bb_update_" + s + ".linear.weight"), 256, c->P(tk + "bb_update_" + s + ".linear.bias"), c->upd6, 6, R, 6, 256, st, 0, nullptr, 0, c->diffuse);
+    frame_update(c->quat, c->trans, c->upd6, c->diffuse, R, st);
+    if (b < N_BLK - 1) do_edge_transition(c, b, B, L, c->node, c->z, rmask, c->z, st);
+  }
+  const std::string tp = "translator.torsion_pred.";
+  linear(c, c->node, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1);
+  linear(c, c->a256, 256, c->P(tp + "linear_2.weight"), 256, c->P(tp + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 0, c->node, 256);
+  linear(c, c->b256, 256, c->P(tp + "linear_final.weight"), 256, c->P(tp + "linear_final.bias"), c->psi_u, 2, R, 2, 256, st);
+  psi_finalize(c->psi_u, gt_psi, fixed, out_psi, R, st);
+  join_rigids(c->quat, c->trans, out_rigids, R, st);
+}
+
+void do_forward(s2s_ctx* c, int B, int L, const float* rigids_t, const float* sc_ca, const float* t,
+                const long long* ridx, const float* rmask, const float* fixed, const float* gt_psi, float* out_rigids,
+                float* out_psi, cudaStream_t st) {
+  check_shape(c, B, L);
+  do_embed(c, B, L, t, ridx, fixed, sc_ca, rmask, c->node, c->z, st);
+  do_trunk(c, B, L, rigids_t, rmask, fixed, gt_psi, out_rigids, out_psi, st);
+}
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int s2s_abi_version(void) { return S2S_ABI_VERSION; }
+const char* s2s_last_error(void) { return g_error.c_str(); }
+int64_t s2s_launch_count(void) { return g_launch_count; }
+
+s2s_ctx* s2s_create(const float* tfreq, const float* pdenom, const float* bin_lower, const float* backbone) {
+  s2s_ctx* c = nullptr;
+  const int rc = guarded([&] {
+    S2S_CHECK(tfreq && pdenom && bin_lower && backbone, "s2s_create: null table");
+    c = new s2s_ctx();
+    auto up = [&](const float* h, size_t n) {
+      float* d;
+      S2S_CUDA(cudaMalloc(&d, n * 4));
+      S2S_CUDA(cudaMemcpy(d, h, n * 4, cudaMemcpyHostToDevice));
+      return d;
+    };
+    c->tfreq = up(tfreq, 16); c->pdenom = up(pdenom, 16); c->bin_lower = up(bin_lower, N_BINS); c->backbone = up(backbone, 21 * 33);
+  });
+  if (rc) { delete c; return nullptr; }
+  return c;
+}
+
+void s2s_destroy(s2s_ctx* c) {
+  if (!c) return;
+  c->ws.release(); c->wslab.release();
+  cudaFree(c->tfreq); cudaFree(c->pdenom); cudaFree(c->bin_lower); cudaFree(c->backbone);
+  delete c;
+}
+
+int s2s_set_param(s2s_ctx* c, const char* name, const float* data, int64_t numel) {
+  return guarded([&] {
+    S2S_CHECK(c && name && data && numel > 0, "s2s_set_param: bad argument");
+    c->params[name] = {data, numel};
+    c->finalized = false;
+  });
+}
+
+int s2s_finalize(s2s_ctx* c, void* stream) {
+  return guarded([&] { S2S_CHECK(c, "null ctx"); do_finalize(c, (cudaStream_t)stream); });
+}
+
+int s2s_set_option(s2s_ctx* c, const char* key, int value) {
+  return guarded([&] {
+    S2S_CHECK(c && key, "null argument");
+    const std::string k = key;
+    if (k == "pair_kernels") { S2S_CHECK(value == 0 || value == 1, "pair_kernels: 0|1"); c->opt_pair = value; }
+    else if (k == "node_gemm") { S2S_CHECK(value == 0 || value == 1, "node_gemm: 0|1"); c->opt_node = value; }
+    else S2S_CHECK(false, "unknown option " + k);
+  });
+}
+
+int s2s_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, void* stream) {
+  return guarded([&] { S2S_CHECK(c, "null ctx"); do_reserve(c, B, L, d_min, d_max, (cudaStream_t)stream); });
+}
+
+int s2s_net_forward(s2s_ctx* c, int B, int L, const float* rigids_t, const float* sc_ca, const float* t,
+                    const int64_t* residue_idx, const float* residue_mask, const float* fixed_mask, const float* gt_psi,
+                    float* out_rigids, float* out_psi, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && rigids_t && sc_ca && t && residue_idx && residue_mask && fixed_mask && gt_psi && out_rigids && out_psi, "s2s_net_forward: null argument");
+    do_forward(c, B, L, rigids_t, sc_ca, t, (const long long*)residue_idx, residue_mask, fixed_mask, gt_psi, out_rigids, out_psi, (cudaStream_t)stream);
+  });
+}
+
+int s2s_trunk(s2s_ctx* c, int B, int L, const float* node_embed, const void* z, const float* rigids_t,
+              const float* residue_mask, const float* fixed_mask, const float* gt_psi, float* out_rigids, float* out_psi,
+              void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && node_embed && z && rigids_t && residue_mask && fixed_mask && out_rigids && out_psi, "s2s_trunk: null argument");
+    check_shape(c, B, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t R = (size_t)B * L;
+    if (node_embed != c->node) S2S_CUDA(cudaMemcpyAsync(c->node, node_embed, R * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    if (z != (const void*)c->z) S2S_CUDA(cudaMemcpyAsync(c->z, z, R * L * C_Z * 2, cudaMemcpyDeviceToDevice, st));
+    do_trunk(c, B, L, rigids_t, residue_mask, fixed_mask, gt_psi, out_rigids, out_psi, st);
+  });
+}
+
+int s2s_embed(s2s_ctx* c, int B, int L, const float* t, const int64_t* residue_idx, const float* fixed_mask,
+              const float* sc_ca, const float* residue_mask, float* node_out, void* z_out, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && t && residue_idx && fixed_mask && sc_ca && residue_mask && node_out && z_out, "s2s_embed: null argument");
+    check_shape(c, B, L);
+    do_embed(c, B, L, t, (const long long*)residue_idx, fixed_mask, sc_ca, residue_mask, node_out, (bf16*)z_out, (cudaStream_t)stream);
+  });
+}
+
+int s2s_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const void* z, const float* quat, const float* trans_nm,
+            const float* residue_mask, float* out, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && node && z && quat && trans_nm && residue_mask && out && blk >= 0 && blk < N_BLK, "s2s_ipa: bad argument");
+    check_shape(c, B, L);
+    do_ipa(c, blk, B, L, node, (const bf16*)z, quat, trans_nm, residue_mask, out, nullptr, nullptr, (cudaStream_t)stream);
+  });
+}
+
+int s2s_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, const void* z_in, const float* residue_mask,
+                        void* z_out, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && node && z_in && residue_mask && z_out && blk >= 0 && blk < N_BLK - 1, "s2s_edge_transition: bad argument");
+    check_shape(c, B, L);
+    do_edge_transition(c, blk, B, L, node, (const bf16*)z_in, residue_mask, (bf16*)z_out, (cudaStream_t)stream);
+  });
+}
+
+int s2s_se3_step(int B, int L, const float* rigids_t, const float* rigids_0, const float* residue_mask,
+                 const float* diffuse_mask, const float* sched_f, const double* sched_d, const float* rot_noise,
+                 const float* trans_noise, float noise_scale, int probability_flow, int mode, double* rot_score,
+                 double* trans_score, float* rigids_out, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(B > 0 && L > 0 && rigids_t && residue_mask && sched_f && sched_d, "s2s_se3_step: bad argument");
+    S2S_CHECK(mode == 2 || rigids_0, "s2s_se3_step: rigids_0 required");
+    S2S_CHECK(mode == 1 || rigids_out, "s2s_se3_step: rigids_out required");
+    S2S_CHECK(mode == 0 || (rot_score && trans_score), "s2s_se3_step: score buffers required");
+    S2S_CHECK((rot_score == nullptr) == (trans_score == nullptr), "s2s_se3_step: pass both score buffers or none");
+    Se3StepArgs a;
+    a.B = B; a.L = L; a.rig_t = rigids_t; a.rig_0 = rigids_0; a.mask = residue_mask; a.diffuse = diffuse_mask;
+    a.sched_f = sched_f; a.sched_d = sched_d; a.rot_noise = rot_noise; a.trans_noise = trans_noise;
+    a.noise_scale = noise_scale; a.probability_flow = probability_flow; a.mode = mode;
+    a.rot_score = rot_score; a.trans_score = trans_score; a.rig_out = rigids_out;
+    se3_step(a, (cudaStream_t)stream);
+  });
+}
+
+int s2s_se3_perturb(int B, int L, const float* rot0, const float* trans0, const float* diffuse_mask, const float* sched_f,
+                    const double* cdf, const float* omega_grid, const float* axis_noise, const float* u_noise,
+                    const float* trans_noise, float* rigids_out, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(B > 0 && L > 0 && rot0 && trans0 && sched_f && cdf && omega_grid && axis_noise && u_noise && trans_noise && rigids_out, "s2s_se3_perturb: bad argument");
+    Se3PerturbArgs a;
+    a.B = B; a.L = L; a.rot0 = rot0; a.trans0 = trans0; a.diffuse = diffuse_mask; a.sched_f = sched_f; a.cdf = cdf;
+    a.omega_grid = omega_grid; a.axis_noise = axis_noise; a.u_noise = u_noise; a.trans_noise = trans_noise; a.rig_out = rigids_out;
+    se3_perturb(a, (cudaStream_t)stream);
+  });
+}
+
+int s2s_backbone_atoms(s2s_ctx* c, int rows, const float* rigids, const float* psi, const int64_t* aatype, float* atom37,
+                       float* atom14, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && rows > 0 && rigids && psi && atom37, "s2s_backbone_atoms: bad argument");
+    backbone_atoms(rigids, psi, (const long long*)aatype, c->backbone, atom37, atom14, rows, (cudaStream_t)stream);
+  });
+}
+
+int s2s_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(A && W && C, "s2s_linear_f32: null argument");
+    GemmArgs g;
+    g.A = A; g.lda = K; g.B = W; g.ldb = K; g.C = C; g.ldc = N; g.bias = bias; g.M = M; g.N = N; g.K = K; g.relu = relu;
+    gemm_f32(g, (cudaStream_t)stream);
+  });
+}
+
+}  // extern "C"

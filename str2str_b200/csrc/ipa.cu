@@ -1,0 +1,283 @@
+// Invariant Point Attention kernels (reference src/models/net/ipa.py:100-268).
+//
+// The pair tensor z[b,i,:,:] (L x 128 bf16) is read from HBM exactly once per IPA call, by
+// ipa_pair_attention_kernel: one CTA per (decoy, query residue) stages the slab in shared memory and uses it
+// for BOTH the pair bias (linear_b, before the softmax) and the pair value aggregation (down_z, after it).
+// The q.k logits and the point term arrive in S (written by a batched GEMM + ipa_point_logits); the
+// attention weights go back into S for the P*V / P*V_pts products.
+#include "s2s_internal.cuh"
+
+namespace s2s {
+
+namespace {
+
+// raw point projections -> global-frame points (ipa.py:144-171): x|y|z chunk layout, R p + t (t in nm)
+__global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict__ qp, long ld_q,
+                                                         const float* __restrict__ kvp, long ld_kv,
+                                                         const float* __restrict__ quat,
+                                                         const float* __restrict__ trans, float* __restrict__ q_pts,
+                                                         float* __restrict__ k_pts, float* __restrict__ v_pts,
+                                                         int rows) {
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (r >= rows) return;
+  float q[4] = {quat[r * 4], quat[r * 4 + 1], quat[r * 4 + 2], quat[r * 4 + 3]};
+  float R[9];
+  quat_to_rot(q, R);
+  const float tx = trans[r * 3], ty = trans[r * 3 + 1], tz = trans[r * 3 + 2];
+  constexpr int NQ = N_H * P_Q, NKV = N_H * (P_Q + P_V);
+  if (tid >= NQ + NKV) return;
+  float x, y, z;
+  float* dst;
+  if (tid < NQ) {
+    x = qp[r * ld_q + tid];
+    y = qp[r * ld_q + NQ + tid];
+    z = qp[r * ld_q + 2 * NQ + tid];
+    dst = q_pts + ((long)r * NQ + tid) * 3;
+  } else {
+    const int k = tid - NQ, h = k / (P_Q + P_V), p = k % (P_Q + P_V);
+    x = kvp[r * ld_kv + k];
+    y = kvp[r * ld_kv + NKV + k];
+    z = kvp[r * ld_kv + 2 * NKV + k];
+    dst = p < P_Q ? k_pts + (((long)r * N_H + h) * P_Q + p) * 3 : v_pts + (((long)r * N_H + h) * P_V + (p - P_Q)) * 3;
+  }
+  dst[0] = R[0] * x + R[1] * y + R[2] * z + tx;
+  dst[1] = R[3] * x + R[4] * y + R[5] * z + ty;
+  dst[2] = R[6] * x + R[7] * y + R[8] * z + tz;
+}
+
+// S[b,h,i,j] += -0.5 * w_h * sum_p |q_pts[b,i,h,p] - k_pts[b,j,h,p]|^2      (ipa.py:191-205)
+// Direct differences in fp32: the |q|^2+|k|^2-2q.k expansion cancels catastrophically for nm-scale coordinates.
+__global__ void __launch_bounds__(256) ipa_point_logits_kernel(float* __restrict__ S, const float* __restrict__ q_pts,
+                                                               const float* __restrict__ k_pts,
+                                                               const float* __restrict__ pt_w, int L) {
+  __shared__ float qs[8][P_Q * 3];
+  __shared__ float ks[32][P_Q * 3 + 1];
+  const int bh = blockIdx.z, b = bh / N_H, h = bh % N_H;
+  const int i0 = blockIdx.y * 8, j0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  if (tid < 8 * 24) {
+    const int il = tid / 24, c = tid % 24;
+    qs[il][c] = (i0 + il < L) ? q_pts[(((long)b * L + i0 + il) * N_H + h) * 24 + c] : 0.f;
+  }
+  for (int idx = tid; idx < 32 * 24; idx += 256) {
+    const int jl = idx / 24, c = idx % 24;
+    ks[jl][c] = (j0 + jl < L) ? k_pts[(((long)b * L + j0 + jl) * N_H + h) * 24 + c] : 0.f;
+  }
+  __syncthreads();
+  const int il = tid / 32, jl = tid % 32;
+  const int i = i0 + il, j = j0 + jl;
+  if (i >= L || j >= L) return;
+  const float w = pt_w[h];
+  float acc = 0.f;
+#pragma unroll
+  for (int p = 0; p < P_Q; ++p) {
+    const float dx = qs[il][p * 3] - ks[jl][p * 3];
+    const float dy = qs[il][p * 3 + 1] - ks[jl][p * 3 + 1];
+    const float dz = qs[il][p * 3 + 2] - ks[jl][p * 3 + 2];
+    acc += (dx * dx + dy * dy + dz * dz) * w;
+  }
+  S[(((long)b * N_H + h) * L + i) * L + j] += acc * (-0.5f);
+}
+
+// ---- the pair kernel ----------------------------------------------------------------------------------
+constexpr int ZP = C_Z + 8;  // padded bf16 row pitch (272 B): conflict-free ldmatrix
+
+__global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int L = a.L, Lp = (L + 15) & ~15;
+  const int LP4 = Lp + 4, LP8 = Lp + 8;
+  bf16* z_s = reinterpret_cast<bf16*>(smem_raw);                      // [Lp][ZP]
+  float* P_s = reinterpret_cast<float*>(z_s + (size_t)Lp * ZP);        // [8][LP4] logits -> probabilities
+  bf16* Ph = reinterpret_cast<bf16*>(P_s + 8 * LP4);                   // [8][LP8] bf16 hi part of P
+  bf16* Pl = Ph + 8 * LP8;                                             // [8][LP8] bf16 lo part of P
+  float* zsum = reinterpret_cast<float*>(Pl + 8 * LP8);                // [8][C_Z+4]  sum_j P[h][j] z[j][:]
+
+  const int b = blockIdx.x / L, i = blockIdx.x % L;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int g = lane / 4, t = lane % 4;
+
+  // ---- stage the z slab (one HBM read of z per IPA call) and the logits row block ----------------------
+  const bf16* zg = a.z + ((long)b * L + i) * L * C_Z;
+  for (int idx = tid; idx < L * (C_Z / 8); idx += 256) {
+    const int j = idx / (C_Z / 8), c8 = idx % (C_Z / 8);
+    cp_async16(z_s + j * ZP + c8 * 8, zg + (long)j * C_Z + c8 * 8);
+  }
+  cp_async_commit();
+  for (int idx = tid; idx < (Lp - L) * (C_Z / 8); idx += 256) {
+    const int j = L + idx / (C_Z / 8), c8 = idx % (C_Z / 8);
+    *reinterpret_cast<uint4*>(z_s + j * ZP + c8 * 8) = make_uint4(0, 0, 0, 0);
+  }
+  {
+    const float* Srow = a.S + (((long)b * N_H + warp) * L + i) * L;
+    for (int j = lane; j < Lp; j += 32) P_s[warp * LP4 + j] = j < L ? Srow[j] : 0.f;
+  }
+  // linear_b weight fragments (B operand: k = channel, n = head), hi and lo bf16 terms
+  uint32_t wbh[8][2], wbl[8][2];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const int k0 = ks * 16 + 2 * t;
+    wbh[ks][0] = *reinterpret_cast<const uint32_t*>(a.Wb_hi + g * C_Z + k0);
+    wbh[ks][1] = *reinterpret_cast<const uint32_t*>(a.Wb_hi + g * C_Z + k0 + 8);
+    wbl[ks][0] = *reinterpret_cast<const uint32_t*>(a.Wb_lo + g * C_Z + k0);
+    wbl[ks][1] = *reinterpret_cast<const uint32_t*>(a.Wb_lo + g * C_Z + k0 + 8);
+  }
+  const float m_i = a.mask[(long)b * L + i];
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- pair bias: [16 keys x 128] x [128 x 8 heads] per m-tile, added into the logits ------------------
+  constexpr float SQRT1_3 = 0.57735026918962576f;
+  for (int mt = warp; mt < Lp / 16; mt += 8) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    const bf16* arow = z_s + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ZP + (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t af[4];
+      ldmatrix_x4(af, arow + ks * 16);
+      mma_bf16_16816(d, af, wbh[ks]);
+      mma_bf16_16816(d, af, wbl[ks]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int h = 2 * t + (e & 1);
+      const int j = mt * 16 + g + (e >> 1) * 8;
+      if (j < L) {
+        const float m_j = a.mask[(long)b * L + j];
+        P_s[h * LP4 + j] += SQRT1_3 * (d[e] + a.bb[h]) + 1e5f * (m_i * m_j - 1.f);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax over keys, one warp per head -------------------------------------------------------------
+  {
+    float* row = P_s + warp * LP4;
+    float mx = -INFINITY;
+    for (int j = lane; j < L; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      const float e = __expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+    const float inv = 1.f / warp_sum(sum);
+    float* Srow = a.S + (((long)b * N_H + warp) * L + i) * L;
+    for (int j = lane; j < Lp; j += 32) {
+      const float pv = j < L ? row[j] * inv : 0.f;
+      if (j < L) Srow[j] = pv;
+      const bf16 hi = __float2bfloat16_rn(pv);
+      Ph[warp * LP8 + j] = hi;
+      Pl[warp * LP8 + j] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+    }
+  }
+  __syncthreads();
+
+  // ---- zsum^T[c][h] = sum_j z[j][c] P[h][j] : warp w owns channels 16w..16w+15 --------------------------
+  {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    const bf16* arow = z_s + ((lane >> 4) * 8 + (lane & 7)) * ZP + warp * 16 + ((lane >> 3) & 1) * 8;
+    const bf16* ph = Ph + g * LP8 + 2 * t;
+    const bf16* pl = Pl + g * LP8 + 2 * t;
+    for (int ks = 0; ks < Lp / 16; ++ks) {
+      uint32_t af[4], bh[2], bl[2];
+      ldmatrix_x4_trans(af, arow + (size_t)ks * 16 * ZP);
+      bh[0] = *reinterpret_cast<const uint32_t*>(ph + ks * 16);
+      bh[1] = *reinterpret_cast<const uint32_t*>(ph + ks * 16 + 8);
+      bl[0] = *reinterpret_cast<const uint32_t*>(pl + ks * 16);
+      bl[1] = *reinterpret_cast<const uint32_t*>(pl + ks * 16 + 8);
+      mma_bf16_16816(d, af, bh);
+      mma_bf16_16816(d, af, bl);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int h = 2 * t + (e & 1);
+      const int c = warp * 16 + g + (e >> 1) * 8;
+      zsum[h * (C_Z + 4) + c] = d[e];
+    }
+  }
+  __syncthreads();
+
+  // ---- o_pair[h][d] = down_z(zsum[h]) (sum_j P = 1, so the bias passes through; ipa.py:253-254) ---------
+  {
+    const int h = tid / 32, dd = tid % 32;
+    float acc = a.bdz[dd];
+    const float* zs = zsum + h * (C_Z + 4);
+#pragma unroll 8
+    for (int c = 0; c < C_Z; ++c) acc = fmaf(a.Wdz_t[c * 32 + dd], zs[c], acc);
+    a.o_pair[((long)b * L + i) * a.ld_opair + h * 32 + dd] = acc;
+  }
+}
+
+// o_pt (global frame, [rows][H][P_V][3]) -> local frame, norms -> feature columns (ipa.py:229-248,259)
+__global__ void __launch_bounds__(96) ipa_finalize_points_kernel(const float* __restrict__ opt,
+                                                                  const float* __restrict__ quat,
+                                                                  const float* __restrict__ trans,
+                                                                  float* __restrict__ feats, int rows) {
+  const int r = blockIdx.x, k = threadIdx.x;  // k = h*12 + p
+  if (r >= rows) return;
+  float q[4] = {quat[r * 4], quat[r * 4 + 1], quat[r * 4 + 2], quat[r * 4 + 3]};
+  float R[9];
+  quat_to_rot(q, R);
+  const float* o = opt + ((long)r * N_H * P_V + k) * 3;
+  const float x = o[0] - trans[r * 3], y = o[1] - trans[r * 3 + 1], z = o[2] - trans[r * 3 + 2];
+  const float lx = R[0] * x + R[3] * y + R[6] * z;
+  const float ly = R[1] * x + R[4] * y + R[7] * z;
+  const float lz = R[2] * x + R[5] * y + R[8] * z;
+  float* f = feats + (long)r * IPA_FEAT + N_H * C_H;
+  constexpr int NP = N_H * P_V;
+  f[k] = lx;
+  f[NP + k] = ly;
+  f[2 * NP + k] = lz;
+  f[3 * NP + k] = sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f);
+}
+
+__global__ void softplus_point_weights_kernel(const float* __restrict__ hw, float* __restrict__ out) {
+  const int h = threadIdx.x;
+  if (h >= N_H) return;
+  const float x = hw[h];
+  const float sp = x > 20.f ? x : log1pf(expf(x));  // torch.nn.Softplus(beta=1, threshold=20)
+  out[h] = sp * 0.09622504486493763f;               // sqrt(1 / (3 * (8 * 9 / 2)))  (ipa.py:198-200)
+}
+
+}  // namespace
+
+void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv, const float* quat,
+                const float* trans, float* q_pts, float* k_pts, float* v_pts, int rows, cudaStream_t st) {
+  ipa_points_kernel<<<rows, 256, 0, st>>>(qp_raw, ld_q, kvp_raw, ld_kv, quat, trans, q_pts, k_pts, v_pts, rows);
+  S2S_LAUNCH_CHECK();
+}
+
+void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const float* pt_w, int B, int L,
+                      cudaStream_t st) {
+  dim3 grid(ceil_div(L, 32), ceil_div(L, 8), B * N_H);
+  ipa_point_logits_kernel<<<grid, 256, 0, st>>>(S, q_pts, k_pts, pt_w, L);
+  S2S_LAUNCH_CHECK();
+}
+
+void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st) {
+  const int Lp = (a.L + 15) & ~15;
+  const size_t smem = (size_t)Lp * ZP * 2 + 8 * (Lp + 4) * 4 + 2 * 8 * (Lp + 8) * 2 + 8 * (C_Z + 4) * 4;
+  S2S_CHECK(smem <= 227 * 1024, "ipa_pair_attention: chain too long for one shared-memory slab (L <= 768)");
+  static size_t configured = 0;
+  if (smem > configured) {
+    S2S_CUDA(cudaFuncSetAttribute(ipa_pair_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ipa_pair_attention_kernel<<<a.B * a.L, 256, smem, st>>>(a);
+  S2S_LAUNCH_CHECK();
+}
+
+void ipa_finalize_points(const float* opt_glob, const float* quat, const float* trans, float* feats, int rows,
+                         cudaStream_t st) {
+  ipa_finalize_points_kernel<<<rows, 96, 0, st>>>(opt_glob, quat, trans, feats, rows);
+  S2S_LAUNCH_CHECK();
+}
+
+void softplus_point_weights(const float* head_w, float* pt_w, cudaStream_t st) {
+  softplus_point_weights_kernel<<<1, 32, 0, st>>>(head_w, pt_w);
+  S2S_LAUNCH_CHECK();
+}
+
+}  // namespace s2s

@@ -1,0 +1,199 @@
+// Row-wise kernels of the node track: LayerNorm(+residual,+mask), key-biased softmax, input features,
+// psi head normalisation.  One warp per row; rows are 128..512 floats so everything stays in registers.
+#include "s2s_internal.cuh"
+
+namespace s2s {
+
+namespace {
+
+// y[r] = LN(x[r] (+ res[r])) * w + b, then * rowscale[r]
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        const float* __restrict__ rowscale, float* __restrict__ y,
+                                                        int rows) {
+  constexpr int PER = D / 32;
+  const int row = blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = x[(long)row * D + c];
+    if (res) v[i] += res[(long)row * D + c];
+    s += v[i];
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+  const float sc = rowscale ? rowscale[row] : 1.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    y[(long)row * D + c] = ((v[i] - mean) * rstd * w[c] + b[c]) * sc;
+  }
+}
+
+// in-place softmax over the last dim of S[nb][nh][L][L] with an additive per-key bias keybias[b][j]
+__global__ void __launch_bounds__(256) softmax_keybias_kernel(float* __restrict__ S, const float* __restrict__ keybias,
+                                                              int L, int rows_per_batch, long rows) {
+  const long row = (long)blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const int b = (int)(row / rows_per_batch);
+  float* p = S + row * L;
+  const float* kb = keybias ? keybias + (long)b * L : nullptr;
+  float mx = -INFINITY;
+  for (int j = lane; j < L; j += 32) {
+    float v = p[j] + (kb ? kb[j] : 0.f);
+    p[j] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    float e = __expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+  const float inv = 1.f / warp_sum(sum);
+  for (int j = lane; j < L; j += 32) p[j] *= inv;
+}
+
+// node features [B*L][65] = [sin(1e4 t f_k) (16) | cos (16) | fixed | sin(idx*pi/d_k) (16) | cos (16)]
+// and the 33-wide per-residue time feature tf [B*L][33] used by the pair embedder.
+// (reference src/models/net/denoising_ipa.py:13-46,126-146). freq/denom tables come from the host so the
+// sin/cos arguments are bit-identical to the reference's fp32 tensors.
+__global__ void node_features_kernel(const float* __restrict__ t, const long long* __restrict__ ridx,
+                                     const float* __restrict__ fixed, const float* __restrict__ tfreq,
+                                     const float* __restrict__ pdenom, float* __restrict__ feat,
+                                     float* __restrict__ tf, int B, int L) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B * L) return;
+  const int b = r / L;
+  const float ts = t[b] * 10000.f;
+  float* f = feat + (long)r * 65;
+  float* g = tf + (long)r * 33;
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const float a = ts * tfreq[k];
+    const float s = sinf(a), c = cosf(a);
+    f[k] = s;
+    f[16 + k] = c;
+    g[k] = s;
+    g[16 + k] = c;
+  }
+  f[32] = fixed[r];
+  g[32] = fixed[r];
+  const float p = (float)ridx[r] * 3.14159274101257324f;
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const float a = __fdiv_rn(p, pdenom[k]);
+    f[33 + k] = sinf(a);
+    f[49 + k] = cosf(a);
+  }
+}
+
+// relative-position feature rows for offsets d_min .. d_min+n-1 : [n][32]
+__global__ void relpos_features_kernel(const float* __restrict__ pdenom, float* __restrict__ out, int d_min, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float p = (float)(d_min + r) * 3.14159274101257324f;
+  for (int k = 0; k < 16; ++k) {
+    const float a = __fdiv_rn(p, pdenom[k]);
+    out[(long)r * 32 + k] = sinf(a);
+    out[(long)r * 32 + 16 + k] = cosf(a);
+  }
+}
+
+// psi = u / sqrt(max(|u|^2, 1e-8)); then mixed with the ground-truth psi on fixed residues
+// (layers.py:205-213, denoising_ipa.py:192-194)
+__global__ void psi_finalize_kernel(const float* __restrict__ u, const float* __restrict__ gt_psi,
+                                    const float* __restrict__ fixed, float* __restrict__ psi, int rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float a = u[2 * r], b = u[2 * r + 1];
+  const float inv = 1.f / sqrtf(fmaxf(a * a + b * b, 1e-8f));
+  if (!gt_psi) {  // TranslationIPA.forward returns the raw head output (ipa.py:375)
+    psi[2 * r] = a * inv;
+    psi[2 * r + 1] = b * inv;
+    return;
+  }
+  const float fx = fixed[r];
+  psi[2 * r] = gt_psi[2 * r] * fx + a * inv * (1.f - fx);
+  psi[2 * r + 1] = gt_psi[2 * r + 1] * fx + b * inv * (1.f - fx);
+}
+
+__global__ void concat_skip_kernel(const float* __restrict__ node, const float* __restrict__ skip,
+                                   float* __restrict__ out, long rows) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D_TFM) return;
+  const long r = i / D_TFM;
+  const int c = (int)(i % D_TFM);
+  out[i] = c < C_S ? node[r * C_S + c] : skip[r * D_SKIP + (c - C_S)];
+}
+
+__global__ void masks_kernel(const float* __restrict__ rmask, const float* __restrict__ fixed,
+                             float* __restrict__ diffuse, float* __restrict__ keybias, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  diffuse[i] = (1.f - fixed[i]) * rmask[i];
+  keybias[i] = 1.f - rmask[i];  // float src_key_padding_mask is ADDED to the logits (ipa.py:357)
+}
+
+}  // namespace
+
+void layernorm(const float* x, const float* res, const float* w, const float* b, const float* rowscale, float* y,
+               int rows, int D, cudaStream_t st) {
+  const int grid = ceil_div(rows, 8);
+  if (D == 128)
+    layernorm_kernel<128><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows);
+  else if (D == 256)
+    layernorm_kernel<256><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows);
+  else if (D == 320)
+    layernorm_kernel<320><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows);
+  else
+    S2S_CHECK(false, "layernorm: unsupported width");
+  S2S_LAUNCH_CHECK();
+}
+
+void softmax_keybias(float* S, const float* keybias, int nb, int nh, int L, cudaStream_t st) {
+  const long rows = (long)nb * nh * L;
+  softmax_keybias_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(S, keybias, L, nh * L, rows);
+  S2S_LAUNCH_CHECK();
+}
+
+void node_features(const float* t, const long long* ridx, const float* fixed, const float* tfreq,
+                   const float* pdenom, float* feat, float* tf, int B, int L, cudaStream_t st) {
+  node_features_kernel<<<ceil_div((long)B * L, 128), 128, 0, st>>>(t, ridx, fixed, tfreq, pdenom, feat, tf, B, L);
+  S2S_LAUNCH_CHECK();
+}
+
+void relpos_features(const float* pdenom, float* out, int d_min, int n, cudaStream_t st) {
+  relpos_features_kernel<<<ceil_div(n, 128), 128, 0, st>>>(pdenom, out, d_min, n);
+  S2S_LAUNCH_CHECK();
+}
+
+void psi_finalize(const float* u, const float* gt_psi, const float* fixed, float* psi, int rows, cudaStream_t st) {
+  psi_finalize_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(u, gt_psi, fixed, psi, rows);
+  S2S_LAUNCH_CHECK();
+}
+
+void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st) {
+  concat_skip_kernel<<<ceil_div(rows * D_TFM, 256), 256, 0, st>>>(node, skip, out, rows);
+  S2S_LAUNCH_CHECK();
+}
+
+void make_masks(const float* rmask, const float* fixed, float* diffuse, float* keybias, int n, cudaStream_t st) {
+  masks_kernel<<<ceil_div(n, 256), 256, 0, st>>>(rmask, fixed, diffuse, keybias, n);
+  S2S_LAUNCH_CHECK();
+}
+
+}  // namespace s2s

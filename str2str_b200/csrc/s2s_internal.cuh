@@ -1,0 +1,147 @@
+// Internal launcher declarations shared by the .cu files (not part of the C ABI; see include/str2str_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace s2s {
+
+// ---- gemm.cu ------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A = nullptr; long lda = 0; long sAb = 0, sAh = 0;
+  const float* B = nullptr; long ldb = 0; long sBb = 0, sBh = 0;
+  float* C = nullptr;       long ldc = 0; long sCb = 0, sCh = 0;
+  const float* bias = nullptr;
+  const float* res = nullptr; long ldres = 0;  // residual shares C's batch offsets
+  const float* row_pre = nullptr;               // [M] scale on the accumulator (before bias)
+  const float* row_post = nullptr;              // [M] scale after bias/activation
+  int M = 0, N = 0, K = 0;
+  int nb = 1, nh = 1;
+  int b_kn = 0;   // 0: B is [N][K] (nn.Linear weight); 1: B is [K][N]
+  int relu = 0;
+  float alpha = 1.f;
+};
+void gemm_f32(const GemmArgs& g, cudaStream_t st);
+// tensor-core variants (gemm_tc.cu): bf16 operands, fp32 accumulate; passes = 1 (plain) or 3 (hi/lo split)
+void gemm_tc(const GemmArgs& g, int passes, cudaStream_t st);
+
+// ---- rows.cu ------------------------------------------------------------------------------------------
+void layernorm(const float* x, const float* res, const float* w, const float* b, const float* rowscale, float* y,
+               int rows, int D, cudaStream_t st);
+void softmax_keybias(float* S, const float* keybias, int nb, int nh, int L, cudaStream_t st);
+void node_features(const float* t, const long long* ridx, const float* fixed, const float* tfreq,
+                   const float* pdenom, float* feat, float* tf, int B, int L, cudaStream_t st);
+void relpos_features(const float* pdenom, float* out, int d_min, int n, cudaStream_t st);
+void psi_finalize(const float* u, const float* gt_psi, const float* fixed, float* psi, int rows, cudaStream_t st);
+void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st);
+void make_masks(const float* rmask, const float* fixed, float* diffuse, float* keybias, int n, cudaStream_t st);
+
+// ---- pair kernels -------------------------------------------------------------------------------------
+// distogram bin of |a-b| with the reference's strict inequalities (geo_utils.py:44-56); -1 = no bin
+__device__ __forceinline__ int pair_distogram_bin(const float* a, const float* b, const float* lower) {
+  const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+#pragma unroll 1
+  for (int k = N_BINS - 1; k >= 0; --k) {
+    if (d > lower[k]) {
+      const float upper = (k < N_BINS - 1) ? lower[k + 1] : 1e8f;
+      return d < upper ? k : -1;
+    }
+  }
+  return -1;
+}
+
+struct EdgeEmbedArgs {
+  int B, L, d_min;
+  const float* Ti;    // [B*L][128]  W1[:, 0:33] tf_i + b1
+  const float* Tj;    // [B*L][128]  W1[:,33:66] tf_j
+  const float* Tpos;  // [n_off][128] W1[:,66:98] pos(d_min + r)
+  const float* Wd;    // [22][128]   W1[:,98+bin]
+  const float* bin_lower;  // [22]
+  const float* sc_ca;      // [B*L][3] Angstrom
+  const long long* ridx;   // [B*L]
+  const float* mask;       // [B*L]
+  const bf16 *W2, *W3;     // [128][128] (out, in)
+  const bf16 *W2t, *W3t;   // [in][out]
+  const float *b2, *b3, *ln_w, *ln_b;
+  bf16* z_out;             // [B,L,L,128]
+};
+void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st);
+void edge_embed_tc(const EdgeEmbedArgs& a, cudaStream_t st);
+
+struct EdgeTransitionArgs {
+  int B, L;
+  const bf16* z_in;   // [B,L,L,128]
+  const float* u;     // [B*L][384] W1[:,128:256] n'_i + b1
+  const float* v;     // [B*L][384] W1[:,256:384] n'_j
+  const float* p;     // [B*L][128] Wf[:,128:256] n'_i + bf
+  const float* q;     // [B*L][128] Wf[:,256:384] n'_j
+  const float* mask;  // [B*L]
+  const bf16 *W1z, *W2, *Wfh, *Wfz;      // [384][128], [384][384], [128][384], [128][128]  (out, in)
+  const bf16 *W1zt, *W2t, *Wft, *Wfzt;   // transposed copies [in][out]
+  const float *b2, *ln_w, *ln_b;
+  bf16* z_out;        // may alias z_in
+};
+void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st);
+void edge_transition_tc(const EdgeTransitionArgs& a, cudaStream_t st);
+
+// ---- ipa.cu -------------------------------------------------------------------------------------------
+void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv, const float* quat,
+                const float* trans, float* q_pts, float* k_pts, float* v_pts, int rows, cudaStream_t st);
+void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const float* pt_w, int B, int L,
+                      cudaStream_t st);
+struct IpaPairArgs {
+  int B, L;
+  const bf16* z;       // [B,L,L,128]
+  float* S;            // [B,H,L,L]  in: scaled q.k + point term; out: attention weights
+  const float* mask;   // [B*L]
+  const bf16 *Wb_hi, *Wb_lo;  // linear_b weight split in two bf16 terms, [8][128]
+  const float* bb;     // [8]
+  const float* Wdz_t;  // down_z weight transposed, [128][32]
+  const float* bdz;    // [32]
+  float* o_pair;       // [B*L] rows, H*32 wide, row stride ld_opair
+  long ld_opair;
+};
+void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st);
+void ipa_finalize_points(const float* opt_glob, const float* quat, const float* trans, float* feats, int rows,
+                         cudaStream_t st);
+void softplus_point_weights(const float* head_w, float* pt_w, cudaStream_t st);
+
+// ---- rigid.cu -----------------------------------------------------------------------------------------
+void frame_update(float* quat, float* trans, const float* upd6, const float* diffuse, int rows, cudaStream_t st);
+void split_rigids(const float* rig7, float* quat, float* trans_nm, int rows, cudaStream_t st);
+void join_rigids(const float* quat, const float* trans_nm, float* rig7, int rows, cudaStream_t st);
+struct Se3StepArgs {
+  int B, L;
+  const float* rig_t;      // [B,L,7]
+  const float* rig_0;      // [B,L,7] predicted clean frames (needed unless scores are given)
+  const float* mask;       // [B,L] residue mask (scores are multiplied by it)
+  const float* diffuse;    // [B,L] (1-fixed)*mask; nullptr = update everything
+  const float* sched_f;    // [B][8]: t, sigma_q, g_rot, g_rot^2, exp(-beta/2), 1-exp(-beta), b_t, sqrt(b_t)
+  const double* sched_d;   // [B][2]: dt, sqrt(dt)
+  const float* rot_noise;  // [B,L,3] or nullptr (SDE only)
+  const float* trans_noise;
+  float noise_scale;
+  int probability_flow;
+  int mode;                // 0 fused score+reverse, 1 score only, 2 reverse from given scores
+  double* rot_score;       // [B,L,3] out (mode 0/1, optional) or in (mode 2)
+  double* trans_score;
+  float* rig_out;          // [B,L,7] (mode 0/2)
+};
+void se3_step(const Se3StepArgs& a, cudaStream_t st);
+struct Se3PerturbArgs {
+  int B, L;
+  const float* rot0;       // [B,L,9] rotation matrices
+  const float* trans0;     // [B,L,3] Angstrom
+  const float* diffuse;    // [B,L] or nullptr
+  const float* sched_f;    // [B][2]: exp(-beta/2), sqrt(1-exp(-beta))
+  const double* cdf;       // [B][1000] IGSO3 cdf row of each decoy's sigma bucket
+  const float* omega_grid; // [1000]
+  const float* axis_noise; // [B,L,3] N(0,1)
+  const float* u_noise;    // [B,L]   U[0,1)
+  const float* trans_noise;// [B,L,3] N(0,1)
+  float* rig_out;          // [B,L,7]
+};
+void se3_perturb(const Se3PerturbArgs& a, cudaStream_t st);
+void backbone_atoms(const float* rig7, const float* psi, const long long* aatype, const float* table,
+                    float* atom37, float* atom14, int rows, cudaStream_t st);
+
+}  // namespace s2s

@@ -1,0 +1,217 @@
+"""Forward-backward conformation sampler (reference src/models/diffusion_module.py:214-369, `predict_step`).
+
+`ForwardBackwardSampler.forward_backward(rigids_0, t_delta)` is the reference's inner closure
+(diffusion_module.py:260-334) on the native kernels: one perturbation, one self-conditioning priming forward,
+n denoising iterations (network forward + fused score/reverse step), one backbone build, one D2H copy.
+The per-iteration body is captured once in a CUDA graph and replayed; step-dependent scalars (t, sigma bucket,
+g^2, beta terms) live in small device tables refreshed by two tiny copies per step.
+
+Decoys are independent, so multi-GPU sampling shards the decoy dimension across ranks with no data-path
+collective and a single all-gather of the final coordinates (`sample_sharded`).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .net.denoising_ipa import DenoisingNet
+from .rigid import Rigid
+from .score.frame import FrameDiffuser, schedule_rows
+
+FEATURE_KEYS = ("aatype", "residue_mask", "fixed_mask", "residue_idx", "torsion_angles_sin_cos")
+
+
+@dataclass
+class InferenceConfig:
+    """`inference:` block of the reference's configs/model/diffusion.yaml:88-100 (same keys, same defaults)."""
+    delta_min: float = 0.25
+    delta_max: float = 0.70
+    delta_step: float = 0.05
+    n_replica: int = 100
+    replica_per_batch: int = 64
+    num_timesteps: int = 1000
+    noise_scale: float = 1.0
+    probability_flow: bool = True
+    self_conditioning: bool = True
+    min_t: float = 1e-2
+    output_dir: Optional[str] = None
+    backward_only: bool = False
+
+
+class ForwardBackwardSampler:
+    def __init__(self, net: DenoisingNet, diffuser: FrameDiffuser, inference: InferenceConfig, use_cuda_graph: bool = True):
+        self.net, self.diffuser, self.cfg = net, diffuser, inference
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs: Dict[tuple, tuple] = {}
+        self.launches = 0  # kernels launched by the last forward_backward (library launches; graph replays included)
+
+    # ------------------------------------------------------------------------------------------------
+    def _static_feats(self, batch: Dict[str, torch.Tensor], B: int, device):
+        """The reference repeats the single-protein features B times (diffusion_module.py:269-272)."""
+        rep = lambda v: v.repeat(B, *(1,) * (v.ndim - 1)) if v.shape[0] == 1 else v
+        f = {k: rep(batch[k]).to(device) for k in FEATURE_KEYS if k in batch}
+        s = {
+            "ridx": f["residue_idx"].contiguous(),
+            "rmask": f["residue_mask"].to(torch.float32).contiguous(),
+            "fixed": f["fixed_mask"].to(torch.float32).contiguous(),
+            "gt_psi": f["torsion_angles_sin_cos"][..., 2, :].to(torch.float32).contiguous(),
+            "aatype": f["aatype"].contiguous() if "aatype" in f else None,
+            "rmask64": f["residue_mask"],
+        }
+        s["diffuse"] = ((1 - s["fixed"]) * s["rmask"]).contiguous()
+        return s
+
+    def forward_backward(self, batch: Dict[str, torch.Tensor], rigids_0: Rigid, t_delta: float, rigids_t: torch.Tensor = None,
+                         noises=None, return_numpy: bool = True, return_rigids: bool = False):
+        """Sample `rigids_0.shape[0]` conformations.  `rigids_t` (tensor_7) optionally replaces the internal
+        perturbation (parity tests feed the reference's perturbed state); `noises[k] = (rot, trans)` injects the
+        SDE noise of iteration k."""
+        cfg = self.cfg
+        T = t_delta if t_delta > 0 else 1.0
+        B, L = rigids_0.shape
+        dev = rigids_0.device
+        n = int(float(cfg.num_timesteps) * T)
+        dt = 1.0 / n
+        ts = np.linspace(cfg.min_t, T, n)[::-1]
+        eng = self.net.native(dev)
+        s = self._static_feats(batch, B, dev)
+        eng.reserve(B, L, s["ridx"])
+        lib0 = int(eng.lib.s2s_launch_count())
+
+        if rigids_t is None:
+            if t_delta > 0:
+                rigids_t = self.diffuser.forward_marginal(rigids_0, t_delta * torch.ones(B), diffuse_mask=s["rmask64"],
+                                                          as_tensor_7=True)["rigids_t"]
+            else:
+                rigids_t = self.diffuser.sample_prior(rigids_0.shape, dev, as_tensor_7=True)["rigids_t"]
+        state = rigids_t.to(dev, torch.float32).contiguous().clone()
+
+        # device tables for all iterations (t identical across decoys, as in the reference)
+        t_all = torch.as_tensor(ts.copy(), dtype=torch.float64).to(torch.float32)  # t * ones(B) is fp32 in the reference
+        rows, _ = schedule_rows(self.diffuser.trans_diffuser, self.diffuser.rot_diffuser, t_all)
+        sched_all = rows[:, None, :].expand(n, B, 8).contiguous().to(dev)
+        t_dev_all = t_all[:, None].expand(n, B).contiguous().to(dev)
+        sched_d = torch.tensor([[dt, np.sqrt(dt)]] * B, dtype=torch.float64, device=dev)
+
+        t_cur = torch.empty(B, device=dev, dtype=torch.float32)
+        sched_cur = torch.empty(B, 8, device=dev, dtype=torch.float32)
+        sc = torch.zeros(B, L, 3, device=dev, dtype=torch.float32)
+        out7 = torch.empty(B, L, 7, device=dev, dtype=torch.float32)
+        psi = torch.empty(B, L, 2, device=dev, dtype=torch.float32)
+        sde = not cfg.probability_flow
+        rot_n = torch.empty(B, L, 3, device=dev) if sde else None
+        tr_n = torch.empty(B, L, 3, device=dev) if sde else None
+
+        def net_call():
+            eng.net_forward(state, sc, t_cur, s["ridx"], s["rmask"], s["fixed"], s["gt_psi"], out7, psi)
+
+        def step_body():
+            net_call()
+            if cfg.self_conditioning:
+                sc.copy_(out7[..., 4:])
+            self.diffuser.score_and_reverse(out7, state, s["rmask"], s["diffuse"], sched_cur, sched_d, state,
+                                            noise_scale=cfg.noise_scale, probability_flow=cfg.probability_flow,
+                                            rot_noise=rot_n, trans_noise=tr_n)
+
+        with torch.no_grad():
+            if cfg.self_conditioning:  # priming forward at ts[0] with zero self-conditioning (:294-297)
+                t_cur.copy_(t_dev_all[0])
+                net_call()
+                sc.copy_(out7[..., 4:])
+            graph, per_replay = None, 0
+            if self.use_cuda_graph and n > 2:
+                # warm-up outside capture (lazy allocations, function attributes), then capture one iteration
+                snap = (state.clone(), sc.clone())
+                t_cur.copy_(t_dev_all[0]); sched_cur.copy_(sched_all[0])
+                if sde:
+                    rot_n.normal_(); tr_n.normal_()
+                step_body()
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                c0 = int(eng.lib.s2s_launch_count())
+                with torch.cuda.graph(graph):
+                    step_body()
+                per_replay = int(eng.lib.s2s_launch_count()) - c0
+                state.copy_(snap[0]); sc.copy_(snap[1])
+            replays = 0
+            for k in range(n):
+                t_cur.copy_(t_dev_all[k])
+                last = (ts[k] == cfg.min_t)
+                if last:  # the final iterate is the network's x0 prediction itself (:304-305)
+                    net_call()
+                    break
+                sched_cur.copy_(sched_all[k])
+                if sde:
+                    if noises is not None:
+                        rot_n.copy_(noises[k][0]); tr_n.copy_(noises[k][1])
+                    else:
+                        rot_n.normal_(); tr_n.normal_()
+                if graph is not None:
+                    graph.replay()
+                    replays += 1
+                else:
+                    step_body()
+            pred = out7 if last else state
+            atom37, _ = eng.backbone_atoms(pred, psi, s["aatype"], want_atom14=False)
+        # launches recorded while capturing were not executed; each replay executes them once
+        self.launches = int(eng.lib.s2s_launch_count()) - lib0 + (replays - (1 if graph is not None else 0)) * per_replay
+        result = atom37.detach().cpu().numpy() if return_numpy else atom37
+        if return_rigids:
+            return result, pred.clone(), psi.clone()
+        return result
+
+    # ------------------------------------------------------------------------------------------------
+    def sample(self, batch: Dict[str, torch.Tensor], t_delta: float, n_replica: Optional[int] = None):
+        """All replicas of one protein at one delta, chunked by replica_per_batch (:339-352). -> [N,L,37,3] numpy."""
+        cfg = self.cfg
+        n_replica = cfg.n_replica if n_replica is None else n_replica
+        assert batch["aatype"].shape[0] == 1, "Batch size must be 1 for correct inference."
+        gt = batch["rigidgroups_gt_frames"][..., 0, :, :]
+        outs, done = [], 0
+        while done < n_replica:
+            bs = min(cfg.replica_per_batch, n_replica - done)
+            r0 = Rigid.from_tensor_4x4(gt.repeat(bs, *(1,) * (gt.ndim - 1)))
+            outs.append(self.forward_backward(batch, r0, t_delta))
+            done += bs
+        return np.concatenate(outs, axis=0)
+
+    def sample_sharded(self, batch: Dict[str, torch.Tensor], t_delta: float, n_replica: int):
+        """Decoy-sharded sampling under torch.distributed: rank r samples its contiguous share, then ONE
+        all_gather of the final atom coordinates.  Works with any backend (nccl on GPUs)."""
+        import torch.distributed as dist
+
+        world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+        share = shard_bounds(n_replica, world)
+        lo, hi = share[rank], share[rank + 1]
+        local = self.sample(batch, t_delta, hi - lo) if hi > lo else np.zeros((0,) + tuple(batch["aatype"].shape[1:]) + (37, 3), np.float32)
+        if world == 1:
+            return local
+        return all_gather_decoys(torch.as_tensor(local), share).numpy()
+
+
+def shard_bounds(n: int, world: int):
+    """Contiguous, balanced split of n decoys over `world` ranks: bounds[r] .. bounds[r+1]."""
+    base, rem = divmod(n, world)
+    b = [0]
+    for r in range(world):
+        b.append(b[-1] + base + (1 if r < rem else 0))
+    return b
+
+
+def all_gather_decoys(local: torch.Tensor, bounds):
+    """all_gather of per-rank decoy blocks with (possibly) unequal counts: pad to the max share, gather once, trim."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = [bounds[r + 1] - bounds[r] for r in range(world)]
+    mx = max(counts)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
+    pad[: counts[rank]] = local.to(dev)
+    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
+    dist.all_gather_into_tensor(out, pad)
+    out = out.view((world, mx) + tuple(local.shape[1:]))
+    return torch.cat([out[r, : counts[r]] for r in range(world)], 0).cpu()

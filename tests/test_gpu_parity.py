@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the host mirror) against the CPU oracle and the
+reference's golden vectors.  Run on the B200 box:  python -m pytest tests -m gpu
+
+Tolerances (relative L2 unless stated):
+  * fp32 node-track stages ......................... 2e-5
+  * pair tensor z (stored in bf16 by design) ....... 6e-3   (bf16 has 8 mantissa bits: 2^-9 = 2e-3 per element)
+  * network outputs / trajectories (C-alpha) ....... 1e-4   (BASELINE.json north_star)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import str2str_oracle as O
+from str2str_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+PAIR_MODES = [int(v) for v in os.environ.get("S2S_TEST_PAIR_MODES", "0,1").split(",")]
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def load(golden_dir, name):
+    return {k: torch.as_tensor(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def make_net(params, pair_kernels=1, node_gemm=0):
+    from str2str_b200.net import DenoisingNet, EmbeddingModule, TranslationIPA
+
+    net = DenoisingNet(
+        EmbeddingModule(init_embed_size=32, node_embed_size=256, edge_embed_size=128),
+        TranslationIPA(c_s=256, c_z=128, coordinate_scaling=0.1, no_ipa_blocks=4, skip_embed_size=64),
+        pair_kernels=pair_kernels, node_gemm=node_gemm,
+    )
+    net.load_state_dict(params, strict=True)
+    return net.cuda().eval()
+
+
+def make_diffuser(tmp="/tmp/str2str_b200_cache"):
+    from str2str_b200.score import FrameDiffuser, R3Diffuser, SO3Diffuser
+
+    return FrameDiffuser(R3Diffuser(0.1, 20.0, 0.1), SO3Diffuser(cache_dir=tmp), min_t=1e-2)
+
+
+def small_feats(g):
+    f = synthetic.make_features(2, 12, seed=3, n_pad=2, n_fixed=1, random_aatype=True)
+    f.update(rigids_t=g["rigids_t"], sc_ca_t=g["sc_ca_t"], t=g["t"])
+    return f
+
+
+def cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def test_linear_f32_exact():
+    from str2str_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K) in [(70, 6, 256), (33, 128, 65), (200, 256, 2688), (64, 64, 16)]:
+        A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+        Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
+        Cd = torch.empty(M, N, device="cuda")
+        _lib.check(lib.s2s_linear_f32(_lib.ptr(Ad), _lib.ptr(Wd), _lib.ptr(bd), _lib.ptr(Cd), M, N, K, 1, _lib.stream()))
+        ref = torch.relu(A.double() @ W.double().T + b.double())
+        assert rel(Cd, ref) < 2e-6
+
+
+@pytest.mark.parametrize("pair", PAIR_MODES)
+def test_embedder_vs_oracle(golden_dir, params, pair):
+    g = load(golden_dir, "net_forward_small.npz")
+    f = small_feats(g)
+    net = make_net(params, pair)
+    fc = cuda(f)
+    node, edge = net.embedder(fc["residue_idx"], fc["t"], fc["fixed_mask"], fc["sc_ca_t"])
+    node_o, edge_o = O.embedder(params, f["residue_idx"], f["t"], f["fixed_mask"].float(), f["sc_ca_t"])
+    assert rel(node, node_o) < 2e-5 and rel(node, g["node_embed"]) < 2e-5
+    assert rel(edge, edge_o) < 6e-3 and rel(edge, g["edge_embed"]) < 6e-3
+    # a wrong distogram bin or relative-position offset would shift a whole row by O(1)
+    assert float((edge.cpu() - edge_o).abs().max()) < 0.08
+
+
+def test_ipa_block_vs_oracle(golden_dir, params):
+    from str2str_b200.rigid import Rigid
+
+    g = load(golden_dir, "net_forward_small.npz")
+    f = small_feats(g)
+    net = make_net(params, 0)
+    nm = f["residue_mask"].float()
+    node = g["node_embed"] * nm[..., None]
+    edge = (g["edge_embed"] * (nm[..., None] * nm[..., None, :])[..., None]).bfloat16().float()  # what the kernel is fed
+    rig = f["rigids_t"].clone()
+    rig[..., 4:] *= 0.1
+    out = net.translator.trunk["ipa_0"](node.cuda(), edge.cuda(), Rigid.from_tensor_7(rig.cuda()), nm.cuda())
+    ref = O.ipa(params, "translator.trunk.ipa_0.", node, edge, rig[..., :4], rig[..., 4:], nm)
+    valid = nm.bool()
+    assert rel(out.cpu()[valid], ref[valid]) < 1e-4
+
+
+@pytest.mark.parametrize("pair", PAIR_MODES)
+def test_edge_transition_vs_oracle(golden_dir, params, pair):
+    g = load(golden_dir, "net_forward_small.npz")
+    f = small_feats(g)
+    net = make_net(params, pair)
+    nm = f["residue_mask"].float()
+    node = g["node_embed"] * nm[..., None]
+    edge = (g["edge_embed"] * (nm[..., None] * nm[..., None, :])[..., None]).bfloat16()
+    eng = net.native("cuda")
+    eng.reserve(2, 12, f["residue_idx"])
+    out = eng.edge_transition(0, node.cuda().contiguous(), edge.cuda().contiguous(), nm.cuda().contiguous())
+    ref = O.edge_transition(params, "translator.trunk.edge_transition_0.", node, edge.float())
+    ref = ref * (nm[..., None] * nm[..., None, :])[..., None]
+    assert rel(out.float(), ref) < 8e-3
+
+
+@pytest.mark.parametrize("pair", PAIR_MODES)
+def test_network_forward_vs_reference_golden(golden_dir, params, pair):
+    g = load(golden_dir, "net_forward_small.npz")
+    net = make_net(params, pair)
+    with torch.no_grad():
+        out = net(cuda(small_feats(g)), as_tensor_7=True)
+    valid = small_feats(g)["residue_mask"].bool()
+    assert rel(out["rigids"].cpu()[valid][:, 4:], g["out_rigids"][valid][:, 4:]) < 1e-4
+    assert rel(out["rigids"].cpu()[valid][:, :4], g["out_rigids"][valid][:, :4]) < 1e-4
+    assert rel(out["psi"].cpu()[valid], g["out_psi"][valid]) < 2e-3
+    assert rel(out["atom37"].cpu()[valid][:, :5], g["out_atom37"][valid]) < 1e-4
+    assert rel(out["atom14"].cpu()[valid][:, :5], g["out_atom14"][valid]) < 1e-4
+    assert float(out["atom37"][..., 5:, :].abs().max()) == 0.0
+
+
+def test_diffuser_vs_reference_golden(golden_dir):
+    from str2str_b200.rigid import Rigid, Rotation
+
+    g = load(golden_dir, "diffuser_steps.npz")
+    d = make_diffuser()
+    r0, rt, t, mask = g["r0"].cuda(), g["rt"].cuda(), g["t"], g["mask"].cuda()
+    sc = d.score(Rigid.from_tensor_7(r0, normalize_quats=True), Rigid.from_tensor_7(rt), t, mask)
+    assert sc["rot_score"].dtype == torch.float64
+    assert rel(sc["rot_score"], g["rot_score"]) < 5e-5
+    assert rel(sc["trans_score"], g["trans_score"]) < 1e-6
+    diffuse = ((1 - g["fixed"]) * g["mask"]).cuda()
+    ode = d.reverse(Rigid.from_tensor_7(rt), g["rot_score"].cuda(), g["trans_score"].cuda(), t, 0.02, diffuse_mask=diffuse).to_tensor_7()
+    assert rel(ode, g["ode"]) < 2e-6
+    sde = d.reverse(Rigid.from_tensor_7(rt), g["rot_score"].cuda(), g["trans_score"].cuda(), t, 0.02, diffuse_mask=diffuse,
+                    noise_scale=0.7, probability_flow=False, rot_noise=g["z_rot"].cuda(), trans_noise=g["z_tr"].cuda()).to_tensor_7()
+    assert rel(sde, g["sde"]) < 2e-6
+    rig0 = Rigid(Rotation(rot_mats=O.quat_to_rotmat(g["r0"][..., :4]).cuda()), r0[..., 4:])
+    fm = d.forward_marginal(rig0, t, diffuse_mask=diffuse, noise=(g["fm_axis"], g["fm_u"], g["fm_z"]))["rigids_t"]
+    assert rel(fm, g["fm"]) < 2e-6
+
+
+def test_sigma_buckets_bit_exact(golden_dir):
+    g = load(golden_dir, "diffuser_steps.npz")
+    d = make_diffuser()
+    idx = d.rot_diffuser.t_to_idx(torch.linspace(0.01, 1.0, 397))
+    assert torch.equal(idx, g["sigma_idx_grid"].long())
+    assert np.array_equal(d.rot_diffuser.cdf_row(500), g["cdf_row_500"].numpy())
+
+
+def _run_traj(golden_dir, params, name, pair, graph):
+    from str2str_b200.rigid import Rigid
+    from str2str_b200.sampler import ForwardBackwardSampler, InferenceConfig
+
+    g = load(golden_dir, name)
+    B, L, n, n_pad, n_fixed, seed = [int(v) for v in g["meta"]]
+    feats = synthetic.make_features(1, L, seed=seed, n_pad=n_pad, n_fixed=n_fixed, random_aatype=True)
+    net = make_net(params, pair)
+    cfg = InferenceConfig(num_timesteps=2 * n, min_t=0.01)
+    smp = ForwardBackwardSampler(net, make_diffuser(), cfg, use_cuda_graph=graph)
+    q, x = synthetic.make_backbone(L, seed=seed)
+    r0 = Rigid.from_tensor_7(torch.cat([q, x], -1)[None].repeat(B, 1, 1).cuda(), normalize_quats=True)
+    atom37, fin, psi = smp.forward_backward(cuda(feats), r0, 0.5, rigids_t=g["rigids_t"].cuda(), return_rigids=True)
+    valid = synthetic.make_features(B, L, seed=seed, n_pad=n_pad, n_fixed=n_fixed)["residue_mask"].bool()
+    ca, ca_ref = fin.cpu()[..., 4:][valid], g["final_rigids"][..., 4:][valid]
+    r = rel(ca, ca_ref)
+    print(f"{name} pair={pair} graph={graph}: C-alpha rel-L2 {r:.3e}, max|d| {float((ca - ca_ref).abs().max()):.3e} A, "
+          f"launches {smp.launches}")
+    assert r < 1e-4
+    assert rel(torch.as_tensor(atom37)[valid][:, :5], g["final_atom37"][valid]) < 1e-4
+    assert smp.launches > 0
+
+
+@pytest.mark.parametrize("pair", PAIR_MODES)
+@pytest.mark.parametrize("graph", [False, True])
+def test_trajectory_cfg1_vs_reference_golden(golden_dir, params, pair, graph):
+    """BASELINE.json configs[0]: 64 residues, 10 denoise steps, batch 1 — final C-alpha within 1e-4 relative."""
+    _run_traj(golden_dir, params, "traj_cfg1_L64_n10.npz", pair, graph)
+
+
+def test_trajectory_masked_vs_reference_golden(golden_dir, params):
+    _run_traj(golden_dir, params, "traj_masked_L24_n6.npz", 1, True)
+
+
+@pytest.mark.parametrize("L", [40, 128])
+def test_pair_kernels_tc_vs_simt(params, L):
+    """tcgen05 pair kernels against the SIMT restatement with identical rounding points, full forward."""
+    B = 2
+    feats = synthetic.make_features(B, L, seed=11, n_pad=3 if L == 40 else 0)
+    q, x = synthetic.make_backbone(L, seed=11)
+    g = torch.Generator().manual_seed(5)
+    feats["rigids_t"] = (torch.cat([q, x], -1)[None].repeat(B, 1, 1) + 0.2 * torch.randn(B, L, 7, generator=g)).float()
+    feats["sc_ca_t"] = (x[None] + torch.randn(B, L, 3, generator=g)).float()
+    feats["t"] = torch.tensor([0.4, 0.6])
+    outs = []
+    for pair in (0, 1):
+        net = make_net(params, pair)
+        eng = net.native("cuda")
+        fc = cuda(feats)
+        eng.reserve(B, L, fc["residue_idx"])
+        node, z = eng.embed(fc["t"], fc["residue_idx"], fc["fixed_mask"].float(), fc["sc_ca_t"], fc["residue_mask"].float())
+        z2 = eng.edge_transition(0, node, z, fc["residue_mask"].float().contiguous())
+        outs.append((z.float().cpu(), z2.float().cpu()))
+    assert rel(outs[1][0], outs[0][0]) < 3e-3   # bf16 output rounding of slightly different fp32 sums
+    assert rel(outs[1][1], outs[0][1]) < 3e-3
+
+
+def test_se3_equivariance_full_size(params):
+    """Size-independent property at BASELINE cfg-2 chain length: rotating + translating the input frames
+    rotates + translates the predicted frames (IPA is SE(3)-equivariant), checked on the CUDA path at L=256."""
+    B, L = 2, 256
+    feats = synthetic.make_features(B, L, seed=13)
+    q, x = synthetic.make_backbone(L, seed=13)
+    feats["rigids_t"] = torch.cat([q, x], -1)[None].repeat(B, 1, 1).float()
+    feats["sc_ca_t"] = torch.zeros(B, L, 3)
+    feats["t"] = torch.tensor([0.3, 0.3])
+    g = torch.Generator().manual_seed(3)
+    qg = torch.nn.functional.normalize(torch.randn(4, generator=g), dim=0)
+    Rg = O.quat_to_rotmat(qg)
+    tg = torch.tensor([3.0, -2.0, 5.0])
+    moved = dict(feats)
+    rt = feats["rigids_t"].clone()
+    rt[..., :4] = O.quat_mul(qg.expand(B, L, 4), rt[..., :4])
+    rt[..., 4:] = rt[..., 4:] @ Rg.T + tg
+    moved["rigids_t"] = rt
+    net = make_net(params, 1)
+    with torch.no_grad():
+        a = net(cuda(feats), as_tensor_7=True)["rigids"].cpu()
+        b = net(cuda(moved), as_tensor_7=True)["rigids"].cpu()
+    expect = a[..., 4:] @ Rg.T + tg
+    assert rel(b[..., 4:], expect) < 2e-5

@@ -1,0 +1,125 @@
+"""CPU-side tests: the C-ABI library loads and exports what include/str2str_b200.h declares, the host mirror
+keeps the reference's state-dict keys and schedule arithmetic, decoy sharding works over gloo (world_size 2).
+No compute call into the library happens here (there is no GPU in this container)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import str2str_oracle as O
+from str2str_b200 import synthetic
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol():
+    from str2str_b200 import _lib, build
+
+    build.build()
+    header = open(os.path.join(ROOT, "include", "str2str_b200.h")).read()
+    declared = set(re.findall(r"\b(s2s_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    lib = _lib.load()  # sets argtypes for every entry in SIGNATURES; AttributeError if one is missing
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_lib.SIGNATURES) == declared
+    assert lib.s2s_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (s2s_[a-z0-9_]+)", out))
+    assert declared <= exported
+
+
+def test_no_cpu_fallback():
+    from str2str_b200.net import DenoisingNet, EmbeddingModule, TranslationIPA
+
+    net = DenoisingNet(EmbeddingModule(32, 256, 128), TranslationIPA(c_s=256, c_z=128, coordinate_scaling=0.1,
+                                                                      no_ipa_blocks=4, skip_embed_size=64))
+    feats = synthetic.make_features(1, 8)
+    feats.update(rigids_t=torch.zeros(1, 8, 7), sc_ca_t=torch.zeros(1, 8, 3), t=torch.tensor([0.5]))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(feats)
+
+
+def test_state_dict_keys_and_shapes_match_reference_layout(params):
+    from str2str_b200.net import DenoisingNet, EmbeddingModule, TranslationIPA
+
+    net = DenoisingNet(EmbeddingModule(32, 256, 128), TranslationIPA(c_s=256, c_z=128, coordinate_scaling=0.1,
+                                                                      no_ipa_blocks=4, skip_embed_size=64))
+    sd = net.state_dict()
+    assert len(sd) == 274 and sum(v.numel() for v in sd.values()) == 17446106
+    assert set(sd) == set(params)
+    assert all(tuple(sd[k].shape) == tuple(params[k].shape) for k in sd)
+    net.load_state_dict(params, strict=True)
+    with pytest.raises(ValueError):
+        EmbeddingModule(16, 256, 128)
+
+
+def test_schedule_rows_match_oracle_formulas():
+    from str2str_b200.score import R3Diffuser, SO3Diffuser
+    from str2str_b200.score.frame import schedule_rows
+
+    t = torch.as_tensor(np.linspace(0.01, 0.5, 10)[::-1].copy()).float()
+    so3 = SO3Diffuser(cache_dir="/tmp/str2str_b200_cache")
+    rows, idx = schedule_rows(R3Diffuser(0.1, 20.0, 0.1), so3, t)
+    assert torch.equal(idx, O.sigma_index(t))  # integer buckets: bit exact
+    assert torch.equal(rows[:, 1], O.discrete_sigma()[idx])
+    assert torch.equal(rows[:, 3], O.rot_g2(t))
+    assert torch.equal(rows[:, 4], torch.exp(-0.5 * O.beta_int(t)))
+    assert torch.equal(rows[:, 6], O.b_of_t(t))
+    assert np.array_equal(so3.cdf_row(123), O.igso3_cdf_row(123))
+    with pytest.raises(ValueError):
+        so3.sigma(torch.tensor([1.5]))
+
+
+def test_rigid_types_roundtrip():
+    from str2str_b200.rigid import Rigid, Rotation
+
+    g = torch.Generator().manual_seed(0)
+    q = torch.nn.functional.normalize(torch.randn(5, 7, 4, generator=g), dim=-1)
+    x = torch.randn(5, 7, 3, generator=g)
+    r = Rigid.from_tensor_7(torch.cat([q, x], -1))
+    assert torch.allclose(r.get_rots().get_rot_mats(), O.quat_to_rotmat(q))
+    r2 = Rigid(Rotation(rot_mats=O.quat_to_rotmat(q)), x)
+    assert torch.allclose(r2.to_tensor_7()[..., :4], O.rotmat_to_quat(O.quat_to_rotmat(q)))
+    with pytest.raises(ValueError):
+        Rigid.from_tensor_7(torch.zeros(3, 6))
+
+
+def test_shard_bounds():
+    from str2str_b200.sampler import shard_bounds
+
+    assert shard_bounds(512, 8) == [64 * i for i in range(9)]
+    assert shard_bounds(10, 4) == [0, 3, 6, 8, 10]
+    assert shard_bounds(2, 4) == [0, 1, 2, 2, 2]
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from str2str_b200.sampler import shard_bounds, all_gather_decoys
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+n = 5
+b = shard_bounds(n, 2)
+r = dist.get_rank()
+local = torch.arange(b[r], b[r + 1], dtype=torch.float32)[:, None, None].expand(-1, 4, 3).contiguous() + 0.5
+full = all_gather_decoys(local, b)
+assert full.shape == (n, 4, 3), full.shape
+assert torch.equal(full[:, 0, 0], torch.arange(n, dtype=torch.float32) + 0.5)
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_decoy_sharding_all_gather_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok" in out, err[-2000:]
