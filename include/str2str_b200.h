@@ -108,6 +108,13 @@ int s2s_backbone_atoms(s2s_ctx* ctx, int rows, const float* rigids, const float*
 int s2s_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
                    void* stream);
 
+/* Per-kernel device timing for the benchmark's roofline line: when enabled, CUDA events bracket the launches of
+ * the named kernels ("edge_transition", "edge_embed", "ipa_pair_attention", "gemm") on their stream.  Must be
+ * off during CUDA-graph capture.  s2s_profile_read returns 1 if no launch of `name` was recorded. */
+void s2s_profile_enable(int on);
+void s2s_profile_reset(void);
+int s2s_profile_read(const char* name, double* total_ms, int64_t* count);
+
 /* number of kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t s2s_launch_count(void);
 

@@ -35,6 +35,9 @@ SIGNATURES = {
     "s2s_backbone_atoms": (_i, [_vp, _i] + [_vp] * 6),
     "s2s_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "s2s_launch_count": (_i64, []),
+    "s2s_profile_enable": (None, [_i]),
+    "s2s_profile_reset": (None, []),
+    "s2s_profile_read": (_i, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_i64)]),
 }
 
 _lib = None

@@ -10,7 +10,38 @@
 namespace s2s {
 
 long long g_launch_count = 0;
+bool g_profile_on = false;
 static thread_local std::string g_error;
+
+struct ProfRec { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; double ms = 0; long long n = 0; };
+static std::map<std::string, ProfRec> g_prof;
+
+ProfScope::ProfScope(const char* n, cudaStream_t s) : name(n), st(s) {
+  if (!g_profile_on) return;
+  cudaEventCreate(&e0);
+  cudaEventRecord(e0, st);
+}
+ProfScope::~ProfScope() {
+  if (!e0) return;
+  cudaEvent_t e1;
+  cudaEventCreate(&e1);
+  cudaEventRecord(e1, st);
+  g_prof[name].ev.emplace_back(e0, e1);
+}
+static void prof_drain() {
+  for (auto& kv : g_prof) {
+    for (auto& pr : kv.second.ev) {
+      cudaEventSynchronize(pr.second);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pr.first, pr.second);
+      kv.second.ms += ms;
+      kv.second.n += 1;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    kv.second.ev.clear();
+  }
+}
 
 namespace {
 
@@ -434,6 +465,16 @@ int guarded(F&& f) {
 extern "C" {
 
 int s2s_abi_version(void) { return S2S_ABI_VERSION; }
+void s2s_profile_enable(int on) { g_profile_on = on != 0; }
+void s2s_profile_reset(void) { prof_drain(); g_prof.clear(); }
+int s2s_profile_read(const char* name, double* total_ms, int64_t* count) {
+  prof_drain();
+  auto it = g_prof.find(name ? name : "");
+  if (it == g_prof.end()) return 1;
+  if (total_ms) *total_ms = it->second.ms;
+  if (count) *count = it->second.n;
+  return 0;
+}
 const char* s2s_last_error(void) { return g_error.c_str(); }
 int64_t s2s_launch_count(void) { return g_launch_count; }
 

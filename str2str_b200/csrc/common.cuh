@@ -49,6 +49,18 @@ extern long long g_launch_count;  // kernels launched by this library (api.cu)
     S2S_CUDA(cudaGetLastError());     \
   } while (0)
 
+// Optional per-kernel timing (bench.py roofline): when enabled, CUDA events bracket the named launches on the
+// launching stream.  Off by default and never enabled while a CUDA graph is being captured.
+struct ProfScope {
+  const char* name;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr;
+  ProfScope(const char* n, cudaStream_t s);
+  ~ProfScope();
+};
+extern bool g_profile_on;
+#define S2S_PROF(name, st) ::s2s::ProfScope _prof_scope(name, st)
+
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 typedef __nv_bfloat16 bf16;

@@ -265,6 +265,7 @@ void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st) {
     S2S_CUDA(cudaFuncSetAttribute(ipa_pair_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  S2S_PROF("ipa_pair_attention", st);
   ipa_pair_attention_kernel<<<a.B * a.L, 256, smem, st>>>(a);
   S2S_LAUNCH_CHECK();
 }

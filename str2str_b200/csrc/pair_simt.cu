@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(D_ET) edge_transition_simt_kernel(EdgeTransiti
 void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st) {
   const long rows = (long)a.B * a.L * a.L;
   const size_t smem = 2 * C_Z * RT * sizeof(float);
+  S2S_PROF("edge_embed", st);
   edge_embed_simt_kernel<<<ceil_div(rows, RT), 128, smem, st>>>(a);
   S2S_LAUNCH_CHECK();
 }
@@ -192,6 +193,7 @@ void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st) {
     S2S_CUDA(cudaFuncSetAttribute(edge_transition_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  S2S_PROF("edge_transition", st);
   edge_transition_simt_kernel<<<ceil_div(rows, RT), D_ET, smem, st>>>(a);
   S2S_LAUNCH_CHECK();
 }
