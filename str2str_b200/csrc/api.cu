@@ -97,6 +97,7 @@ struct IpaW {
 };
 struct EtW {
   bf16 *W1z, *W2, *Wfh, *Wfz, *W1zt, *W2t, *Wft, *Wfzt;
+  bf16* wimg;  // tcgen05 weight image
 };
 
 }  // namespace
@@ -112,7 +113,7 @@ struct s2s_ctx {
   Slab wslab;  // derived weights
   IpaW ipa[N_BLK];
   EtW et[N_BLK - 1];
-  bf16 *ee_W2, *ee_W3, *ee_W2t, *ee_W3t;
+  bf16 *ee_W2, *ee_W3, *ee_W2t, *ee_W3t, *ee_wimg;
   float* ee_Wd;
   // workspace
   Slab ws;
@@ -120,7 +121,7 @@ struct s2s_ctx {
   float *feat65, *tf33, *node, *init_node, *a256, *b256, *proj, *feats, *q_pts, *k_pts, *v_pts, *S, *opt;
   float *skip64, *x320, *t320, *y320, *qkv, *nprime, *u384, *v384, *p128, *q128, *Ti, *Tj, *Tpos, *relfeat;
   float *quat, *trans, *upd6, *psi_u, *diffuse, *keybias;
-  bf16* z;
+  bf16 *z, *nprime_bf16;
 
   const float* P(const std::string& n) const {
     auto it = params.find(n);
@@ -200,7 +201,7 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
                                                  " elements, expected " + std::to_string(ps.numel));
   }
   c->wslab.release();
-  c->wslab.cap = 64u << 20;
+  c->wslab.cap = 96u << 20;
   S2S_CUDA(cudaMalloc(&c->wslab.base, c->wslab.cap));
   const std::string t = "translator.trunk.";
   for (int b = 0; b < N_BLK; ++b) {
@@ -233,6 +234,8 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
       prep_split(W2, 384, 384, 0, 384, x.W2, nullptr, st);   prep_t_bf16(W2, 384, 384, 0, 384, x.W2t, st);
       prep_split(Wf, 384, 128, 0, 384, x.Wfh, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 384, x.Wft, st);
       prep_split(Wf, 384, 128, 0, 128, x.Wfz, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 128, x.Wfzt, st);
+      x.wimg = c->wslab.take<bf16>(et_wimg_elems());
+      build_et_wimg(W1, W2, Wf, x.wimg, st);
     }
   }
   {
@@ -244,6 +247,8 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
     prep_split(W2, 128, 128, 0, 128, c->ee_W2, nullptr, st); prep_t_bf16(W2, 128, 128, 0, 128, c->ee_W2t, st);
     prep_split(W3, 128, 128, 0, 128, c->ee_W3, nullptr, st); prep_t_bf16(W3, 128, 128, 0, 128, c->ee_W3t, st);
     prep_t_f32(W1, 120, 128, 98, N_BINS, c->ee_Wd, st);
+    c->ee_wimg = c->wslab.take<bf16>(ee_wimg_elems());
+    build_ee_wimg(W2, W3, c->ee_wimg, st);
   }
   // Wfh above holds the full [128][384] final-layer image; only its action on h2 (all 384 inputs) is used:
   // final_layer(h2 + x) = Wf h2 + Wf[:, :128] z + Wf[:,128:256] n_i + Wf[:,256:] n_j.
@@ -267,7 +272,7 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     add(R * 128, 4); add(R * 384, 4); add(R * 384, 4); add(R * 128, 4); add(R * 128, 4); add(R * 128, 4); add(R * 128, 4);
     add((size_t)n_off * 128, 4); add((size_t)n_off * 32, 4);
     add(R * 4, 4); add(R * 3, 4); add(R * 6, 4); add(R * 2, 4); add(R, 4); add(R, 4);
-    add(R * L * C_Z, 2);
+    add(R * L * C_Z, 2); add(R * 128, 2);
     c->ws.cap = bytes + 4096;
     S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
     Slab& w = c->ws;
@@ -284,6 +289,7 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->quat = w.take<float>(R * 4); c->trans = w.take<float>(R * 3); c->upd6 = w.take<float>(R * 6); c->psi_u = w.take<float>(R * 2);
     c->diffuse = w.take<float>(R); c->keybias = w.take<float>(R);
     c->z = w.take<bf16>(R * L * C_Z);
+    c->nprime_bf16 = w.take<bf16>(R * 128);
     c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
   }
   // relative-position table: Tpos[r] = W1[:,66:98] pos(d_min + r)   (denoising_ipa.py:144-149)
@@ -316,8 +322,10 @@ void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, c
   a.sc_ca = sc_ca; a.ridx = ridx; a.mask = rmask;
   a.W2 = c->ee_W2; a.W3 = c->ee_W3; a.W2t = c->ee_W2t; a.W3t = c->ee_W3t;
   a.b2 = c->P(ee + "2.bias"); a.b3 = c->P(ee + "4.bias"); a.ln_w = c->P(ee + "5.weight"); a.ln_b = c->P(ee + "5.bias");
-  a.z_out = z_out;
-  if (c->opt_pair == 1) edge_embed_tc(a, st); else edge_embed_simt(a, st);
+  a.z_out = z_out; a.wimg = c->ee_wimg;
+  // the tcgen05 kernels work on 128-row tiles of one (b, i): chain lengths that are not a multiple of 128 take the
+  // SIMT kernels (same inputs, same rounding points)
+  if (c->opt_pair == 1 && L % 128 == 0) edge_embed_tc(a, st); else edge_embed_simt(a, st);
 }
 
 // InvariantPointAttention.forward of block blk -> out (linear_out result; not yet masked)
@@ -367,18 +375,23 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   const std::string e = "translator.trunk.edge_transition_" + std::to_string(blk) + ".";
   const float *W1 = c->P(e + "trunk.0.weight"), *Wf = c->P(e + "final_layer.weight");
   linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st);
+  const bool tc = c->opt_pair == 1 && L % 128 == 0;
   linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st);
-  linear(c, c->nprime, 128, W1 + 256, 384, nullptr, c->v384, 384, R, 384, 128, st);
   linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st);
-  linear(c, c->nprime, 128, Wf + 256, 384, nullptr, c->q128, 128, R, 128, 128, st);
+  if (tc) {  // the n'_j terms ride along as extra K columns of the MMAs
+    f32_to_bf16(c->nprime, c->nprime_bf16, (long)R * 128, st);
+  } else {
+    linear(c, c->nprime, 128, W1 + 256, 384, nullptr, c->v384, 384, R, 384, 128, st);
+    linear(c, c->nprime, 128, Wf + 256, 384, nullptr, c->q128, 128, R, 128, 128, st);
+  }
   EdgeTransitionArgs a;
   a.B = B; a.L = L; a.z_in = z_in; a.u = c->u384; a.v = c->v384; a.p = c->p128; a.q = c->q128; a.mask = rmask;
   const EtW& w = c->et[blk];
   a.W1z = w.W1z; a.W2 = w.W2; a.Wfh = w.Wfh; a.Wfz = w.Wfz;
   a.W1zt = w.W1zt; a.W2t = w.W2t; a.Wft = w.Wft; a.Wfzt = w.Wfzt;
   a.b2 = c->P(e + "trunk.2.bias"); a.ln_w = c->P(e + "layer_norm.weight"); a.ln_b = c->P(e + "layer_norm.bias");
-  a.z_out = z_out;
-  if (c->opt_pair == 1) edge_transition_tc(a, st); else edge_transition_simt(a, st);
+  a.z_out = z_out; a.wimg = w.wimg; a.nprime_bf16 = c->nprime_bf16;
+  if (tc) edge_transition_tc(a, st); else edge_transition_simt(a, st);
 }
 
 void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {

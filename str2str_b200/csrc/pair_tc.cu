@@ -1,6 +1,640 @@
-// placeholder — replaced by the tcgen05 kernels
+// Pair-track MLPs on the 5th-gen tensor cores: fused EdgeTransition and fused edge embedder.
+//
+// Both kernels work on tiles of 128 consecutive pair rows (fixed decoy b and residue i, 128 values of j), keep the
+// whole MLP chain on chip and touch HBM once per row for reading and once for writing (bf16):
+//   * operands are staged in shared memory in the canonical K-major SWIZZLE_128B layout (TMA tensor maps for the
+//     activation tiles, pre-swizzled weight images streamed with 1-D bulk TMA copies),
+//   * one elected thread issues tcgen05.mma (M=128, N=128, K=16, bf16 x bf16 -> fp32) with accumulators in TMEM,
+//   * four epilogue warps pull accumulators back with tcgen05.ld, apply bias/ReLU/LayerNorm and either re-stage the
+//     bf16 activations for the next layer in shared memory or store the output rows.
+// Roles talk through mbarriers only.  Requires L % 128 == 0 (the launcher routes other lengths to pair_simt.cu).
+//
+// EdgeTransition algebra (reference src/models/net/layers.py:170-185), with x = [z_ij, n'_i, n'_j]:
+//   h1 = relu(W1 x + b1) = relu(W1[:, z|n'_j] [z_ij, n'_j] + u_i),       u_i = W1[:,128:256] n'_i + b1   (per residue)
+//   h2 = relu(W2 h1 + b2)
+//   y  = Wf (h2 + x) + bf = [Wf | Wf[:, :128] | Wf[:,256:]] [h2, z_ij, n'_j] + p_i,   p_i = Wf[:,128:256] n'_i + bf
+//   out = LayerNorm(y) * mask_i * mask_j
+#include <cuda.h>
+
 #include "s2s_internal.cuh"
+
 namespace s2s {
-void edge_embed_tc(const EdgeEmbedArgs&, cudaStream_t) { S2S_CHECK(false, "edge_embed_tc: not built"); }
-void edge_transition_tc(const EdgeTransitionArgs&, cudaStream_t) { S2S_CHECK(false, "edge_transition_tc: not built"); }
+
+namespace {
+
+constexpr int TM = 128;                  // pair rows per tile (= UMMA M)
+constexpr int KBLK = 64;                 // bf16 elements per 128-byte swizzle row
+constexpr int TILE_BYTES = TM * KBLK * 2;  // 16 KiB: one [128 x 64] bf16 operand block
+constexpr int ET_RING = 3;
+constexpr int ET_WTILES = 40;            // weight blocks per row tile: 12 (layer 1) + 18 (layer 2) + 10 (final)
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_bulk_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major, bf16, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B between 8-row groups | version 1 | layout 2
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A/B, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of element (row r, column c) inside a [128 x 64] bf16 block in the SW128 K-major layout
+__device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
+}
+
+// one 64-wide K-block of MMAs: D += A_blk * B_blk^T
+__device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_blk, uint32_t b_blk, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int k = 0; k < KBLK / 16; ++k)
+    umma_bf16(d_tmem, smem_desc_sw128(a_blk + k * 32), smem_desc_sw128(b_blk + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+}
+
+// 8 fp32 -> 8 bf16 packed store into the swizzled operand block
+__device__ __forceinline__ void store8_sw128(unsigned char* blk_base, int r, int c, const float* h) {
+  uint4 pk = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+  *reinterpret_cast<uint4*>(blk_base + sw128_offset(r, c)) = pk;
+}
+
+// ---- fused EdgeTransition -----------------------------------------------------------------------------------------
+struct EtTcArgs {
+  const bf16* wimg;  // ET_WTILES pre-swizzled [128 x 64] weight blocks in consumption order
+  const float *u, *p, *b2, *ln_w, *ln_b, *mask;
+  bf16* z_out;
+  int L, n_tiles;
+};
+
+constexpr int ET_OFF_A0 = 0;                          // [z | n'_j] tile: 4 K-blocks
+constexpr int ET_OFF_H = 4 * TILE_BYTES;              // hidden activations: 6 K-blocks
+constexpr int ET_OFF_W = ET_OFF_H + 6 * TILE_BYTES;   // weight ring
+constexpr int ET_OFF_VEC = ET_OFF_W + ET_RING * TILE_BYTES;
+constexpr int ET_VEC_FLOATS = D_ET + C_Z + D_ET + C_Z + C_Z;  // u_i, p_i, b2, ln_w, ln_b
+constexpr int ET_OFF_BAR = ET_OFF_VEC + ET_VEC_FLOATS * 4;
+constexpr int ET_SMEM = ET_OFF_BAR + 16 * 8 + 16;
+
+__global__ void __launch_bounds__(192, 1)
+edge_transition_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_n, EtTcArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  float* u_s = reinterpret_cast<float*>(smem + ET_OFF_VEC);
+  float* p_s = u_s + D_ET;
+  float* b2_s = p_s + C_Z;
+  float* lnw_s = b2_s + D_ET;
+  float* lnb_s = lnw_s + C_Z;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ET_OFF_BAR);
+  uint64_t* w_full = bars;            // [ET_RING]
+  uint64_t* w_empty = bars + 3;       // [ET_RING]
+  uint64_t* a0_full = bars + 6;
+  uint64_t* a0_empty = bars + 7;
+  uint64_t* acc_full = bars + 8;
+  uint64_t* h_full = bars + 9;
+  uint64_t* acc3_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ET_RING; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(a0_full, 1);
+    mbar_init(a0_empty, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(h_full, 128);
+    mbar_init(acc3_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int c = threadIdx.x; c < D_ET; c += blockDim.x) b2_s[c] = a.b2[c];
+  for (int c = threadIdx.x; c < C_Z; c += blockDim.x) {
+    lnw_s[c] = a.ln_w[c];
+    lnb_s[c] = a.ln_b[c];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int tiles_per_i = a.L / TM;
+  constexpr uint32_t IDESC = make_idesc(128, 128);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t cnt = 0, ph_a0 = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
+        const int b = bi / a.L;
+        mbar_wait(a0_empty, ph_a0 ^ 1);
+        mbar_expect_tx(a0_full, 4 * TILE_BYTES);
+        tma_load_2d(smem + ET_OFF_A0, &tmap_z, 0, tile * TM, a0_full);
+        tma_load_2d(smem + ET_OFF_A0 + TILE_BYTES, &tmap_z, KBLK, tile * TM, a0_full);
+        tma_load_2d(smem + ET_OFF_A0 + 2 * TILE_BYTES, &tmap_n, 0, b * a.L + j0, a0_full);
+        tma_load_2d(smem + ET_OFF_A0 + 3 * TILE_BYTES, &tmap_n, KBLK, b * a.L + j0, a0_full);
+        ph_a0 ^= 1;
+        for (int wt = 0; wt < ET_WTILES; ++wt, ++cnt) {
+          const uint32_t s = cnt % ET_RING, ph = (cnt / ET_RING) & 1;
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_expect_tx(&w_full[s], TILE_BYTES);
+          tma_bulk_1d(smem + ET_OFF_W + s * TILE_BYTES, a.wimg + (size_t)wt * (TILE_BYTES / 2), TILE_BYTES, &w_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t a0 = smem_u32(smem + ET_OFF_A0), hb = smem_u32(smem + ET_OFF_H), wr = smem_u32(smem + ET_OFF_W);
+      uint32_t cnt = 0, ph_a0 = 0, ph_h = 0, ph_3 = 0;
+      auto wblock = [&](uint32_t d_tmem, uint32_t a_blk, bool first) {
+        const uint32_t s = cnt % ET_RING, ph = (cnt / ET_RING) & 1;
+        mbar_wait(&w_full[s], ph);
+        tc_fence_after();
+        mma_kblock(d_tmem, a_blk, wr + s * TILE_BYTES, IDESC, first);
+        umma_commit(&w_empty[s]);
+        ++cnt;
+      };
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        mbar_wait(a0_full, ph_a0);
+        ph_a0 ^= 1;
+        tc_fence_after();
+        for (int nc = 0; nc < 3; ++nc)  // layer 1: K = [z | n'_j] = 4 blocks
+          for (int kb = 0; kb < 4; ++kb) wblock(tmem + nc * 128, a0 + kb * TILE_BYTES, kb == 0);
+        umma_commit(acc_full);
+        mbar_wait(h_full, ph_h);
+        ph_h ^= 1;
+        tc_fence_after();
+        for (int nc = 0; nc < 3; ++nc)  // layer 2: K = h1 = 6 blocks
+          for (int kb = 0; kb < 6; ++kb) wblock(tmem + nc * 128, hb + kb * TILE_BYTES, kb == 0);
+        umma_commit(acc_full);
+        mbar_wait(h_full, ph_h);
+        ph_h ^= 1;
+        mbar_wait(acc3_empty, ph_3 ^ 1);  // previous tile's output accumulator has been drained
+        ph_3 ^= 1;
+        tc_fence_after();
+        for (int kb = 0; kb < 6; ++kb) wblock(tmem + 384, hb + kb * TILE_BYTES, kb == 0);  // final: h2
+        for (int kb = 0; kb < 4; ++kb) wblock(tmem + 384, a0 + kb * TILE_BYTES, false);    //        z, n'_j
+        umma_commit(acc_full);
+        umma_commit(a0_empty);
+      }
+    }
+  } else {
+    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    const int q = warp & 3, r = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    unsigned char* hbuf = smem + ET_OFF_H;
+    uint32_t ph_acc = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
+      const int b = bi / a.L;
+      named_bar_sync(1, 128);  // everyone is done with the previous tile's u_i / p_i
+      for (int c = et; c < D_ET; c += 128) u_s[c] = a.u[(size_t)bi * D_ET + c];
+      p_s[et] = a.p[(size_t)bi * C_Z + et];
+      named_bar_sync(1, 128);
+      const float m = a.mask[bi] * a.mask[(size_t)b * a.L + j0 + r];
+      float v[32];
+      // hidden layers: acc -> (+ vec) -> relu -> bf16 -> swizzled operand block for the next MMA
+      for (int layer = 0; layer < 2; ++layer) {
+        const float* vec = layer == 0 ? u_s : b2_s;
+        mbar_wait(acc_full, ph_acc);
+        ph_acc ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < D_ET; c0 += 32) {
+          tmem_ld32(lane_base + c0, v);
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            float h[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h[e] = fmaxf(v[gq * 8 + e] + vec[c0 + gq * 8 + e], 0.f);
+            const int c = c0 + gq * 8;
+            store8_sw128(hbuf + (c / KBLK) * TILE_BYTES, r, c % KBLK, h);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(h_full);
+      }
+      // output layer: + p_i, LayerNorm over 128 channels (exact two-pass), * edge mask, bf16 store
+      mbar_wait(acc_full, ph_acc);
+      ph_acc ^= 1;
+      tc_fence_after();
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_Z; c0 += 32) {
+        tmem_ld32(lane_base + 384 + c0, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sum += v[e] + p_s[c0 + e];
+      }
+      const float mean = sum * (1.f / C_Z);
+      float sq = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_Z; c0 += 32) {
+        tmem_ld32(lane_base + 384 + c0, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float d = v[e] + p_s[c0 + e] - mean;
+          sq += d * d;
+        }
+      }
+      const float rstd = rsqrtf(sq * (1.f / C_Z) + 1e-5f);
+      bf16* orow = a.z_out + ((size_t)tile * TM + r) * C_Z;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_Z; c0 += 32) {
+        tmem_ld32(lane_base + 384 + c0, v);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c0 + gq * 8 + e;
+            o[e] = ((v[gq * 8 + e] + p_s[c] - mean) * rstd * lnw_s[c] + lnb_s[c]) * m;
+          }
+          *reinterpret_cast<uint4*>(orow + c0 + gq * 8) =
+              make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc3_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---- fused edge embedder ---------------------------------------------------------------------------------------------
+struct EeTcArgs {
+  EdgeEmbedArgs e;
+  const bf16* wimg;  // 4 pre-swizzled blocks: W2 k0, W2 k1, W3 k0, W3 k1
+  int n_tiles;
+};
+constexpr int WD_PITCH = C_Z + 4;
+constexpr int EE_OFF_A = 0;                      // activation tile: 2 K-blocks
+constexpr int EE_OFF_W = 2 * TILE_BYTES;         // 4 resident weight blocks
+constexpr int EE_OFF_VEC = EE_OFF_W + 4 * TILE_BYTES;
+constexpr int EE_VEC_FLOATS = C_Z * 5 + N_BINS * WD_PITCH + 32;  // Ti, b2, b3, ln_w, ln_b, Wd, bin edges
+constexpr int EE_OFF_BAR = EE_OFF_VEC + EE_VEC_FLOATS * 4;
+constexpr int EE_SMEM = EE_OFF_BAR + 8 * 8 + 16;
+
+__global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  float* ti_s = reinterpret_cast<float*>(smem + EE_OFF_VEC);
+  float* b2_s = ti_s + C_Z;
+  float* b3_s = b2_s + C_Z;
+  float* lnw_s = b3_s + C_Z;
+  float* lnb_s = lnw_s + C_Z;
+  float* wd_s = lnb_s + C_Z;
+  float* edge_s = wd_s + N_BINS * WD_PITCH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EE_OFF_BAR);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* acc_full = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const EdgeEmbedArgs& e = a.e;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 128);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  for (int c = threadIdx.x; c < C_Z; c += blockDim.x) {
+    b2_s[c] = e.b2[c];
+    b3_s[c] = e.b3[c];
+    lnw_s[c] = e.ln_w[c];
+    lnb_s[c] = e.ln_b[c];
+  }
+  for (int c = threadIdx.x; c < N_BINS * C_Z; c += blockDim.x) wd_s[(c / C_Z) * WD_PITCH + (c % C_Z)] = e.Wd[c];
+  if (threadIdx.x < N_BINS) edge_s[threadIdx.x] = e.bin_lower[threadIdx.x];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int tiles_per_i = e.L / TM;
+  constexpr uint32_t IDESC = make_idesc(128, 128);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 4 * TILE_BYTES);
+      for (int t = 0; t < 4; ++t) tma_bulk_1d(smem + EE_OFF_W + t * TILE_BYTES, a.wimg + (size_t)t * (TILE_BYTES / 2), TILE_BYTES, w_full);
+      mbar_wait(w_full, 0);
+      const uint32_t ab = smem_u32(smem + EE_OFF_A), wb = smem_u32(smem + EE_OFF_W);
+      uint32_t ph_a = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        for (int layer = 0; layer < 2; ++layer) {
+          mbar_wait(a_full, ph_a);
+          ph_a ^= 1;
+          tc_fence_after();
+          mma_kblock(tmem, ab, wb + (2 * layer) * TILE_BYTES, IDESC, true);
+          mma_kblock(tmem, ab + TILE_BYTES, wb + (2 * layer + 1) * TILE_BYTES, IDESC, false);
+          umma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane;
+    const int wt = threadIdx.x - 32;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    unsigned char* abuf = smem + EE_OFF_A;
+    uint32_t ph_acc = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
+      const int b = bi / e.L;
+      const size_t bj = (size_t)b * e.L + j0 + r;
+      named_bar_sync(1, 128);
+      ti_s[wt] = e.Ti[(size_t)bi * C_Z + wt];
+      named_bar_sync(1, 128);
+      // layer 1 by table lookups (reference denoising_ipa.py:126-158): time/fixed features of i and j, relative
+      // position, self-conditioning distogram bin
+      const int bin = pair_distogram_bin(e.sc_ca + (size_t)bi * 3, e.sc_ca + bj * 3, edge_s);
+      const int off = (int)(e.ridx[bi] - e.ridx[bj]) - e.d_min;
+      const float4* tj = reinterpret_cast<const float4*>(e.Tj + bj * C_Z);
+      const float4* tp = reinterpret_cast<const float4*>(e.Tpos + (size_t)off * C_Z);
+      const float* wd = wd_s + (bin >= 0 ? bin : 0) * WD_PITCH;
+      const float wdm = bin >= 0 ? 1.f : 0.f;
+#pragma unroll 2
+      for (int c = 0; c < C_Z; c += 8) {
+        const float4 j0v = __ldg(tj + c / 4), j1v = __ldg(tj + c / 4 + 1);
+        const float4 p0v = __ldg(tp + c / 4), p1v = __ldg(tp + c / 4 + 1);
+        const float tjv[8] = {j0v.x, j0v.y, j0v.z, j0v.w, j1v.x, j1v.y, j1v.z, j1v.w};
+        const float tpv[8] = {p0v.x, p0v.y, p0v.z, p0v.w, p1v.x, p1v.y, p1v.z, p1v.w};
+        float h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) h[k] = fmaxf(ti_s[c + k] + tjv[k] + tpv[k] + wdm * wd[c + k], 0.f);
+        store8_sw128(abuf + (c / KBLK) * TILE_BYTES, r, c % KBLK, h);
+      }
+      fence_proxy_async();
+      mbar_arrive(a_full);
+      // layer 2 epilogue: + b2, relu, restage
+      float v[32];
+      mbar_wait(acc_full, ph_acc);
+      ph_acc ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_Z; c0 += 32) {
+        tmem_ld32(lane_base + c0, v);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          float h[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) h[k] = fmaxf(v[gq * 8 + k] + b2_s[c0 + gq * 8 + k], 0.f);
+          const int c = c0 + gq * 8;
+          store8_sw128(abuf + (c / KBLK) * TILE_BYTES, r, c % KBLK, h);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(a_full);
+      // layer 3 epilogue: + b3, LayerNorm, mask, store
+      mbar_wait(acc_full, ph_acc);
+      ph_acc ^= 1;
+      tc_fence_after();
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_Z; c0 += 32) {
+        tmem_ld32(lane_base + c0, v);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sum += v[k] + b3_s[c0 + k];
+      }
+      const float mean = sum * (1.f / C_Z);
+      float sq = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_Z; c0 += 32) {
+        tmem_ld32(lane_base + c0, v);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float d = v[k] + b3_s[c0 + k] - mean;
+          sq += d * d;
+        }
+      }
+      const float rstd = rsqrtf(sq * (1.f / C_Z) + 1e-5f);
+      const float m = e.mask[bi] * e.mask[bj];
+      bf16* orow = e.z_out + ((size_t)tile * TM + r) * C_Z;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_Z; c0 += 32) {
+        tmem_ld32(lane_base + c0, v);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = c0 + gq * 8 + k;
+            o[k] = ((v[gq * 8 + k] + b3_s[c] - mean) * rstd * lnw_s[c] + lnb_s[c]) * m;
+          }
+          *reinterpret_cast<uint4*>(orow + c0 + gq * 8) =
+              make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+      }
+      tc_fence_before();  // TMEM reads done before the next tile's MMA (ordered by the next a_full arrive)
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+__global__ void build_wtile_kernel(const float* __restrict__ src, int ld, int n0, int k0, unsigned char* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= TM * KBLK) return;
+  const int r = idx / KBLK, c = idx % KBLK;
+  *reinterpret_cast<bf16*>(dst + sw128_offset(r, c)) = __float2bfloat16_rn(src[(size_t)(n0 + r) * ld + k0 + c]);
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    S2S_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    S2S_CHECK(p && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from this driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// [rows][128] bf16 row-major tensor, boxes of 128 rows x 64 columns, 128-byte swizzle
+CUtensorMap make_rows128_map(const void* base, size_t rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)C_Z, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C_Z * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)TM};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  S2S_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
+  return m;
+}
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    S2S_CUDA(cudaGetDevice(&dev));
+    S2S_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+}  // namespace
+
+size_t et_wimg_elems() { return (size_t)ET_WTILES * TM * KBLK; }
+size_t ee_wimg_elems() { return (size_t)4 * TM * KBLK; }
+
+// Weight images in the order the MMA issuer consumes them (see the kernel's loops).
+void build_et_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st) {
+  unsigned char* d = reinterpret_cast<unsigned char*>(dst);
+  auto tile = [&](const float* src, int n0, int k0) {
+    build_wtile_kernel<<<TM * KBLK / 256, 256, 0, st>>>(src, D_ET, n0, k0, d);
+    S2S_LAUNCH_CHECK();
+    d += TILE_BYTES;
+  };
+  for (int nc = 0; nc < 3; ++nc)
+    for (int kb = 0; kb < 4; ++kb) tile(W1, nc * 128, kb < 2 ? kb * KBLK : 256 + (kb - 2) * KBLK);
+  for (int nc = 0; nc < 3; ++nc)
+    for (int kb = 0; kb < 6; ++kb) tile(W2, nc * 128, kb * KBLK);
+  for (int kb = 0; kb < 6; ++kb) tile(Wf, 0, kb * KBLK);
+  for (int kb = 0; kb < 2; ++kb) tile(Wf, 0, kb * KBLK);
+  for (int kb = 0; kb < 2; ++kb) tile(Wf, 0, 256 + kb * KBLK);
+}
+void build_ee_wimg(const float* W2, const float* W3, bf16* dst, cudaStream_t st) {
+  unsigned char* d = reinterpret_cast<unsigned char*>(dst);
+  const float* srcs[2] = {W2, W3};
+  for (int l = 0; l < 2; ++l)
+    for (int kb = 0; kb < 2; ++kb) {
+      build_wtile_kernel<<<TM * KBLK / 256, 256, 0, st>>>(srcs[l], C_Z, 0, kb * KBLK, d);
+      S2S_LAUNCH_CHECK();
+      d += TILE_BYTES;
+    }
+}
+void f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t st) {
+  f32_to_bf16_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, dst, n);
+  S2S_LAUNCH_CHECK();
+}
+
+void edge_transition_tc(const EdgeTransitionArgs& a, cudaStream_t st) {
+  S2S_CHECK(a.L % TM == 0, "edge_transition_tc needs L % 128 == 0");
+  S2S_CHECK(a.wimg && a.nprime_bf16, "edge_transition_tc: weight image / bf16 node embedding missing");
+  const size_t rows = (size_t)a.B * a.L * a.L;
+  const CUtensorMap mz = make_rows128_map(a.z_in, rows);
+  const CUtensorMap mn = make_rows128_map(a.nprime_bf16, (size_t)a.B * a.L);
+  EtTcArgs k;
+  k.wimg = a.wimg; k.u = a.u; k.p = a.p; k.b2 = a.b2; k.ln_w = a.ln_w; k.ln_b = a.ln_b; k.mask = a.mask;
+  k.z_out = a.z_out; k.L = a.L; k.n_tiles = (int)(rows / TM);
+  static bool configured = false;
+  const int smem = ET_SMEM + 1024;
+  if (!configured) {
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  S2S_PROF("edge_transition", st);
+  const int grid = k.n_tiles < sm_count() ? k.n_tiles : sm_count();
+  edge_transition_tc_kernel<<<grid, 192, smem, st>>>(mz, mn, k);
+  S2S_LAUNCH_CHECK();
+}
+
+void edge_embed_tc(const EdgeEmbedArgs& a, cudaStream_t st) {
+  S2S_CHECK(a.L % TM == 0, "edge_embed_tc needs L % 128 == 0");
+  S2S_CHECK(a.wimg, "edge_embed_tc: weight image missing");
+  EeTcArgs k;
+  k.e = a; k.wimg = a.wimg; k.n_tiles = (int)((size_t)a.B * a.L * a.L / TM);
+  static bool configured = false;
+  const int smem = EE_SMEM + 1024;
+  if (!configured) {
+    S2S_CUDA(cudaFuncSetAttribute(edge_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  S2S_PROF("edge_embed", st);
+  const int cap = 2 * sm_count();
+  edge_embed_tc_kernel<<<k.n_tiles < cap ? k.n_tiles : cap, 160, smem, st>>>(k);
+  S2S_LAUNCH_CHECK();
+}
+
 }  // namespace s2s

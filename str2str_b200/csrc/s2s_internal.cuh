@@ -63,6 +63,7 @@ struct EdgeEmbedArgs {
   const bf16 *W2t, *W3t;   // [in][out]
   const float *b2, *b3, *ln_w, *ln_b;
   bf16* z_out;             // [B,L,L,128]
+  const bf16* wimg = nullptr;  // tcgen05 path: pre-swizzled weight blocks (build_ee_wimg)
 };
 void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st);
 void edge_embed_tc(const EdgeEmbedArgs& a, cudaStream_t st);
@@ -79,9 +80,16 @@ struct EdgeTransitionArgs {
   const bf16 *W1zt, *W2t, *Wft, *Wfzt;   // transposed copies [in][out]
   const float *b2, *ln_w, *ln_b;
   bf16* z_out;        // may alias z_in
+  const bf16* wimg = nullptr;         // tcgen05 path: pre-swizzled weight blocks (build_et_wimg)
+  const bf16* nprime_bf16 = nullptr;  // tcgen05 path: n' [B*L][128] in bf16 (the n'_j operand rows)
 };
 void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st);
 void edge_transition_tc(const EdgeTransitionArgs& a, cudaStream_t st);
+size_t et_wimg_elems();
+size_t ee_wimg_elems();
+void build_et_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);
+void build_ee_wimg(const float* W2, const float* W3, bf16* dst, cudaStream_t st);
+void f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t st);
 
 // ---- ipa.cu -------------------------------------------------------------------------------------------
 void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv, const float* quat,
