@@ -109,6 +109,7 @@ struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
   int opt_pair = 1, opt_node = 0;
+  int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
   float *tfreq = nullptr, *pdenom = nullptr, *bin_lower = nullptr, *backbone = nullptr;
   Slab wslab;  // derived weights
   IpaW ipa[N_BLK];
@@ -122,6 +123,9 @@ struct s2s_ctx {
   float *skip64, *x320, *t320, *y320, *qkv, *nprime, *u384, *v384, *p128, *q128, *Ti, *Tj, *Tpos, *relfeat;
   float *quat, *trans, *upd6, *psi_u, *diffuse, *keybias;
   bf16 *z, *nprime_bf16;
+  // tensor-core node track: bf16 hi/lo images of every weight matrix, scratch split buffers, attention operands
+  std::map<const float*, std::pair<size_t, std::pair<bf16*, bf16*>>> wsplit;  // fp32 base -> (numel, (hi, lo))
+  bf16 *sa_hi, *sa_lo, *qkv_bf16, *vT, *P_bf16;
 
   const float* P(const std::string& n) const {
     auto it = params.find(n);
@@ -132,10 +136,36 @@ struct s2s_ctx {
 
 namespace {
 
+enum Prec { EXACT = 0, TC3 = 3, TC1 = 1 };
+
+// bf16 (hi, lo) image of a weight (or of a sub-block of one) registered at finalize
+std::pair<const bf16*, const bf16*> weight_split(const s2s_ctx* c, const float* W) {
+  auto it = c->wsplit.upper_bound(W);
+  S2S_CHECK(it != c->wsplit.begin(), "weight_split: unknown weight pointer");
+  --it;
+  const size_t off = (size_t)(W - it->first);
+  S2S_CHECK(off < it->second.first, "weight_split: pointer outside any registered weight");
+  return {it->second.second.first + off, it->second.second.second + off};
+}
+
+// y = act((x W^T * row_pre + bias)) * row_post + res.  prec selects exact fp32 FFMA or the tensor-core GEMM
+// (3-pass split-bf16 / single bf16) when the context runs with node_gemm = 1.
 void linear(const s2s_ctx* c, const float* x, long ldx, const float* W, long ldw, const float* bias, float* y, long ldy,
             int M, int N, int K, cudaStream_t st, int relu = 0, const float* res = nullptr, long ldres = 0,
-            const float* row_pre = nullptr, const float* row_post = nullptr) {
-  (void)c;
+            const float* row_pre = nullptr, const float* row_post = nullptr, int prec_arg = -1) {
+  const Prec prec = (Prec)(prec_arg < 0 ? c->cur_prec : prec_arg);
+  if (prec != EXACT && c->opt_node == 1 && K % 16 == 0 && ldx % 4 == 0 && ldw % 8 == 0) {
+    split_bf16(x, ldx, M, K, c->sa_hi, prec == TC3 ? c->sa_lo : nullptr, st);
+    const auto w = weight_split(c, W);
+    TcGemm g;
+    g.A_hi = c->sa_hi; g.A_lo = c->sa_lo; g.a_rows = M; g.a_cols = K; g.a_pitch = K;
+    g.B_hi = w.first; g.B_lo = w.second; g.b_rows = N; g.b_cols = K; g.b_pitch = ldw;
+    g.M = M; g.N = N; g.K = K; g.passes = (int)prec; g.relu = relu;
+    g.bias = bias; g.row_pre = row_pre; g.row_post = row_post; g.res = res; g.ldres = ldres;
+    g.C = y; g.ldc = ldy;
+    gemm_tc(g, st);
+    return;
+  }
   GemmArgs g;
   g.A = x; g.lda = ldx; g.B = W; g.ldb = ldw; g.C = y; g.ldc = ldy;
   g.bias = bias; g.res = res; g.ldres = ldres; g.row_pre = row_pre; g.row_post = row_post;
@@ -201,7 +231,7 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
                                                  " elements, expected " + std::to_string(ps.numel));
   }
   c->wslab.release();
-  c->wslab.cap = 96u << 20;
+  c->wslab.cap = 256u << 20;
   S2S_CUDA(cudaMalloc(&c->wslab.base, c->wslab.cap));
   const std::string t = "translator.trunk.";
   for (int b = 0; b < N_BLK; ++b) {
@@ -250,6 +280,27 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
     c->ee_wimg = c->wslab.take<bf16>(ee_wimg_elems());
     build_ee_wimg(W2, W3, c->ee_wimg, st);
   }
+  // bf16 hi/lo images of every matrix the tensor-core node track multiplies by
+  c->wsplit.clear();
+  auto reg = [&](const float* W, size_t numel, int cols) {
+    bf16* hi = c->wslab.take<bf16>(numel);
+    bf16* lo = c->wslab.take<bf16>(numel);
+    prep_split(W, cols, (int)(numel / cols), 0, cols, hi, lo, st);
+    c->wsplit[W] = {numel, {hi, lo}};
+  };
+  for (const auto& ps : expected_params()) {
+    const std::string& n = ps.name;
+    if (n.size() < 7 || n.compare(n.size() - 6, 6, "weight") != 0 || ps.numel < 4096) continue;
+    if (n.find("in_proj") != std::string::npos) { reg(c->P(n), ps.numel, 320); continue; }
+    if (n.find("ipa_") != std::string::npos && (n.find("linear_q") != std::string::npos || n.find("linear_kv") != std::string::npos)) continue;
+    int cols = 256;
+    if (n.find("transformer") != std::string::npos || (n.find("trunk.linear_") != std::string::npos)) cols = 320;
+    if (n.find("linear_out") != std::string::npos) cols = IPA_FEAT;
+    if (n.find("trunk.0") != std::string::npos || n.find("trunk.2") != std::string::npos || n.find("final_layer") != std::string::npos) cols = 384;
+    if (n.find("embedder") != std::string::npos || n.find("linear_b.") != std::string::npos || n.find("down_z") != std::string::npos) continue;
+    reg(c->P(n), ps.numel, cols);
+  }
+  for (int b = 0; b < N_BLK; ++b) reg(c->ipa[b].proj_w, (size_t)6816 * 256, 256);
   // Wfh above holds the full [128][384] final-layer image; only its action on h2 (all 384 inputs) is used:
   // final_layer(h2 + x) = Wf h2 + Wf[:, :128] z + Wf[:,128:256] n_i + Wf[:,256:] n_j.
   c->finalized = true;
@@ -273,6 +324,7 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     add((size_t)n_off * 128, 4); add((size_t)n_off * 32, 4);
     add(R * 4, 4); add(R * 3, 4); add(R * 6, 4); add(R * 2, 4); add(R, 4); add(R, 4);
     add(R * L * C_Z, 2); add(R * 128, 2);
+    add(R * IPA_FEAT, 2); add(R * IPA_FEAT, 2); add(R * 6144, 2); add(R * 2048, 2); add((size_t)B * N_H * L * L, 2);
     c->ws.cap = bytes + 4096;
     S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
     Slab& w = c->ws;
@@ -290,6 +342,8 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->diffuse = w.take<float>(R); c->keybias = w.take<float>(R);
     c->z = w.take<bf16>(R * L * C_Z);
     c->nprime_bf16 = w.take<bf16>(R * 128);
+    c->sa_hi = w.take<bf16>(R * IPA_FEAT); c->sa_lo = w.take<bf16>(R * IPA_FEAT);
+    c->qkv_bf16 = w.take<bf16>(R * 6144); c->vT = w.take<bf16>(R * 2048); c->P_bf16 = w.take<bf16>((size_t)B * N_H * L * L);
     c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
   }
   // relative-position table: Tpos[r] = W1[:,66:98] pos(d_min + r)   (denoising_ipa.py:144-149)
@@ -334,14 +388,43 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   const int R = B * L;
   const IpaW& w = c->ipa[blk];
   const std::string ip = "translator.trunk.ipa_" + std::to_string(blk) + ".";
-  linear(c, node, 256, w.proj_w, 256, w.proj_b, c->proj, 6816, R, 6816, 256, st);
+  const bool tc = c->opt_node == 1 && L % 16 == 0;
+  const float qk_scale = 0.03608439182435161f;  // sqrt(1 / (3 * 256))   (ipa.py:187)
+  if (tc) {
+    // q | k | v projection in one bf16 tensor-core GEMM whose epilogue writes the attention operands directly:
+    // row-major bf16 q,k (K-major for q.k^T) and the transposed v (K-major for P.v); no fp32 copy is needed.
+    split_bf16(node, 256, R, 256, c->sa_hi, c->sa_lo, st);
+    const auto ws = weight_split(c, w.proj_w);
+    TcGemm g;
+    g.A_hi = c->sa_hi; g.a_rows = R; g.a_cols = 256; g.a_pitch = 256;
+    g.B_hi = ws.first; g.b_rows = 6144; g.b_cols = 256; g.b_pitch = 256;
+    g.M = R; g.N = 6144; g.K = 256; g.passes = 1; g.bias = w.proj_b;
+    g.out_hi = c->qkv_bf16; g.ldo = 6144; g.out_vt = c->vT; g.vt_L = L;
+    gemm_tc(g, st);
+    // point projections keep split-bf16 accuracy (they become nm-scale coordinates)
+    TcGemm p;
+    p.A_hi = c->sa_hi; p.A_lo = c->sa_lo; p.a_rows = R; p.a_cols = 256; p.a_pitch = 256;
+    p.B_hi = ws.first + (size_t)6144 * 256; p.B_lo = ws.second + (size_t)6144 * 256; p.b_rows = 672; p.b_cols = 256; p.b_pitch = 256;
+    p.M = R; p.N = 672; p.K = 256; p.passes = 3; p.bias = w.proj_b + 6144;
+    p.C = c->proj + 6144; p.ldc = 6816;
+    gemm_tc(p, st);
+  } else {
+    linear(c, node, 256, w.proj_w, 256, w.proj_b, c->proj, 6816, R, 6816, 256, st, 0, nullptr, 0, nullptr, nullptr, EXACT);
+  }
   ipa_points(c->proj + 6144, 6816, c->proj + 6336, 6816, quat, trans, c->q_pts, c->k_pts, c->v_pts, R, st);
-  {  // S = sqrt(1/(3*256)) q.k     (ipa.py:183-187)
+  if (tc) {  // S = scale * q.k^T, batched over (decoy, head)
+    TcGemm g;
+    g.A_hi = c->qkv_bf16; g.a_rows = R; g.a_cols = 6144; g.a_pitch = 6144; g.a_rb = L; g.a_ch = 256;
+    g.B_hi = c->qkv_bf16 + 2048; g.b_rows = R; g.b_cols = 4096; g.b_pitch = 6144; g.b_rb = L; g.b_ch = 512;
+    g.M = L; g.N = L; g.K = 256; g.nb = B; g.nh = N_H; g.passes = 1; g.alpha = qk_scale;
+    g.C = c->S; g.ldc = L; g.sCb = (long)N_H * L * L; g.sCh = (long)L * L;
+    gemm_tc(g, st);
+  } else {
     GemmArgs g;
     g.A = c->proj; g.lda = 6816; g.sAb = (long)L * 6816; g.sAh = 256;
     g.B = c->proj + 2048; g.ldb = 6816; g.sBb = (long)L * 6816; g.sBh = 512;
     g.C = c->S; g.ldc = L; g.sCb = (long)N_H * L * L; g.sCh = (long)L * L;
-    g.M = L; g.N = L; g.K = 256; g.nb = B; g.nh = N_H; g.alpha = 0.03608439182435161f;
+    g.M = L; g.N = L; g.K = 256; g.nb = B; g.nh = N_H; g.alpha = qk_scale;
     gemm_f32(g, st);
   }
   ipa_point_logits(c->S, c->q_pts, c->k_pts, w.pt_w, B, L, st);
@@ -350,15 +433,26 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   p.Wb_hi = w.Wb_hi; p.Wb_lo = w.Wb_lo; p.bb = c->P(ip + "linear_b.bias");
   p.Wdz_t = w.Wdz_t; p.bdz = c->P(ip + "down_z.bias");
   p.o_pair = c->feats + (N_H * C_H + 4 * N_H * P_V); p.ld_opair = IPA_FEAT;
+  p.P_bf16 = tc ? c->P_bf16 : nullptr;
   ipa_pair_attention(p, st);
-  {  // o = P v  -> feats[:, h*256 + c]
+  if (tc) {  // o = P v -> feats[:, h*256 + c]
+    TcGemm g;
+    g.A_hi = c->P_bf16; g.a_rows = (size_t)B * N_H * L; g.a_cols = L; g.a_pitch = L; g.a_rb = N_H * L; g.a_rh = L;
+    g.B_hi = c->vT; g.b_rows = (size_t)B * N_H * C_H; g.b_cols = L; g.b_pitch = L; g.b_rb = N_H * C_H; g.b_rh = C_H;
+    g.M = L; g.N = C_H; g.K = L; g.nb = B; g.nh = N_H; g.passes = 1;
+    g.C = c->feats; g.ldc = IPA_FEAT; g.sCb = (long)L * IPA_FEAT; g.sCh = C_H;
+    gemm_tc(g, st);
+  }
+  {
     GemmArgs g;
     g.A = c->S; g.lda = L; g.sAb = (long)N_H * L * L; g.sAh = (long)L * L;
-    g.B = c->proj + 2048 + 256; g.ldb = 6816; g.sBb = (long)L * 6816; g.sBh = 512; g.b_kn = 1;
-    g.C = c->feats; g.ldc = IPA_FEAT; g.sCb = (long)L * IPA_FEAT; g.sCh = 256;
-    g.M = L; g.N = 256; g.K = L; g.nb = B; g.nh = N_H;
-    gemm_f32(g, st);
-    // o_pt (global frame) = P v_pts
+    g.M = L; g.K = L; g.nb = B; g.nh = N_H; g.b_kn = 1;
+    if (!tc) {  // o = P v  (exact path)
+      g.B = c->proj + 2048 + 256; g.ldb = 6816; g.sBb = (long)L * 6816; g.sBh = 512;
+      g.C = c->feats; g.ldc = IPA_FEAT; g.sCb = (long)L * IPA_FEAT; g.sCh = 256; g.N = 256;
+      gemm_f32(g, st);
+    }
+    // o_pt (global frame) = P v_pts : 36 columns per head, exact fp32
     g.B = c->v_pts; g.ldb = N_H * P_V * 3; g.sBb = (long)L * N_H * P_V * 3; g.sBh = P_V * 3;
     g.C = c->opt; g.ldc = N_H * P_V * 3; g.sCb = (long)L * N_H * P_V * 3; g.sCh = P_V * 3;
     g.N = P_V * 3;
@@ -366,7 +460,7 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   }
   ipa_finalize_points(c->opt, quat, trans, c->feats, R, st);
   linear(c, c->feats, IPA_FEAT, c->P(ip + "linear_out.weight"), IPA_FEAT, c->P(ip + "linear_out.bias"), out, 256, R, 256,
-         IPA_FEAT, st, 0, res, 256, nullptr, row_post);
+         IPA_FEAT, st, 0, res, 256, nullptr, row_post, TC3);
 }
 
 void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z_in, const float* rmask,
@@ -423,6 +517,7 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
   const int R = B * L;
   const std::string tk = "translator.trunk.";
   make_masks(rmask, fixed, c->diffuse, c->keybias, R, st);
+  c->cur_prec = TC3;  // residual-stream layers: split-bf16 tensor-core GEMMs (exact fp32 when node_gemm = 0)
   S2S_CUDA(cudaMemcpyAsync(c->init_node, c->node, (size_t)R * 256 * 4, cudaMemcpyDeviceToDevice, st));
   split_rigids(rigids_t, c->quat, c->trans, R, st);
   for (int b = 0; b < N_BLK; ++b) {
@@ -442,14 +537,15 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
     linear(c, c->b256, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), c->a256, 256, R, 256, 256, st, 0, c->node, 256);
     layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, R, 256, st);
     // backbone update on node * diffuse_mask, exact fp32    (ipa.py:367-369)
-    linear(c, c->node, 256, c->P(tk + "bb_update_" + s + ".linear.weight"), 256, c->P(tk + "bb_update_" + s + ".linear.bias"), c->upd6, 6, R, 6, 256, st, 0, nullptr, 0, c->diffuse);
+    linear(c, c->node, 256, c->P(tk + "bb_update_" + s + ".linear.weight"), 256, c->P(tk + "bb_update_" + s + ".linear.bias"), c->upd6, 6, R, 6, 256, st, 0, nullptr, 0, c->diffuse, nullptr, EXACT);
     frame_update(c->quat, c->trans, c->upd6, c->diffuse, R, st);
     if (b < N_BLK - 1) do_edge_transition(c, b, B, L, c->node, c->z, rmask, c->z, st);
   }
   const std::string tp = "translator.torsion_pred.";
   linear(c, c->node, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1);
   linear(c, c->a256, 256, c->P(tp + "linear_2.weight"), 256, c->P(tp + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 0, c->node, 256);
-  linear(c, c->b256, 256, c->P(tp + "linear_final.weight"), 256, c->P(tp + "linear_final.bias"), c->psi_u, 2, R, 2, 256, st);
+  linear(c, c->b256, 256, c->P(tp + "linear_final.weight"), 256, c->P(tp + "linear_final.bias"), c->psi_u, 2, R, 2, 256, st, 0, nullptr, 0, nullptr, nullptr, EXACT);
+  c->cur_prec = EXACT;
   psi_finalize(c->psi_u, gt_psi, fixed, out_psi, R, st);
   join_rigids(c->quat, c->trans, out_rigids, R, st);
 }

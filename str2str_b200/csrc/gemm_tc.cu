@@ -1,0 +1,256 @@
+// Tensor-core GEMM for the node track:  C = epilogue(A * B^T)  with A [M][K] and B [N][K] bf16, K-major, fetched by
+// TMA tensor maps into SWIZZLE_128B operand blocks, tcgen05.mma (128x128x16) into double-buffered TMEM accumulators,
+// epilogue from TMEM by four warps.  Persistent CTAs loop over 128x128 output tiles.
+//
+// passes = 1: plain bf16 product (IPA q/k/v projections, q.k^T, P.V — tools/precision_probe.py shows these tolerate it)
+// passes = 3: split-bf16 product  A_hi B_hi + A_lo B_hi + A_hi B_lo  accumulated in fp32 (≈16 mantissa bits per operand)
+//             for the layers of the residual stream that do not tolerate single bf16 rounding.
+#include "s2s_internal.cuh"
+#include "tc_common.cuh"
+
+namespace s2s {
+
+using namespace tc;
+
+namespace {
+
+constexpr int G_SMEM_RING = 12 * TILE_BYTES;  // 192 KiB of operand blocks: 6 stages x 2 blocks, or 3 stages x 4 blocks
+constexpr int G_OFF_BAR = G_SMEM_RING;
+constexpr int G_SMEM = G_OFF_BAR + 32 * 8 + 16;
+
+struct TcKernelArgs {
+  int a_cb, a_ch, a_rb, a_rh;  // A box coordinates: col = ib*a_cb + ih*a_ch + kb*64, row = ib*a_rb + ih*a_rh + m0
+  int b_cb, b_ch, b_rb, b_rh;
+  int M, N, K, nb, nh, passes, relu, vt_L;
+  float alpha;
+  const float *bias, *row_pre, *row_post, *res;
+  float* C;
+  long ldc, sCb, sCh, ldres;
+  bf16 *out_hi, *out_lo;  // optional dense bf16 copies of the result, row pitch ldo (non-batched calls only)
+  long ldo;
+  bf16* out_vt;           // optional transposed bf16 copy of the v columns of the q|kv projection
+};
+
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+               const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, TcKernelArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
+  uint64_t* s_full = bars;        // [6]
+  uint64_t* s_empty = bars + 6;   // [6]
+  uint64_t* acc_full = bars + 12;   // [2]
+  uint64_t* acc_empty = bars + 14;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int blocks_per_stage = a.passes == 3 ? 4 : 2;
+  const int n_stages = 12 / blocks_per_stage;
+  const uint32_t stage_bytes = blocks_per_stage * TILE_BYTES;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 6; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int MT = (a.M + TM - 1) / TM, NT = (a.N + 127) / 128, KB = (a.K + KBLK - 1) / KBLK;
+  const int n_tiles = a.nb * a.nh * MT * NT;
+  constexpr uint32_t IDESC = make_idesc(128, 128);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int nt = tile % NT, mt = (tile / NT) % MT, bz = tile / (NT * MT);
+        const int ib = bz / a.nh, ih = bz % a.nh;
+        const int arow = ib * a.a_rb + ih * a.a_rh + mt * TM, acol = ib * a.a_cb + ih * a.a_ch;
+        const int brow = ib * a.b_rb + ih * a.b_rh + nt * 128, bcol = ib * a.b_cb + ih * a.b_ch;
+        for (int kb = 0; kb < KB; ++kb, ++cnt) {
+          const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
+          mbar_wait(&s_empty[s], ph ^ 1);
+          mbar_expect_tx(&s_full[s], stage_bytes);
+          unsigned char* st = smem + s * stage_bytes;
+          tma_load_2d(st, &mAh, acol + kb * KBLK, arow, &s_full[s]);
+          tma_load_2d(st + TILE_BYTES, &mBh, bcol + kb * KBLK, brow, &s_full[s]);
+          if (a.passes == 3) {
+            tma_load_2d(st + 2 * TILE_BYTES, &mAl, acol + kb * KBLK, arow, &s_full[s]);
+            tma_load_2d(st + 3 * TILE_BYTES, &mBl, bcol + kb * KBLK, brow, &s_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t cnt = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[ab], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + ab * 128;
+        for (int kb = 0; kb < KB; ++kb, ++cnt) {
+          const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
+          mbar_wait(&s_full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * stage_bytes);
+          const int ksteps = (min(KBLK, a.K - kb * KBLK) + 15) / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t dah = smem_desc_sw128(st + k * 32), dbh = smem_desc_sw128(st + TILE_BYTES + k * 32);
+            umma_bf16(d, dah, dbh, IDESC, (kb | k) ? 1u : 0u);
+            if (a.passes == 3) {
+              umma_bf16(d, smem_desc_sw128(st + 2 * TILE_BYTES + k * 32), dbh, IDESC, 1u);
+              umma_bf16(d, dah, smem_desc_sw128(st + 3 * TILE_BYTES + k * 32), IDESC, 1u);
+            }
+          }
+          umma_commit(&s_empty[s]);
+        }
+        umma_commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % NT, mt = (tile / NT) % MT, bz = tile / (NT * MT);
+      const int ib = bz / a.nh, ih = bz % a.nh;
+      const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+      const int m = mt * TM + r;
+      const bool row_ok = m < a.M;
+      const float pre = (row_ok && a.row_pre) ? a.row_pre[m] * a.alpha : a.alpha;
+      const float post = (row_ok && a.row_post) ? a.row_post[m] : 1.f;
+      float* crow = a.C ? a.C + ib * a.sCb + ih * a.sCh + (long)m * a.ldc : nullptr;
+      const float* rrow = a.res ? a.res + ib * a.sCb + ih * a.sCh + (long)m * a.ldres : nullptr;
+      mbar_wait(&acc_full[ab], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ab * 128 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int n0 = nt * 128 + c0;
+        if (n0 >= a.N) break;  // warp-uniform
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (!row_ok) continue;
+        const bool full = n0 + 32 <= a.N;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int n = n0 + e;
+          float x = v[e] * pre;
+          if (a.bias && (full || n < a.N)) x += a.bias[n];
+          if (a.relu) x = fmaxf(x, 0.f);
+          x *= post;
+          if (rrow && (full || n < a.N)) x += rrow[n];
+          v[e] = x;
+        }
+        if (crow) {
+          if (full && (a.ldc & 3) == 0) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(crow + n0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          } else {
+            for (int e = 0; e < 32 && n0 + e < a.N; ++e) crow[n0 + e] = v[e];
+          }
+        }
+        if (a.out_hi) {
+          bf16* hrow = a.out_hi + (long)m * a.ldo + n0;
+          bf16* lrow = a.out_lo ? a.out_lo + (long)m * a.ldo + n0 : nullptr;
+          if (full && (a.ldo & 7) == 0) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float x0 = v[e + 2 * u], x1 = v[e + 2 * u + 1];
+                h[u] = pack_bf16(x0, x1);
+                l[u] = pack_bf16(x0 - bf16_round(x0), x1 - bf16_round(x1));
+              }
+              *reinterpret_cast<uint4*>(hrow + e) = make_uint4(h[0], h[1], h[2], h[3]);
+              if (lrow) *reinterpret_cast<uint4*>(lrow + e) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          } else {
+            for (int e = 0; e < 32 && n0 + e < a.N; ++e) {
+              const bf16 h = __float2bfloat16_rn(v[e]);
+              hrow[e] = h;
+              if (lrow) lrow[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h));
+            }
+          }
+        }
+        if (a.out_vt && n0 >= 2048 && ((n0 - 2048) & 511) >= 256) {
+          // v columns of the q|kv projection, transposed: VT[((b*8 + h)*256 + c)*L + j]  (row m = b*L + j)
+          const int h = (n0 - 2048) >> 9, c = ((n0 - 2048) & 511) - 256;
+          const int b = m / a.vt_L, j = m % a.vt_L;
+          bf16* dst = a.out_vt + (((long)b * N_H + h) * C_H + c) * a.vt_L + j;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) dst[(long)e * a.vt_L] = __float2bfloat16_rn(v[e]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ src, long ld, int rows, int cols, bf16* __restrict__ hi,
+                                  bf16* __restrict__ lo) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long n4 = (long)rows * (cols / 4);
+  if (i >= n4) return;
+  const int r = (int)(i / (cols / 4)), c = (int)(i % (cols / 4)) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(src + (long)r * ld + c);
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  uint32_t h[2], l[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    h[u] = pack_bf16(x[2 * u], x[2 * u + 1]);
+    l[u] = pack_bf16(x[2 * u] - bf16_round(x[2 * u]), x[2 * u + 1] - bf16_round(x[2 * u + 1]));
+  }
+  *reinterpret_cast<uint2*>(hi + (long)r * cols + c) = make_uint2(h[0], h[1]);
+  if (lo) *reinterpret_cast<uint2*>(lo + (long)r * cols + c) = make_uint2(l[0], l[1]);
+}
+
+}  // namespace
+
+void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st) {
+  S2S_CHECK(cols % 4 == 0 && ld % 4 == 0, "split_bf16: width must be a multiple of 4");
+  split_bf16_kernel<<<ceil_div((long)rows * (cols / 4), 256), 256, 0, st>>>(src, ld, rows, cols, hi, lo);
+  S2S_LAUNCH_CHECK();
+}
+
+void gemm_tc(const TcGemm& g, cudaStream_t st) {
+  S2S_CHECK(g.K % 16 == 0 && g.K > 0, "gemm_tc: K must be a positive multiple of 16");
+  S2S_CHECK(g.passes == 1 || g.passes == 3, "gemm_tc: passes must be 1 or 3");
+  S2S_CHECK(g.A_hi && g.B_hi && (g.passes == 1 || (g.A_lo && g.B_lo)), "gemm_tc: missing operand");
+  const CUtensorMap mAh = make_bf16_2d_map(g.A_hi, g.a_rows, g.a_cols, g.a_pitch);
+  const CUtensorMap mAl = g.passes == 3 ? make_bf16_2d_map(g.A_lo, g.a_rows, g.a_cols, g.a_pitch) : mAh;
+  const CUtensorMap mBh = make_bf16_2d_map(g.B_hi, g.b_rows, g.b_cols, g.b_pitch);
+  const CUtensorMap mBl = g.passes == 3 ? make_bf16_2d_map(g.B_lo, g.b_rows, g.b_cols, g.b_pitch) : mBh;
+  TcKernelArgs k;
+  k.a_cb = g.a_cb; k.a_ch = g.a_ch; k.a_rb = g.a_rb; k.a_rh = g.a_rh;
+  k.b_cb = g.b_cb; k.b_ch = g.b_ch; k.b_rb = g.b_rb; k.b_rh = g.b_rh;
+  k.M = g.M; k.N = g.N; k.K = g.K; k.nb = g.nb; k.nh = g.nh; k.passes = g.passes; k.relu = g.relu; k.vt_L = g.vt_L;
+  k.alpha = g.alpha; k.bias = g.bias; k.row_pre = g.row_pre; k.row_post = g.row_post; k.res = g.res;
+  k.C = g.C; k.ldc = g.ldc; k.sCb = g.sCb; k.sCh = g.sCh; k.ldres = g.ldres;
+  k.out_hi = g.out_hi; k.out_lo = g.out_lo; k.ldo = g.ldo; k.out_vt = g.out_vt;
+  static bool configured = false;
+  const int smem = G_SMEM + 1024;
+  if (!configured) {
+    S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles = g.nb * g.nh * ceil_div(g.M, TM) * ceil_div(g.N, 128);
+  S2S_PROF("gemm_tc", st);
+  gemm_tc_kernel<<<tiles < sm_count() ? tiles : sm_count(), 192, smem, st>>>(mAh, mAl, mBh, mBl, k);
+  S2S_LAUNCH_CHECK();
+}
+
+}  // namespace s2s

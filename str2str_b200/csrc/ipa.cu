@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) 
       const float pv = j < L ? row[j] * inv : 0.f;
       if (j < L) Srow[j] = pv;
       const bf16 hi = __float2bfloat16_rn(pv);
+      if (a.P_bf16 && j < L) a.P_bf16[(((long)b * N_H + warp) * L + i) * L + j] = hi;
       Ph[warp * LP8 + j] = hi;
       Pl[warp * LP8 + j] = __float2bfloat16_rn(pv - __bfloat162float(hi));
     }

@@ -14,125 +14,17 @@
 //   h2 = relu(W2 h1 + b2)
 //   y  = Wf (h2 + x) + bf = [Wf | Wf[:, :128] | Wf[:,256:]] [h2, z_ij, n'_j] + p_i,   p_i = Wf[:,128:256] n'_i + bf
 //   out = LayerNorm(y) * mask_i * mask_j
-#include <cuda.h>
-
 #include "s2s_internal.cuh"
+#include "tc_common.cuh"
 
 namespace s2s {
 
+using namespace tc;
+
 namespace {
 
-constexpr int TM = 128;                  // pair rows per tile (= UMMA M)
-constexpr int KBLK = 64;                 // bf16 elements per 128-byte swizzle row
-constexpr int TILE_BYTES = TM * KBLK * 2;  // 16 KiB: one [128 x 64] bf16 operand block
 constexpr int ET_RING = 3;
 constexpr int ET_WTILES = 40;            // weight blocks per row tile: 12 (layer 1) + 18 (layer 2) + 10 (final)
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(b)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_bulk_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major, bf16, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-//   start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B between 8-row groups | version 1 | layout 2
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A/B, both K-major, M x N
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-// byte offset of element (row r, column c) inside a [128 x 64] bf16 block in the SW128 K-major layout
-__device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
-}
-
-// one 64-wide K-block of MMAs: D += A_blk * B_blk^T
-__device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_blk, uint32_t b_blk, uint32_t idesc, bool first) {
-#pragma unroll
-  for (int k = 0; k < KBLK / 16; ++k)
-    umma_bf16(d_tmem, smem_desc_sw128(a_blk + k * 32), smem_desc_sw128(b_blk + k * 32), idesc, (first && k == 0) ? 0u : 1u);
-}
-
-// 8 fp32 -> 8 bf16 packed store into the swizzled operand block
-__device__ __forceinline__ void store8_sw128(unsigned char* blk_base, int r, int c, const float* h) {
-  uint4 pk = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-  *reinterpret_cast<uint4*>(blk_base + sw128_offset(r, c)) = pk;
-}
 
 // ---- fused EdgeTransition -----------------------------------------------------------------------------------------
 struct EtTcArgs {
@@ -540,11 +432,14 @@ EncodeTiledFn encode_tiled() {
   }
   return fn;
 }
-// [rows][128] bf16 row-major tensor, boxes of 128 rows x 64 columns, 128-byte swizzle
-CUtensorMap make_rows128_map(const void* base, size_t rows) {
+}  // namespace
+
+// [rows][cols] bf16 row-major tensor (row pitch in elements), boxes of 128 rows x 64 columns, 128-byte swizzle;
+// out-of-bounds box elements read as zero
+CUtensorMap make_bf16_2d_map(const void* base, size_t rows, size_t cols, size_t row_pitch_elems) {
   CUtensorMap m;
-  cuuint64_t dims[2] = {(cuuint64_t)C_Z, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)C_Z * 2};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_pitch_elems * 2};
   cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)TM};
   cuuint32_t estr[2] = {1, 1};
   const CUresult rc = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -562,8 +457,6 @@ int sm_count() {
   }
   return n;
 }
-
-}  // namespace
 
 size_t et_wimg_elems() { return (size_t)ET_WTILES * TM * KBLK; }
 size_t ee_wimg_elems() { return (size_t)4 * TM * KBLK; }
@@ -603,8 +496,8 @@ void edge_transition_tc(const EdgeTransitionArgs& a, cudaStream_t st) {
   S2S_CHECK(a.L % TM == 0, "edge_transition_tc needs L % 128 == 0");
   S2S_CHECK(a.wimg && a.nprime_bf16, "edge_transition_tc: weight image / bf16 node embedding missing");
   const size_t rows = (size_t)a.B * a.L * a.L;
-  const CUtensorMap mz = make_rows128_map(a.z_in, rows);
-  const CUtensorMap mn = make_rows128_map(a.nprime_bf16, (size_t)a.B * a.L);
+  const CUtensorMap mz = make_bf16_2d_map(a.z_in, rows, C_Z, C_Z);
+  const CUtensorMap mn = make_bf16_2d_map(a.nprime_bf16, (size_t)a.B * a.L, C_Z, C_Z);
   EtTcArgs k;
   k.wimg = a.wimg; k.u = a.u; k.p = a.p; k.b2 = a.b2; k.ln_w = a.ln_w; k.ln_b = a.ln_b; k.mask = a.mask;
   k.z_out = a.z_out; k.L = a.L; k.n_tiles = (int)(rows / TM);

@@ -20,8 +20,21 @@ struct GemmArgs {
   float alpha = 1.f;
 };
 void gemm_f32(const GemmArgs& g, cudaStream_t st);
-// tensor-core variants (gemm_tc.cu): bf16 operands, fp32 accumulate; passes = 1 (plain) or 3 (hi/lo split)
-void gemm_tc(const GemmArgs& g, int passes, cudaStream_t st);
+// tensor-core GEMM (gemm_tc.cu): C = epilogue(A B^T), bf16 K-major operands via TMA, fp32 accumulate in TMEM.
+// Operand tensors are [rows][cols] bf16 with a row pitch; the box of tile (m0 | n0), batch (ib, ih), k-block kb is at
+// row = ib*rb + ih*rh + m0, col = ib*cb + ih*ch + kb*64.  passes = 1 (plain bf16) or 3 (hi/lo split, needs *_lo).
+struct TcGemm {
+  const bf16 *A_hi = nullptr, *A_lo = nullptr; size_t a_rows = 0, a_cols = 0, a_pitch = 0; int a_cb = 0, a_ch = 0, a_rb = 0, a_rh = 0;
+  const bf16 *B_hi = nullptr, *B_lo = nullptr; size_t b_rows = 0, b_cols = 0, b_pitch = 0; int b_cb = 0, b_ch = 0, b_rb = 0, b_rh = 0;
+  int M = 0, N = 0, K = 0, nb = 1, nh = 1, passes = 1, relu = 0, vt_L = 0;
+  float alpha = 1.f;
+  const float *bias = nullptr, *row_pre = nullptr, *row_post = nullptr, *res = nullptr; long ldres = 0;
+  float* C = nullptr; long ldc = 0, sCb = 0, sCh = 0;
+  bf16 *out_hi = nullptr, *out_lo = nullptr; long ldo = 0;  // optional bf16 (split) copies of the result
+  bf16* out_vt = nullptr;                                    // optional transposed copy of the v columns (q|kv projection)
+};
+void gemm_tc(const TcGemm& g, cudaStream_t st);
+void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st);
 
 // ---- rows.cu ------------------------------------------------------------------------------------------
 void layernorm(const float* x, const float* res, const float* w, const float* b, const float* rowscale, float* y,
@@ -107,6 +120,7 @@ struct IpaPairArgs {
   const float* bdz;    // [32]
   float* o_pair;       // [B*L] rows, H*32 wide, row stride ld_opair
   long ld_opair;
+  bf16* P_bf16 = nullptr;  // optional bf16 copy of the attention weights [B,H,L,L] (A operand of the tensor-core P.V)
 };
 void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st);
 void ipa_finalize_points(const float* opt_glob, const float* quat, const float* trans, float* feats, int rows,

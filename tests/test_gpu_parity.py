@@ -16,7 +16,8 @@ from oracle import str2str_oracle as O
 from str2str_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
-PAIR_MODES = [int(v) for v in os.environ.get("S2S_TEST_PAIR_MODES", "0,1").split(",")]
+# (pair_kernels, node_gemm): 0/0 = SIMT pair kernels + exact fp32 node GEMMs, 1/1 = tcgen05 everywhere (the default)
+PAIR_MODES = [(0, 0), (1, 0), (1, 1)]
 
 
 def rel(a, b):
@@ -28,7 +29,9 @@ def load(golden_dir, name):
     return {k: torch.as_tensor(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
 
 
-def make_net(params, pair_kernels=1, node_gemm=0):
+def make_net(params, pair_kernels=1, node_gemm=1):
+    if isinstance(pair_kernels, tuple):
+        pair_kernels, node_gemm = pair_kernels
     from str2str_b200.net import DenoisingNet, EmbeddingModule, TranslationIPA
 
     net = DenoisingNet(
@@ -89,7 +92,7 @@ def test_ipa_block_vs_oracle(golden_dir, params):
 
     g = load(golden_dir, "net_forward_small.npz")
     f = small_feats(g)
-    net = make_net(params, 0)
+    net = make_net(params, 0, 0)
     nm = f["residue_mask"].float()
     node = g["node_embed"] * nm[..., None]
     edge = (g["edge_embed"] * (nm[..., None] * nm[..., None, :])[..., None]).bfloat16().float()  # what the kernel is fed
@@ -192,7 +195,7 @@ def test_trajectory_cfg1_vs_reference_golden(golden_dir, params, pair, graph):
 
 
 def test_trajectory_masked_vs_reference_golden(golden_dir, params):
-    _run_traj(golden_dir, params, "traj_masked_L24_n6.npz", 1, True)
+    _run_traj(golden_dir, params, "traj_masked_L24_n6.npz", (1, 1), True)
 
 
 @pytest.mark.parametrize("L", [128, 256])
@@ -207,7 +210,7 @@ def test_pair_kernels_tc_vs_simt(params, L):
     feats["t"] = torch.tensor([0.4, 0.6])
     outs = []
     for pair in (0, 1):
-        net = make_net(params, pair)
+        net = make_net(params, pair, 0)
         eng = net.native("cuda")
         fc = cuda(feats)
         eng.reserve(B, L, fc["residue_idx"])
@@ -242,3 +245,45 @@ def test_se3_equivariance_full_size(params):
         b = net(cuda(moved), as_tensor_7=True)["rigids"].cpu()
     expect = a[..., 4:] @ Rg.T + tg
     assert rel(b[..., 4:], expect) < 2e-5
+
+
+@pytest.mark.parametrize("L", [64, 128])
+def test_ipa_block_tensor_core_vs_oracle(params, L):
+    """IPA block with the tensor-core projections / q.k^T / P.v (node_gemm=1) against the fp32 oracle."""
+    from str2str_b200.rigid import Rigid
+
+    B = 2
+    g = torch.Generator().manual_seed(17)
+    node = torch.randn(B, L, 256, generator=g)
+    edge = torch.randn(B, L, L, 128, generator=g).bfloat16().float()
+    q, x = synthetic.make_backbone(L, seed=17)
+    rig = torch.cat([q, 0.1 * x], -1)[None].repeat(B, 1, 1) + 0.05 * torch.randn(B, L, 7, generator=g)
+    nm = torch.ones(B, L)
+    nm[:, -3:] = 0
+    net = make_net(params, 1, 1)
+    out = net.translator.trunk["ipa_1"](node.cuda(), edge.cuda(), Rigid.from_tensor_7(rig.cuda()), nm.cuda())
+    ref = O.ipa(params, "translator.trunk.ipa_1.", node, edge, rig[..., :4], rig[..., 4:], nm)
+    valid = nm.bool()
+    r = rel(out.cpu()[valid], ref[valid])
+    print(f"ipa tensor-core path L={L}: rel {r:.2e}")
+    assert r < 5e-3  # single-pass bf16 projections / logits / P.v by design (tools/precision_probe.py)
+
+
+def test_forward_tensor_core_vs_exact_L128(params):
+    """Whole network forward: tcgen05 everywhere against SIMT pair kernels + exact fp32 node GEMMs."""
+    B, L = 2, 128
+    feats = synthetic.make_features(B, L, seed=19, n_pad=4, n_fixed=2)
+    q, x = synthetic.make_backbone(L, seed=19)
+    g = torch.Generator().manual_seed(2)
+    feats["rigids_t"] = (torch.cat([q, x], -1)[None].repeat(B, 1, 1) + 0.2 * torch.randn(B, L, 7, generator=g)).float()
+    feats["sc_ca_t"] = (x[None] + torch.randn(B, L, 3, generator=g)).float()
+    feats["t"] = torch.tensor([0.35, 0.35])
+    outs = []
+    for mode in ((0, 0), (1, 1)):
+        net = make_net(params, mode)
+        with torch.no_grad():
+            outs.append(net(cuda(feats), as_tensor_7=True)["rigids"].cpu())
+    valid = feats["residue_mask"].bool()
+    r = rel(outs[1][valid][:, 4:], outs[0][valid][:, 4:])
+    print(f"forward L=128 tensor-core vs exact: C-alpha rel {r:.2e}")
+    assert r < 2e-5
