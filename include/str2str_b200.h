@@ -43,7 +43,8 @@ int s2s_set_param(s2s_ctx* ctx, const char* name, const float* data, int64_t num
 /* Check that all 274 tensors are present with the right sizes and build the derived device tensors
  * (bf16 / split / transposed weight images, concatenated projections, softplus head weights). */
 int s2s_finalize(s2s_ctx* ctx, void* stream);
-/* Options: "pair_kernels" 0 = SIMT cross-check kernels, 1 = tcgen05 kernels (default);
+/* Options: "pair_kernels" 0 = SIMT cross-check kernels, 1 = tcgen05 kernels (default), 2 = tcgen05 with the
+ *                         first-generation EdgeTransition kernel (serial MMA/epilogue; kept for A/B timing);
  *          "node_gemm"    0 = exact fp32 FFMA everywhere, 1 = tensor-core GEMMs where the parity budget allows. */
 int s2s_set_option(s2s_ctx* ctx, const char* key, int value);
 /* Size the workspace for (B, L) and build the relative-position table for residue-index offsets in

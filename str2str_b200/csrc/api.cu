@@ -97,7 +97,7 @@ struct IpaW {
 };
 struct EtW {
   bf16 *W1z, *W2, *Wfh, *Wfz, *W1zt, *W2t, *Wft, *Wfzt;
-  bf16* wimg;  // tcgen05 weight image
+  bf16 *wimg, *wimg2;  // tcgen05 weight images (first / second generation kernel)
 };
 
 }  // namespace
@@ -266,6 +266,8 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
       prep_split(Wf, 384, 128, 0, 128, x.Wfz, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 128, x.Wfzt, st);
       x.wimg = c->wslab.take<bf16>(et_wimg_elems());
       build_et_wimg(W1, W2, Wf, x.wimg, st);
+      x.wimg2 = c->wslab.take<bf16>(et2_wimg_elems());
+      build_et2_wimg(W1, W2, Wf, x.wimg2, st);
     }
   }
   {
@@ -379,7 +381,7 @@ void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, c
   a.z_out = z_out; a.wimg = c->ee_wimg;
   // the tcgen05 kernels work on 128-row tiles of one (b, i): chain lengths that are not a multiple of 128 take the
   // SIMT kernels (same inputs, same rounding points)
-  if (c->opt_pair == 1 && L % 128 == 0) edge_embed_tc(a, st); else edge_embed_simt(a, st);
+  if (c->opt_pair >= 1 && L % 128 == 0) edge_embed_tc(a, st); else edge_embed_simt(a, st);
 }
 
 // InvariantPointAttention.forward of block blk -> out (linear_out result; not yet masked)
@@ -469,7 +471,7 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   const std::string e = "translator.trunk.edge_transition_" + std::to_string(blk) + ".";
   const float *W1 = c->P(e + "trunk.0.weight"), *Wf = c->P(e + "final_layer.weight");
   linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st);
-  const bool tc = c->opt_pair == 1 && L % 128 == 0;
+  const bool tc = c->opt_pair >= 1 && L % 128 == 0;
   linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st);
   linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st);
   if (tc) {  // the n'_j terms ride along as extra K columns of the MMAs
@@ -484,8 +486,10 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   a.W1z = w.W1z; a.W2 = w.W2; a.Wfh = w.Wfh; a.Wfz = w.Wfz;
   a.W1zt = w.W1zt; a.W2t = w.W2t; a.Wft = w.Wft; a.Wfzt = w.Wfzt;
   a.b2 = c->P(e + "trunk.2.bias"); a.ln_w = c->P(e + "layer_norm.weight"); a.ln_b = c->P(e + "layer_norm.bias");
-  a.z_out = z_out; a.wimg = w.wimg; a.nprime_bf16 = c->nprime_bf16;
-  if (tc) edge_transition_tc(a, st); else edge_transition_simt(a, st);
+  a.z_out = z_out; a.wimg = w.wimg; a.wimg2 = w.wimg2; a.nprime_bf16 = c->nprime_bf16;
+  if (!tc) edge_transition_simt(a, st);
+  else if (c->opt_pair == 2) edge_transition_tc(a, st);  // first-generation kernel (serial MMA / epilogue), kept for A/B
+  else edge_transition_tc2(a, st);
 }
 
 void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {
@@ -627,7 +631,7 @@ int s2s_set_option(s2s_ctx* c, const char* key, int value) {
   return guarded([&] {
     S2S_CHECK(c && key, "null argument");
     const std::string k = key;
-    if (k == "pair_kernels") { S2S_CHECK(value == 0 || value == 1, "pair_kernels: 0|1"); c->opt_pair = value; }
+    if (k == "pair_kernels") { S2S_CHECK(value >= 0 && value <= 2, "pair_kernels: 0|1|2"); c->opt_pair = value; }
     else if (k == "node_gemm") { S2S_CHECK(value == 0 || value == 1, "node_gemm: 0|1"); c->opt_node = value; }
     else S2S_CHECK(false, "unknown option " + k);
   });

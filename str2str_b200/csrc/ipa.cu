@@ -48,36 +48,46 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
 
 // S[b,h,i,j] += -0.5 * w_h * sum_p |q_pts[b,i,h,p] - k_pts[b,j,h,p]|^2      (ipa.py:191-205)
 // Direct differences in fp32: the |q|^2+|k|^2-2q.k expansion cancels catastrophically for nm-scale coordinates.
+// Block = 32 queries x 64 keys of one (decoy, head); a thread keeps one key's 8 points in registers and walks 8 queries.
 __global__ void __launch_bounds__(256) ipa_point_logits_kernel(float* __restrict__ S, const float* __restrict__ q_pts,
                                                                const float* __restrict__ k_pts,
                                                                const float* __restrict__ pt_w, int L) {
-  __shared__ float qs[8][P_Q * 3];
-  __shared__ float ks[32][P_Q * 3 + 1];
+  __shared__ float qs[32][P_Q * 3];
   const int bh = blockIdx.z, b = bh / N_H, h = bh % N_H;
-  const int i0 = blockIdx.y * 8, j0 = blockIdx.x * 32;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 64;
   const int tid = threadIdx.x;
-  if (tid < 8 * 24) {
-    const int il = tid / 24, c = tid % 24;
+  for (int idx = tid; idx < 32 * 24; idx += 256) {
+    const int il = idx / 24, c = idx % 24;
     qs[il][c] = (i0 + il < L) ? q_pts[(((long)b * L + i0 + il) * N_H + h) * 24 + c] : 0.f;
   }
-  for (int idx = tid; idx < 32 * 24; idx += 256) {
-    const int jl = idx / 24, c = idx % 24;
-    ks[jl][c] = (j0 + jl < L) ? k_pts[(((long)b * L + j0 + jl) * N_H + h) * 24 + c] : 0.f;
+  const int jl = tid % 64, ig = tid / 64;
+  const int j = j0 + jl;
+  float kp[24];
+  if (j < L) {
+    const float4* src = reinterpret_cast<const float4*>(k_pts + (((long)b * L + j) * N_H + h) * 24);
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const float4 v = __ldg(src + u);
+      kp[4 * u] = v.x; kp[4 * u + 1] = v.y; kp[4 * u + 2] = v.z; kp[4 * u + 3] = v.w;
+    }
   }
   __syncthreads();
-  const int il = tid / 32, jl = tid % 32;
-  const int i = i0 + il, j = j0 + jl;
-  if (i >= L || j >= L) return;
+  if (j >= L) return;
   const float w = pt_w[h];
-  float acc = 0.f;
 #pragma unroll
-  for (int p = 0; p < P_Q; ++p) {
-    const float dx = qs[il][p * 3] - ks[jl][p * 3];
-    const float dy = qs[il][p * 3 + 1] - ks[jl][p * 3 + 1];
-    const float dz = qs[il][p * 3 + 2] - ks[jl][p * 3 + 2];
-    acc += (dx * dx + dy * dy + dz * dz) * w;
+  for (int u = 0; u < 8; ++u) {
+    const int il = ig * 8 + u, i = i0 + il;
+    if (i >= L) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int p = 0; p < P_Q; ++p) {
+      const float dx = qs[il][p * 3] - kp[p * 3];
+      const float dy = qs[il][p * 3 + 1] - kp[p * 3 + 1];
+      const float dz = qs[il][p * 3 + 2] - kp[p * 3 + 2];
+      acc += (dx * dx + dy * dy + dz * dz) * w;
+    }
+    S[(((long)b * N_H + h) * L + i) * L + j] += acc * (-0.5f);
   }
-  S[(((long)b * N_H + h) * L + i) * L + j] += acc * (-0.5f);
 }
 
 // ---- the pair kernel ----------------------------------------------------------------------------------
@@ -252,7 +262,7 @@ void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv
 
 void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const float* pt_w, int B, int L,
                       cudaStream_t st) {
-  dim3 grid(ceil_div(L, 32), ceil_div(L, 8), B * N_H);
+  dim3 grid(ceil_div(L, 64), ceil_div(L, 32), B * N_H);
   ipa_point_logits_kernel<<<grid, 256, 0, st>>>(S, q_pts, k_pts, pt_w, L);
   S2S_LAUNCH_CHECK();
 }

@@ -318,23 +318,29 @@ __global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
       ti_s[wt] = e.Ti[(size_t)bi * C_Z + wt];
       named_bar_sync(1, 128);
       // layer 1 by table lookups (reference denoising_ipa.py:126-158): time/fixed features of i and j, relative
-      // position, self-conditioning distogram bin
-      const int bin = pair_distogram_bin(e.sc_ca + (size_t)bi * 3, e.sc_ca + bj * 3, edge_s);
-      const int off = (int)(e.ridx[bi] - e.ridx[bj]) - e.d_min;
-      const float4* tj = reinterpret_cast<const float4*>(e.Tj + bj * C_Z);
-      const float4* tp = reinterpret_cast<const float4*>(e.Tpos + (size_t)off * C_Z);
-      const float* wd = wd_s + (bin >= 0 ? bin : 0) * WD_PITCH;
-      const float wdm = bin >= 0 ? 1.f : 0.f;
-#pragma unroll 2
-      for (int c = 0; c < C_Z; c += 8) {
-        const float4 j0v = __ldg(tj + c / 4), j1v = __ldg(tj + c / 4 + 1);
-        const float4 p0v = __ldg(tp + c / 4), p1v = __ldg(tp + c / 4 + 1);
-        const float tjv[8] = {j0v.x, j0v.y, j0v.z, j0v.w, j1v.x, j1v.y, j1v.z, j1v.w};
-        const float tpv[8] = {p0v.x, p0v.y, p0v.z, p0v.w, p1v.x, p1v.y, p1v.z, p1v.w};
-        float h[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) h[k] = fmaxf(ti_s[c + k] + tjv[k] + tpv[k] + wdm * wd[c + k], 0.f);
-        store8_sw128(abuf + (c / KBLK) * TILE_BYTES, r, c % KBLK, h);
+      // position, self-conditioning distogram bin.  Each lane first classifies one of its warp's 32 rows, then the warp
+      // walks the rows together so that every table row is one coalesced 512-byte read (lane = 4 channels).
+      {
+        const int bin_l = pair_distogram_bin(e.sc_ca + (size_t)bi * 3, e.sc_ca + bj * 3, edge_s);
+        const int off_l = (int)(e.ridx[bi] - e.ridx[bj]) - e.d_min;
+        const int c = lane * 4;
+        const float4 tiv = *reinterpret_cast<const float4*>(ti_s + c);
+        const size_t bj0 = (size_t)b * e.L + j0 + q * 32;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int bin = __shfl_sync(0xffffffffu, bin_l, rr);
+          const int off = __shfl_sync(0xffffffffu, off_l, rr);
+          const float4 tjv = __ldg(reinterpret_cast<const float4*>(e.Tj + (bj0 + rr) * C_Z + c));
+          const float4 tpv = __ldg(reinterpret_cast<const float4*>(e.Tpos + (size_t)off * C_Z + c));
+          float4 h = make_float4(tiv.x + tjv.x + tpv.x, tiv.y + tjv.y + tpv.y, tiv.z + tjv.z + tpv.z, tiv.w + tjv.w + tpv.w);
+          if (bin >= 0) {
+            const float4 wv = *reinterpret_cast<const float4*>(wd_s + bin * WD_PITCH + c);
+            h.x += wv.x; h.y += wv.y; h.z += wv.z; h.w += wv.w;
+          }
+          const int row = q * 32 + rr;
+          *reinterpret_cast<uint2*>(abuf + (c / KBLK) * TILE_BYTES + sw128_offset(row, c % KBLK)) =
+              make_uint2(pack_bf16(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f)), pack_bf16(fmaxf(h.z, 0.f), fmaxf(h.w, 0.f)));
+        }
       }
       fence_proxy_async();
       mbar_arrive(a_full);

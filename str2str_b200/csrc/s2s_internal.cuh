@@ -95,9 +95,13 @@ struct EdgeTransitionArgs {
   bf16* z_out;        // may alias z_in
   const bf16* wimg = nullptr;         // tcgen05 path: pre-swizzled weight blocks (build_et_wimg)
   const bf16* nprime_bf16 = nullptr;  // tcgen05 path: n' [B*L][128] in bf16 (the n'_j operand rows)
+  const bf16* wimg2 = nullptr;        // second-generation kernel: 8 KB weight blocks (build_et2_wimg)
 };
 void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st);
 void edge_transition_tc(const EdgeTransitionArgs& a, cudaStream_t st);
+void edge_transition_tc2(const EdgeTransitionArgs& a, cudaStream_t st);
+size_t et2_wimg_elems();
+void build_et2_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);
 size_t et_wimg_elems();
 size_t ee_wimg_elems();
 void build_et_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);

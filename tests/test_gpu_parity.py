@@ -209,7 +209,7 @@ def test_pair_kernels_tc_vs_simt(params, L):
     feats["sc_ca_t"] = (x[None] + torch.randn(B, L, 3, generator=g)).float()
     feats["t"] = torch.tensor([0.4, 0.6])
     outs = []
-    for pair in (0, 1):
+    for pair in (0, 1, 2):
         net = make_net(params, pair, 0)
         eng = net.native("cuda")
         fc = cuda(feats)
@@ -217,8 +217,9 @@ def test_pair_kernels_tc_vs_simt(params, L):
         node, z = eng.embed(fc["t"], fc["residue_idx"], fc["fixed_mask"].float(), fc["sc_ca_t"], fc["residue_mask"].float())
         z2 = eng.edge_transition(0, node, z, fc["residue_mask"].float().contiguous())
         outs.append((z.float().cpu(), z2.float().cpu()))
-    assert rel(outs[1][0], outs[0][0]) < 3e-3   # bf16 output rounding of slightly different fp32 sums
-    assert rel(outs[1][1], outs[0][1]) < 3e-3
+    for k in (1, 2):
+        assert rel(outs[k][0], outs[0][0]) < 3e-3   # bf16 output rounding of slightly different fp32 sums
+        assert rel(outs[k][1], outs[0][1]) < 3e-3, (k, rel(outs[k][1], outs[0][1]))
 
 
 def test_se3_equivariance_full_size(params):
