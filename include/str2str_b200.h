@@ -115,6 +115,8 @@ int s2s_linear_f32(const float* A, const float* W, const float* bias, float* C, 
 void s2s_profile_enable(int on);
 void s2s_profile_reset(void);
 int s2s_profile_read(const char* name, double* total_ms, int64_t* count);
+/* all recorded names as "name\ttotal_ms\tcount\n" lines; returns the length, or -(needed capacity) if buf is too small */
+int s2s_profile_list(char* buf, int cap);
 
 /* number of kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t s2s_launch_count(void);

@@ -37,6 +37,7 @@ SIGNATURES = {
     "s2s_launch_count": (_i64, []),
     "s2s_profile_enable": (None, [_i]),
     "s2s_profile_reset": (None, []),
+    "s2s_profile_list": (_i, [C.c_char_p, _i]),
     "s2s_profile_read": (_i, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_i64)]),
 }
 

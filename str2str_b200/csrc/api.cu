@@ -1,5 +1,8 @@
 // C ABI (include/str2str_b200.h): context, weight preparation, workspace, and the network forward that
 // strings the kernels together.  Host-side only orchestration; every arithmetic op is a kernel of this library.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -27,6 +30,10 @@ ProfScope::~ProfScope() {
   cudaEventCreate(&e1);
   cudaEventRecord(e1, st);
   g_prof[name].ev.emplace_back(e0, e1);
+}
+const char* prof_intern(const std::string& name) {
+  static std::map<std::string, int> names;
+  return names.emplace(name, 0).first->first.c_str();
 }
 static void prof_drain() {
   for (auto& kv : g_prof) {
@@ -109,6 +116,7 @@ struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
   int opt_pair = 1, opt_node = 0;
+  int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
   float *tfreq = nullptr, *pdenom = nullptr, *bin_lower = nullptr, *backbone = nullptr;
   Slab wslab;  // derived weights
@@ -264,10 +272,14 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
       prep_split(W2, 384, 384, 0, 384, x.W2, nullptr, st);   prep_t_bf16(W2, 384, 384, 0, 384, x.W2t, st);
       prep_split(Wf, 384, 128, 0, 384, x.Wfh, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 384, x.Wft, st);
       prep_split(Wf, 384, 128, 0, 128, x.Wfz, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 128, x.Wfzt, st);
-      x.wimg = c->wslab.take<bf16>(et_wimg_elems());
+      x.wimg = c->wslab.take<bf16>(et_wimg_elems() * c->wimg_copies);
       build_et_wimg(W1, W2, Wf, x.wimg, st);
-      x.wimg2 = c->wslab.take<bf16>(et2_wimg_elems());
+      x.wimg2 = c->wslab.take<bf16>(et2_wimg_elems() * c->wimg_copies);
       build_et2_wimg(W1, W2, Wf, x.wimg2, st);
+      for (int k = 1; k < c->wimg_copies; ++k) {
+        S2S_CUDA(cudaMemcpyAsync(x.wimg + k * et_wimg_elems(), x.wimg, et_wimg_elems() * 2, cudaMemcpyDeviceToDevice, st));
+        S2S_CUDA(cudaMemcpyAsync(x.wimg2 + k * et2_wimg_elems(), x.wimg2, et2_wimg_elems() * 2, cudaMemcpyDeviceToDevice, st));
+      }
     }
   }
   {
@@ -486,7 +498,7 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   a.W1z = w.W1z; a.W2 = w.W2; a.Wfh = w.Wfh; a.Wfz = w.Wfz;
   a.W1zt = w.W1zt; a.W2t = w.W2t; a.Wft = w.Wft; a.Wfzt = w.Wfzt;
   a.b2 = c->P(e + "trunk.2.bias"); a.ln_w = c->P(e + "layer_norm.weight"); a.ln_b = c->P(e + "layer_norm.bias");
-  a.z_out = z_out; a.wimg = w.wimg; a.wimg2 = w.wimg2; a.nprime_bf16 = c->nprime_bf16;
+  a.z_out = z_out; a.wimg = w.wimg; a.wimg2 = w.wimg2; a.wimg_copies = c->wimg_copies; a.nprime_bf16 = c->nprime_bf16;
   if (!tc) edge_transition_simt(a, st);
   else if (c->opt_pair == 2) edge_transition_tc(a, st);  // first-generation kernel (serial MMA / epilogue), kept for A/B
   else edge_transition_tc2(a, st);
@@ -580,6 +592,14 @@ extern "C" {
 int s2s_abi_version(void) { return S2S_ABI_VERSION; }
 void s2s_profile_enable(int on) { g_profile_on = on != 0; }
 void s2s_profile_reset(void) { prof_drain(); g_prof.clear(); }
+int s2s_profile_list(char* buf, int cap) {
+  prof_drain();
+  std::string out;
+  for (auto& kv : g_prof) out += kv.first + "\t" + std::to_string(kv.second.ms) + "\t" + std::to_string(kv.second.n) + "\n";
+  if ((int)out.size() + 1 > cap) return -(int)out.size() - 1;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)out.size();
+}
 int s2s_profile_read(const char* name, double* total_ms, int64_t* count) {
   prof_drain();
   auto it = g_prof.find(name ? name : "");
@@ -596,6 +616,7 @@ s2s_ctx* s2s_create(const float* tfreq, const float* pdenom, const float* bin_lo
   const int rc = guarded([&] {
     S2S_CHECK(tfreq && pdenom && bin_lower && backbone, "s2s_create: null table");
     c = new s2s_ctx();
+    if (const char* e = getenv("S2S_WIMG_COPIES")) c->wimg_copies = std::max(1, std::min(32, atoi(e)));
     auto up = [&](const float* h, size_t n) {
       float* d;
       S2S_CUDA(cudaMalloc(&d, n * 4));

@@ -59,6 +59,7 @@ struct ProfScope {
   ~ProfScope();
 };
 extern bool g_profile_on;
+const char* prof_intern(const std::string& name);  // stable storage for dynamically built profile names
 #define S2S_PROF(name, st) ::s2s::ProfScope _prof_scope(name, st)
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmArgs g) {
 
 void gemm_f32(const GemmArgs& g, cudaStream_t st) {
   S2S_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb > 0 && g.nh > 0, "gemm: bad shape");
-  S2S_PROF("gemm", st);
+  S2S_PROF(g_profile_on ? prof_intern("gemm_f32 M" + std::to_string(g.M) + " N" + std::to_string(g.N) + " K" + std::to_string(g.K) + " b" + std::to_string(g.nb * g.nh)) : "gemm", st);
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.nb * g.nh);
   if (g.b_kn)
     gemm_f32_kernel<true><<<grid, NT, 0, st>>>(g);

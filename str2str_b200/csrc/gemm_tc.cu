@@ -5,6 +5,8 @@
 // passes = 1: plain bf16 product (IPA q/k/v projections, q.k^T, P.V — tools/precision_probe.py shows these tolerate it)
 // passes = 3: split-bf16 product  A_hi B_hi + A_lo B_hi + A_hi B_lo  accumulated in fp32 (≈16 mantissa bits per operand)
 //             for the layers of the residual stream that do not tolerate single bf16 rounding.
+#include <cstdlib>
+
 #include "s2s_internal.cuh"
 #include "tc_common.cuh"
 
@@ -29,6 +31,7 @@ struct TcKernelArgs {
   bf16 *out_hi, *out_lo;  // optional dense bf16 copies of the result, row pitch ldo (non-batched calls only)
   long ldo;
   bf16* out_vt;           // optional transposed bf16 copy of the v columns of the q|kv projection
+  int dbg;                // timing experiments only (S2S_GEMM_DEBUG): 8 no TMA, 16 no MMA, 32 no epilogue
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -78,6 +81,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         for (int kb = 0; kb < KB; ++kb, ++cnt) {
           const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
           mbar_wait(&s_empty[s], ph ^ 1);
+          if (a.dbg & 8) { mbar_arrive(&s_full[s]); continue; }
           mbar_expect_tx(&s_full[s], stage_bytes);
           unsigned char* st = smem + s * stage_bytes;
           tma_load_2d(st, &mAh, acol + kb * KBLK, arow, &s_full[s]);
@@ -103,7 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
           tc_fence_after();
           const uint32_t st = smem_u32(smem + s * stage_bytes);
           const int ksteps = (min(KBLK, a.K - kb * KBLK) + 15) / 16;
-          for (int k = 0; k < ksteps; ++k) {
+          for (int k = 0; k < ksteps && !(a.dbg & 16); ++k) {
             const uint64_t dah = smem_desc_sw128(st + k * 32), dbh = smem_desc_sw128(st + TILE_BYTES + k * 32);
             umma_bf16(d, dah, dbh, IDESC, (kb | k) ? 1u : 0u);
             if (a.passes == 3) {
@@ -133,29 +137,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem + ab * 128 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < 128 && !(a.dbg & 32); c0 += 32) {
         const int n0 = nt * 128 + c0;
         if (n0 >= a.N) break;  // warp-uniform
-        float v[32];
+        float v[32];  // static indexing only below: stays in registers
         tmem_ld32(taddr + c0, v);
         if (!row_ok) continue;
         const bool full = n0 + 32 <= a.N;
+        const bool vec_ok = full && (a.ldres & 3) == 0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int n = n0 + e;
-          float x = v[e] * pre;
-          if (a.bias && (full || n < a.N)) x += a.bias[n];
-          if (a.relu) x = fmaxf(x, 0.f);
-          x *= post;
-          if (rrow && (full || n < a.N)) x += rrow[n];
-          v[e] = x;
+        for (int e = 0; e < 32; ++e) v[e] *= pre;
+        if (a.bias) {
+          if (full) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + e));
+              v[e] += bv.x; v[e + 1] += bv.y; v[e + 2] += bv.z; v[e + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n0 + e < a.N) v[e] += a.bias[n0 + e];
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] *= post;
+        if (rrow) {
+          if (vec_ok) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 rv = *reinterpret_cast<const float4*>(rrow + n0 + e);
+              v[e] += rv.x; v[e + 1] += rv.y; v[e + 2] += rv.z; v[e + 3] += rv.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n0 + e < a.N) v[e] += rrow[n0 + e];
+          }
         }
         if (crow) {
           if (full && (a.ldc & 3) == 0) {
 #pragma unroll
             for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(crow + n0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
           } else {
-            for (int e = 0; e < 32 && n0 + e < a.N; ++e) crow[n0 + e] = v[e];
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n0 + e < a.N) crow[n0 + e] = v[e];
           }
         }
         if (a.out_hi) {
@@ -175,10 +206,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
               if (lrow) *reinterpret_cast<uint4*>(lrow + e) = make_uint4(l[0], l[1], l[2], l[3]);
             }
           } else {
-            for (int e = 0; e < 32 && n0 + e < a.N; ++e) {
-              const bf16 h = __float2bfloat16_rn(v[e]);
-              hrow[e] = h;
-              if (lrow) lrow[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h));
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (n0 + e < a.N) {
+                const bf16 h = __float2bfloat16_rn(v[e]);
+                hrow[e] = h;
+                if (lrow) lrow[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h));
+              }
             }
           }
         }
@@ -222,6 +256,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, long ld, int ro
 
 void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st) {
   S2S_CHECK(cols % 4 == 0 && ld % 4 == 0, "split_bf16: width must be a multiple of 4");
+  S2S_PROF("split_bf16", st);
   split_bf16_kernel<<<ceil_div((long)rows * (cols / 4), 256), 256, 0, st>>>(src, ld, rows, cols, hi, lo);
   S2S_LAUNCH_CHECK();
 }
@@ -235,12 +270,20 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   const CUtensorMap mBh = make_bf16_2d_map(g.B_hi, g.b_rows, g.b_cols, g.b_pitch);
   const CUtensorMap mBl = g.passes == 3 ? make_bf16_2d_map(g.B_lo, g.b_rows, g.b_cols, g.b_pitch) : mBh;
   TcKernelArgs k;
+  k.dbg = 0;
   k.a_cb = g.a_cb; k.a_ch = g.a_ch; k.a_rb = g.a_rb; k.a_rh = g.a_rh;
   k.b_cb = g.b_cb; k.b_ch = g.b_ch; k.b_rb = g.b_rb; k.b_rh = g.b_rh;
   k.M = g.M; k.N = g.N; k.K = g.K; k.nb = g.nb; k.nh = g.nh; k.passes = g.passes; k.relu = g.relu; k.vt_L = g.vt_L;
   k.alpha = g.alpha; k.bias = g.bias; k.row_pre = g.row_pre; k.row_post = g.row_post; k.res = g.res;
   k.C = g.C; k.ldc = g.ldc; k.sCb = g.sCb; k.sCh = g.sCh; k.ldres = g.ldres;
   k.out_hi = g.out_hi; k.out_lo = g.out_lo; k.ldo = g.ldo; k.out_vt = g.out_vt;
+  if (const char* e = getenv("S2S_GEMM_DEBUG")) {  // timing experiments only
+    const int d = atoi(e);
+    if (d & 1) k.out_vt = nullptr;
+    if (d & 2) k.out_hi = nullptr;
+    if (d & 4) k.C = nullptr;
+    k.dbg = d;
+  }
   static bool configured = false;
   const int smem = G_SMEM + 1024;
   if (!configured) {
@@ -248,7 +291,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
     configured = true;
   }
   const int tiles = g.nb * g.nh * ceil_div(g.M, TM) * ceil_div(g.N, 128);
-  S2S_PROF("gemm_tc", st);
+  S2S_PROF(g_profile_on ? prof_intern("gemm_tc M" + std::to_string(g.M) + " N" + std::to_string(g.N) + " K" + std::to_string(g.K) + " p" + std::to_string(g.passes) + " b" + std::to_string(g.nb * g.nh)) : "gemm_tc", st);
   gemm_tc_kernel<<<tiles < sm_count() ? tiles : sm_count(), 192, smem, st>>>(mAh, mAl, mBh, mBl, k);
   S2S_LAUNCH_CHECK();
 }

@@ -256,12 +256,14 @@ __global__ void softplus_point_weights_kernel(const float* __restrict__ hw, floa
 
 void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv, const float* quat,
                 const float* trans, float* q_pts, float* k_pts, float* v_pts, int rows, cudaStream_t st) {
+  S2S_PROF("ipa_points", st);
   ipa_points_kernel<<<rows, 256, 0, st>>>(qp_raw, ld_q, kvp_raw, ld_kv, quat, trans, q_pts, k_pts, v_pts, rows);
   S2S_LAUNCH_CHECK();
 }
 
 void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const float* pt_w, int B, int L,
                       cudaStream_t st) {
+  S2S_PROF("ipa_point_logits", st);
   dim3 grid(ceil_div(L, 64), ceil_div(L, 32), B * N_H);
   ipa_point_logits_kernel<<<grid, 256, 0, st>>>(S, q_pts, k_pts, pt_w, L);
   S2S_LAUNCH_CHECK();
@@ -283,6 +285,7 @@ void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st) {
 
 void ipa_finalize_points(const float* opt_glob, const float* quat, const float* trans, float* feats, int rows,
                          cudaStream_t st) {
+  S2S_PROF("ipa_finalize_points", st);
   ipa_finalize_points_kernel<<<rows, 96, 0, st>>>(opt_glob, quat, trans, feats, rows);
   S2S_LAUNCH_CHECK();
 }

@@ -31,7 +31,7 @@ struct EtTcArgs {
   const bf16* wimg;  // ET_WTILES pre-swizzled [128 x 64] weight blocks in consumption order
   const float *u, *p, *b2, *ln_w, *ln_b, *mask;
   bf16* z_out;
-  int L, n_tiles;
+  int L, n_tiles, ncopy;
 };
 
 constexpr int ET_OFF_A0 = 0;                          // [z | n'_j] tile: 4 K-blocks
@@ -91,6 +91,7 @@ edge_transition_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __gr
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t cnt = 0, ph_a0 = 0;
+      const bf16* wimg = a.wimg + (size_t)(blockIdx.x % a.ncopy) * ((size_t)ET_WTILES * TILE_BYTES / 2);
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
         const int b = bi / a.L;
@@ -105,7 +106,7 @@ edge_transition_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __gr
           const uint32_t s = cnt % ET_RING, ph = (cnt / ET_RING) & 1;
           mbar_wait(&w_empty[s], ph ^ 1);
           mbar_expect_tx(&w_full[s], TILE_BYTES);
-          tma_bulk_1d(smem + ET_OFF_W + s * TILE_BYTES, a.wimg + (size_t)wt * (TILE_BYTES / 2), TILE_BYTES, &w_full[s]);
+          tma_bulk_1d(smem + ET_OFF_W + s * TILE_BYTES, wimg + (size_t)wt * (TILE_BYTES / 2), TILE_BYTES, &w_full[s]);
         }
       }
     }
@@ -506,7 +507,7 @@ void edge_transition_tc(const EdgeTransitionArgs& a, cudaStream_t st) {
   const CUtensorMap mn = make_bf16_2d_map(a.nprime_bf16, (size_t)a.B * a.L, C_Z, C_Z);
   EtTcArgs k;
   k.wimg = a.wimg; k.u = a.u; k.p = a.p; k.b2 = a.b2; k.ln_w = a.ln_w; k.ln_b = a.ln_b; k.mask = a.mask;
-  k.z_out = a.z_out; k.L = a.L; k.n_tiles = (int)(rows / TM);
+  k.z_out = a.z_out; k.L = a.L; k.n_tiles = (int)(rows / TM); k.ncopy = a.wimg_copies;
   static bool configured = false;
   const int smem = ET_SMEM + 1024;
   if (!configured) {

@@ -152,6 +152,7 @@ __global__ void masks_kernel(const float* __restrict__ rmask, const float* __res
 
 void layernorm(const float* x, const float* res, const float* w, const float* b, const float* rowscale, float* y,
                int rows, int D, cudaStream_t st) {
+  S2S_PROF("layernorm", st);
   const int grid = ceil_div(rows, 8);
   if (D == 128)
     layernorm_kernel<128><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows);
@@ -166,6 +167,7 @@ void layernorm(const float* x, const float* res, const float* w, const float* b,
 
 void softmax_keybias(float* S, const float* keybias, int nb, int nh, int L, cudaStream_t st) {
   const long rows = (long)nb * nh * L;
+  S2S_PROF("softmax", st);
   softmax_keybias_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(S, keybias, L, nh * L, rows);
   S2S_LAUNCH_CHECK();
 }
@@ -187,6 +189,7 @@ void psi_finalize(const float* u, const float* gt_psi, const float* fixed, float
 }
 
 void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st) {
+  S2S_PROF("concat_skip", st);
   concat_skip_kernel<<<ceil_div(rows * D_TFM, 256), 256, 0, st>>>(node, skip, out, rows);
   S2S_LAUNCH_CHECK();
 }
