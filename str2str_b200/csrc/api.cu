@@ -134,6 +134,7 @@ struct s2s_ctx {
   // tensor-core node track: bf16 hi/lo images of every weight matrix, scratch split buffers, attention operands
   std::map<const float*, std::pair<size_t, std::pair<bf16*, bf16*>>> wsplit;  // fp32 base -> (numel, (hi, lo))
   bf16 *sa_hi, *sa_lo, *qkv_bf16, *vT, *P_bf16;
+  bf16 *tq_hi, *tq_lo, *tvT_hi, *tvT_lo, *tP_lo;  // sequence-transformer attention operands (split bf16)
 
   const float* P(const std::string& n) const {
     auto it = params.find(n);
@@ -339,6 +340,7 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     add(R * 4, 4); add(R * 3, 4); add(R * 6, 4); add(R * 2, 4); add(R, 4); add(R, 4);
     add(R * L * C_Z, 2); add(R * 128, 2);
     add(R * IPA_FEAT, 2); add(R * IPA_FEAT, 2); add(R * 6144, 2); add(R * 2048, 2); add((size_t)B * N_H * L * L, 2);
+    add(R * 960, 2); add(R * 960, 2); add(R * 320, 2); add(R * 320, 2); add((size_t)B * TFM_H * L * L, 2);
     c->ws.cap = bytes + 4096;
     S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
     Slab& w = c->ws;
@@ -358,6 +360,8 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->nprime_bf16 = w.take<bf16>(R * 128);
     c->sa_hi = w.take<bf16>(R * IPA_FEAT); c->sa_lo = w.take<bf16>(R * IPA_FEAT);
     c->qkv_bf16 = w.take<bf16>(R * 6144); c->vT = w.take<bf16>(R * 2048); c->P_bf16 = w.take<bf16>((size_t)B * N_H * L * L);
+    c->tq_hi = w.take<bf16>(R * 960); c->tq_lo = w.take<bf16>(R * 960); c->tvT_hi = w.take<bf16>(R * 320); c->tvT_lo = w.take<bf16>(R * 320);
+    c->tP_lo = w.take<bf16>((size_t)B * TFM_H * L * L);
     c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
   }
   // relative-position table: Tpos[r] = W1[:,66:98] pos(d_min + r)   (denoising_ipa.py:144-149)
@@ -506,20 +510,49 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
 
 void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {
   const int R = B * L;
-  linear(c, c->x320, 320, c->P(tl + "self_attn.in_proj_weight"), 320, c->P(tl + "self_attn.in_proj_bias"), c->qkv, 960, R, 960, 320, st);
-  GemmArgs g;
-  g.A = c->qkv; g.lda = 960; g.sAb = (long)L * 960; g.sAh = TFM_HD;
-  g.B = c->qkv + 320; g.ldb = 960; g.sBb = (long)L * 960; g.sBh = TFM_HD;
-  g.C = c->S; g.ldc = L; g.sCb = (long)TFM_H * L * L; g.sCh = (long)L * L;
-  g.M = L; g.N = L; g.K = TFM_HD; g.nb = B; g.nh = TFM_H; g.alpha = 0.11180339887498948f;  // 1/sqrt(80)
-  gemm_f32(g, st);
-  softmax_keybias(c->S, c->keybias, B, TFM_H, L, st);
-  GemmArgs h;
-  h.A = c->S; h.lda = L; h.sAb = (long)TFM_H * L * L; h.sAh = (long)L * L;
-  h.B = c->qkv + 640; h.ldb = 960; h.sBb = (long)L * 960; h.sBh = TFM_HD; h.b_kn = 1;
-  h.C = c->y320; h.ldc = 320; h.sCb = (long)L * 320; h.sCh = TFM_HD;
-  h.M = L; h.N = TFM_HD; h.K = L; h.nb = B; h.nh = TFM_H;
-  gemm_f32(h, st);
+  const float scale = 0.11180339887498948f;  // 1/sqrt(80)
+  const bool tc = c->opt_node == 1 && L % 16 == 0;
+  if (tc) {
+    // in_proj on the tensor cores; its epilogue emits the split-bf16 attention operands: q|k row-major, v transposed per head
+    split_bf16(c->x320, 320, R, 320, c->sa_hi, c->sa_lo, st);
+    const auto w = weight_split(c, c->P(tl + "self_attn.in_proj_weight"));
+    TcGemm g;
+    g.A_hi = c->sa_hi; g.A_lo = c->sa_lo; g.a_rows = R; g.a_cols = 320; g.a_pitch = 320;
+    g.B_hi = w.first; g.B_lo = w.second; g.b_rows = 960; g.b_cols = 320; g.b_pitch = 320;
+    g.M = R; g.N = 960; g.K = 320; g.passes = 3; g.bias = c->P(tl + "self_attn.in_proj_bias");
+    g.out_hi = c->tq_hi; g.out_lo = c->tq_lo; g.ldo = 960;
+    g.out_vt = c->tvT_hi; g.out_vt_lo = c->tvT_lo; g.vt_L = L;
+    g.vt_col0 = 640; g.vt_stride = TFM_HD; g.vt_off = 0; g.vt_width = TFM_HD; g.vt_heads = TFM_H;
+    gemm_tc(g, st);
+    TcGemm s;  // logits = q.k^T / sqrt(80), batched over (decoy, head), split-bf16
+    s.A_hi = c->tq_hi; s.A_lo = c->tq_lo; s.a_rows = R; s.a_cols = 960; s.a_pitch = 960; s.a_rb = L; s.a_ch = TFM_HD;
+    s.B_hi = c->tq_hi + 320; s.B_lo = c->tq_lo + 320; s.b_rows = R; s.b_cols = 640; s.b_pitch = 960; s.b_rb = L; s.b_ch = TFM_HD;
+    s.M = L; s.N = L; s.K = TFM_HD; s.nb = B; s.nh = TFM_H; s.passes = 3; s.alpha = scale;
+    s.C = c->S; s.ldc = L; s.sCb = (long)TFM_H * L * L; s.sCh = (long)L * L;
+    gemm_tc(s, st);
+    softmax_keybias(c->S, c->keybias, B, TFM_H, L, st, c->P_bf16, c->tP_lo);
+    TcGemm p;  // y = P v
+    p.A_hi = c->P_bf16; p.A_lo = c->tP_lo; p.a_rows = (size_t)B * TFM_H * L; p.a_cols = L; p.a_pitch = L; p.a_rb = TFM_H * L; p.a_rh = L;
+    p.B_hi = c->tvT_hi; p.B_lo = c->tvT_lo; p.b_rows = (size_t)B * TFM_H * TFM_HD; p.b_cols = L; p.b_pitch = L; p.b_rb = TFM_H * TFM_HD; p.b_rh = TFM_HD;
+    p.M = L; p.N = TFM_HD; p.K = L; p.nb = B; p.nh = TFM_H; p.passes = 3;
+    p.C = c->y320; p.ldc = 320; p.sCb = (long)L * 320; p.sCh = TFM_HD;
+    gemm_tc(p, st);
+  } else {
+    linear(c, c->x320, 320, c->P(tl + "self_attn.in_proj_weight"), 320, c->P(tl + "self_attn.in_proj_bias"), c->qkv, 960, R, 960, 320, st);
+    GemmArgs g;
+    g.A = c->qkv; g.lda = 960; g.sAb = (long)L * 960; g.sAh = TFM_HD;
+    g.B = c->qkv + 320; g.ldb = 960; g.sBb = (long)L * 960; g.sBh = TFM_HD;
+    g.C = c->S; g.ldc = L; g.sCb = (long)TFM_H * L * L; g.sCh = (long)L * L;
+    g.M = L; g.N = L; g.K = TFM_HD; g.nb = B; g.nh = TFM_H; g.alpha = scale;
+    gemm_f32(g, st);
+    softmax_keybias(c->S, c->keybias, B, TFM_H, L, st);
+    GemmArgs h;
+    h.A = c->S; h.lda = L; h.sAb = (long)TFM_H * L * L; h.sAh = (long)L * L;
+    h.B = c->qkv + 640; h.ldb = 960; h.sBb = (long)L * 960; h.sBh = TFM_HD; h.b_kn = 1;
+    h.C = c->y320; h.ldc = 320; h.sCb = (long)L * 320; h.sCh = TFM_HD;
+    h.M = L; h.N = TFM_HD; h.K = L; h.nb = B; h.nh = TFM_H;
+    gemm_f32(h, st);
+  }
   linear(c, c->y320, 320, c->P(tl + "self_attn.out_proj.weight"), 320, c->P(tl + "self_attn.out_proj.bias"), c->t320, 320, R, 320, 320, st, 0, c->x320, 320);
   layernorm(c->t320, nullptr, c->P(tl + "norm1.weight"), c->P(tl + "norm1.bias"), nullptr, c->x320, R, 320, st);
   linear(c, c->x320, 320, c->P(tl + "linear1.weight"), 320, c->P(tl + "linear1.bias"), c->t320, 320, R, 320, 320, st, 1);

@@ -24,13 +24,14 @@ struct TcKernelArgs {
   int a_cb, a_ch, a_rb, a_rh;  // A box coordinates: col = ib*a_cb + ih*a_ch + kb*64, row = ib*a_rb + ih*a_rh + m0
   int b_cb, b_ch, b_rb, b_rh;
   int M, N, K, nb, nh, passes, relu, vt_L;
+  int vt_col0, vt_stride, vt_off, vt_width, vt_heads;  // which output columns are 'v' and how they group into heads
   float alpha;
   const float *bias, *row_pre, *row_post, *res;
   float* C;
   long ldc, sCb, sCh, ldres;
   bf16 *out_hi, *out_lo;  // optional dense bf16 copies of the result, row pitch ldo (non-batched calls only)
   long ldo;
-  bf16* out_vt;           // optional transposed bf16 copy of the v columns of the q|kv projection
+  bf16 *out_vt, *out_vt_lo;  // optional transposed bf16 (hi, lo) copy of the v columns of a fused q|k|v projection
   int dbg;                // timing experiments only (S2S_GEMM_DEBUG): 8 no TMA, 16 no MMA, 32 no epilogue
 };
 
@@ -216,13 +217,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             }
           }
         }
-        if (a.out_vt && n0 >= 2048 && ((n0 - 2048) & 511) >= 256) {
-          // v columns of the q|kv projection, transposed: VT[((b*8 + h)*256 + c)*L + j]  (row m = b*L + j)
-          const int h = (n0 - 2048) >> 9, c = ((n0 - 2048) & 511) - 256;
+        if (a.out_vt && n0 + 32 > a.vt_col0) {
+          // v columns, transposed per head: VT[((b*heads + h)*width + c)*L + j]  (row m = b*L + j; lanes = consecutive j)
           const int b = m / a.vt_L, j = m % a.vt_L;
-          bf16* dst = a.out_vt + (((long)b * N_H + h) * C_H + c) * a.vt_L + j;
+          const int nn0 = n0 - a.vt_col0;  // >= 0: vt_col0 is a multiple of the 32-column chunk
+          const int h0 = nn0 / a.vt_stride, w0 = nn0 % a.vt_stride - a.vt_off;
+          const int hL = (nn0 + 31) / a.vt_stride, wL = (nn0 + 31) % a.vt_stride - a.vt_off;
+          if (h0 == hL && (wL < 0 || w0 >= a.vt_width)) {
+            // chunk lies entirely in the q/k part of one head: nothing to transpose (warp-uniform)
+          } else if (full && h0 == hL && w0 >= 0 && wL < a.vt_width) {  // whole chunk inside one head's v range
+            bf16* dh = a.out_vt + (((long)b * a.vt_heads + h0) * a.vt_width + w0) * a.vt_L + j;
+            bf16* dl = a.out_vt_lo ? a.out_vt_lo + (dh - a.out_vt) : nullptr;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) dst[(long)e * a.vt_L] = __float2bfloat16_rn(v[e]);
+            for (int e = 0; e < 32; ++e) {
+              const bf16 hi = __float2bfloat16_rn(v[e]);
+              dh[(long)e * a.vt_L] = hi;
+              if (dl) dl[(long)e * a.vt_L] = __float2bfloat16_rn(v[e] - __bfloat162float(hi));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int nn = nn0 + e;
+              if (nn < 0 || n0 + e >= a.N) continue;
+              const int h = nn / a.vt_stride, c = nn % a.vt_stride - a.vt_off;
+              if (c < 0 || c >= a.vt_width) continue;
+              const long idx = (((long)b * a.vt_heads + h) * a.vt_width + c) * a.vt_L + j;
+              const bf16 hi = __float2bfloat16_rn(v[e]);
+              a.out_vt[idx] = hi;
+              if (a.out_vt_lo) a.out_vt_lo[idx] = __float2bfloat16_rn(v[e] - __bfloat162float(hi));
+            }
+          }
         }
       }
       tc_fence_before();
@@ -274,6 +298,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   k.a_cb = g.a_cb; k.a_ch = g.a_ch; k.a_rb = g.a_rb; k.a_rh = g.a_rh;
   k.b_cb = g.b_cb; k.b_ch = g.b_ch; k.b_rb = g.b_rb; k.b_rh = g.b_rh;
   k.M = g.M; k.N = g.N; k.K = g.K; k.nb = g.nb; k.nh = g.nh; k.passes = g.passes; k.relu = g.relu; k.vt_L = g.vt_L;
+  k.vt_col0 = g.vt_col0; k.vt_stride = g.vt_stride; k.vt_off = g.vt_off; k.vt_width = g.vt_width; k.vt_heads = g.vt_heads; k.out_vt_lo = g.out_vt_lo;
   k.alpha = g.alpha; k.bias = g.bias; k.row_pre = g.row_pre; k.row_post = g.row_post; k.res = g.res;
   k.C = g.C; k.ldc = g.ldc; k.sCb = g.sCb; k.sCh = g.sCh; k.ldres = g.ldres;
   k.out_hi = g.out_hi; k.out_lo = g.out_lo; k.ldo = g.ldo; k.out_vt = g.out_vt;

@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 // in-place softmax over the last dim of S[nb][nh][L][L] with an additive per-key bias keybias[b][j]
 __global__ void __launch_bounds__(256) softmax_keybias_kernel(float* __restrict__ S, const float* __restrict__ keybias,
-                                                              int L, int rows_per_batch, long rows) {
+                                                              int L, int rows_per_batch, long rows,
+                                                              bf16* __restrict__ P_hi, bf16* __restrict__ P_lo) {
   const long row = (long)blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -64,6 +65,15 @@ __global__ void __launch_bounds__(256) softmax_keybias_kernel(float* __restrict_
     sum += e;
   }
   const float inv = 1.f / warp_sum(sum);
+  if (P_hi) {  // split-bf16 copy for the tensor-core P.V (the fp32 row is then not needed any more)
+    for (int j = lane; j < L; j += 32) {
+      const float pv = p[j] * inv;
+      const bf16 hi = __float2bfloat16_rn(pv);
+      P_hi[row * L + j] = hi;
+      P_lo[row * L + j] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+    }
+    return;
+  }
   for (int j = lane; j < L; j += 32) p[j] *= inv;
 }
 
@@ -165,10 +175,10 @@ void layernorm(const float* x, const float* res, const float* w, const float* b,
   S2S_LAUNCH_CHECK();
 }
 
-void softmax_keybias(float* S, const float* keybias, int nb, int nh, int L, cudaStream_t st) {
+void softmax_keybias(float* S, const float* keybias, int nb, int nh, int L, cudaStream_t st, bf16* P_hi, bf16* P_lo) {
   const long rows = (long)nb * nh * L;
   S2S_PROF("softmax", st);
-  softmax_keybias_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(S, keybias, L, nh * L, rows);
+  softmax_keybias_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(S, keybias, L, nh * L, rows, P_hi, P_lo);
   S2S_LAUNCH_CHECK();
 }
 
