@@ -1,18 +1,21 @@
-// Fused EdgeTransition, second generation: MMA and epilogue overlap inside one CTA.
+// Fused EdgeTransition, second generation: MMA / epilogue overlap and BOTH hidden activations resident in tensor memory.
 //
 // Same math, tile shape (128 pair rows) and operand conventions as pair_tc.cu.  What changed, and why (measured on B200,
-// see profiles/README.md): the first-generation kernel ran its three layers strictly serially (MMA, then epilogue, then
-// MMA ...) and spent ~70 % of each tile outside the tensor pipe.  Here
-//   * every layer produces its columns as 128-wide chunks that ping-pong between two TMEM accumulators, so the four
-//     epilogue warps drain chunk c while the tensor pipe computes chunk c+1 (and the LayerNorm/store epilogue of a tile
-//     overlaps layer 1 of the next tile);
-//   * h1 never touches shared memory: the epilogue packs it to bf16 and writes it back to TENSOR MEMORY (tcgen05.st),
-//     where layer 2 reads it as the A operand (tcgen05.mma with A in TMEM) — this halves the shared-memory read traffic
-//     of the largest layer, which at N=128 is otherwise right at the 128 B/clk shared-memory limit;
-//   * weights still stream as pre-swizzled 16 KB blocks [128 n x 64 k]: an ablation (S2S_ET_DEBUG) showed the stream is
-//     not a bottleneck, but that per-block barrier traffic of the single MMA-issuing thread is, so blocks are kept as
-//     large as the operand layout allows.
-// TMEM map (512 columns): [0,256) two 128-col fp32 accumulators | [256,448) h1 as packed bf16 (A operand of layer 2).
+// see profiles/README.md): the first-generation kernel ran its three layers strictly serially and kept h1/h2 in shared
+// memory, which left room for only three 16 KB weight stages.  An ablation (S2S_ET_DEBUG) showed that neither the weight
+// stream's bandwidth nor the MMAs were the limit: the 3-deep ring could not cover the L2 latency of a weight block, so
+// the tensor pipe idled about half of every block.  Here
+//   * h1 AND h2 live in tensor memory as packed bf16 (written by the epilogue with tcgen05.st, read by tcgen05.mma as
+//     the A operand), which frees 96 KB of shared memory: the weight ring is 9 stages deep;
+//   * every layer is produced in chunks that alternate between accumulator regions, so the eight epilogue warps drain
+//     chunk c while the tensor pipe computes chunk c+1, and the LayerNorm/store epilogue overlaps the next tile's layer 1;
+//   * A-from-TMEM MMAs also halve the shared-memory read traffic (an SS-mode 128x128x16 MMA reads 8 KB per 64 cycles,
+//     exactly the 128 B/clk the shared memory can deliver).
+// TMEM map (512 columns x 128 lanes):
+//   [  0,128)  layer-1 accumulator 0  | layer-2 accumulators (2 x 64 columns) | final-layer accumulator
+//   [128,256)  layer-1 accumulator 1  | then h2 columns   0..255 (packed bf16, 4 x 32 columns)
+//   [256,448)  h1 (384 packed bf16)
+//   [448,512)  h2 columns 256..383
 #include <cstdlib>
 
 #include "s2s_internal.cuh"
@@ -24,18 +27,18 @@ using namespace tc;
 
 namespace {
 
-constexpr int NSTAGE = 3;
-constexpr int WTILES = 40;  // 12 (layer 1) + 18 (layer 2) + 10 (final)
-constexpr int OFF_A0 = 0;                       // [z | n'_j] tile: 4 K-blocks
-constexpr int OFF_H2 = 4 * TILE_BYTES;          // h2: 6 K-blocks
-constexpr int OFF_W = OFF_H2 + 6 * TILE_BYTES;  // weight ring
+constexpr int NSTAGE = 9;
+constexpr int WTILES = 40;                  // 12 (layer 1) + 18 (layer 2) + 10 (final) blocks of 16 KB per row tile
+constexpr int OFF_A0 = 0;                   // [z | n'_j] tile: 4 K-blocks
+constexpr int OFF_W = 4 * TILE_BYTES;       // weight ring
 constexpr int OFF_VEC = OFF_W + NSTAGE * TILE_BYTES;
 constexpr int VEC_FLOATS = D_ET + C_Z + D_ET + C_Z + C_Z + 512;  // u_i, p_i, b2, ln_w, ln_b, LayerNorm partial sums
 constexpr int OFF_BAR = OFF_VEC + VEC_FLOATS * 4;
-constexpr int N_BARS = 2 * NSTAGE + 9;
+constexpr int N_BARS = 2 * NSTAGE + 12;
 constexpr int SMEM_BYTES = OFF_BAR + N_BARS * 8 + 16;
 
-constexpr uint32_t COL_ACC = 0, COL_H1 = 256;
+constexpr uint32_t COL_H1 = 256;
+__device__ __forceinline__ uint32_t h2_col(int chunk) { return chunk < 4 ? 128u + 32u * chunk : 448u + 32u * (chunk - 4); }
 
 struct Args {
   const bf16* wimg;
@@ -47,8 +50,8 @@ struct Args {
 
 __global__ void __launch_bounds__(320, 1)
 edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_n, Args a) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B operand blocks need 1024-byte alignment
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   float* u_s = reinterpret_cast<float*>(smem + OFF_VEC);
   float* p_s = u_s + D_ET;
   float* b2_s = p_s + C_Z;
@@ -60,11 +63,17 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   uint64_t* w_empty = bars + NSTAGE;
   uint64_t* a0_full = bars + 2 * NSTAGE;
   uint64_t* a0_empty = a0_full + 1;
-  uint64_t* acc_full = a0_full + 2;   // [2]
-  uint64_t* acc_empty = a0_full + 4;  // [2]
-  uint64_t* h1_full = a0_full + 6;
-  uint64_t* h2_full = a0_full + 7;
-  uint64_t* h2_empty = a0_full + 8;
+  // accumulator regions: R0 = cols [0,64), R1 = [64,128), R2 = [128,256).  Uses: "E" = R0+R1 as one 128-column
+  // accumulator (layer-1 chunks 0 and 2, final layer; drained by all 8 epilogue warps), R2 (layer-1 chunk 1), and
+  // "G0"/"G1" = R0 / R1 alone (even / odd layer-2 chunks; drained by epilogue group 0 / 1 only).
+  uint64_t* fullE = a0_full + 2;
+  uint64_t* full2 = a0_full + 3;
+  uint64_t* fullG = a0_full + 4;    // [2]
+  uint64_t* emptyE = a0_full + 6;
+  uint64_t* empty2 = a0_full + 7;
+  uint64_t* emptyG = a0_full + 8;   // [2]
+  uint64_t* h1_full = a0_full + 10;
+  uint64_t* h2_full = a0_full + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -75,13 +84,16 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
     }
     mbar_init(a0_full, 1);
     mbar_init(a0_empty, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 256);
-    }
+    mbar_init(fullE, 1);
+    mbar_init(full2, 1);
+    mbar_init(&fullG[0], 1);
+    mbar_init(&fullG[1], 1);
+    mbar_init(emptyE, 256);
+    mbar_init(empty2, 256);
+    mbar_init(&emptyG[0], 128);
+    mbar_init(&emptyG[1], 128);
     mbar_init(h1_full, 256);
     mbar_init(h2_full, 256);
-    mbar_init(h2_empty, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -95,7 +107,7 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int tiles_per_i = a.L / TM;
-  constexpr uint32_t IDESC = make_idesc(128, 128);
+  constexpr uint32_t IDESC128 = make_idesc(128, 128), IDESC64 = make_idesc(128, 64);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -122,74 +134,110 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t a0 = smem_u32(smem + OFF_A0), h2b = smem_u32(smem + OFF_H2), wr = smem_u32(smem + OFF_W);
-      uint32_t cnt = 0, ph_a0 = 0, ph_h1 = 0, ph_h2 = 0, chunk = 0;
+    // ===== MMA issuer: the whole warp runs the loop (warp-uniform values), one elected lane issues =====
+    {
+      const uint32_t a0 = desc_lo_sw128(smem_u32(smem + OFF_A0)), wr = desc_lo_sw128(smem_u32(smem + OFF_W));  // descriptor low words
+      constexpr uint32_t BLK = TILE_BYTES >> 4;  // one 16 KB block in descriptor address units
+      uint32_t cnt = 0, ph_a0 = 0, ph_h1 = 0, ph_h2 = 0;
+      uint32_t nE = 0, n2 = 0, nG0 = 0, nG1 = 0;  // barrier phase bookkeeping (waits issued so far)
       const bool do_mma = !(a.dbg & 2);
-      // one streamed weight block (64 k) against an A K-block in shared memory / 32 packed h1 columns in tensor memory
-      auto blk = [&](uint32_t d, uint32_t a_src, bool a_in_tmem, bool first) {
+      auto next_block = [&]() -> uint32_t {  // wait for the next streamed weight block
         const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
         mbar_wait(&w_full[s], ph);
         tc_fence_after();
-        const uint32_t wb = wr + s * TILE_BYTES;
-        if (do_mma) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = (first && k == 0) ? 0u : 1u;
-            if (a_in_tmem) umma_bf16_ts(d, a_src + k * 8, smem_desc_sw128(wb + k * 32), IDESC, acc);
-            else umma_bf16(d, smem_desc_sw128(a_src + k * 32), smem_desc_sw128(wb + k * 32), IDESC, acc);
-          }
-        }
-        umma_commit(&w_empty[s]);
-        ++cnt;
+        return wr + s * BLK;
       };
-      // claim the next accumulator of the ping-pong pair
-      auto claim = [&]() -> uint32_t {
-        const uint32_t buf = chunk & 1, ph = (chunk >> 1) & 1;
-        mbar_wait(&acc_empty[buf], ph ^ 1);
-        tc_fence_after();
-        return buf;
+      auto release_block = [&]() {  // called by the elected lane
+        umma_commit(&w_empty[cnt % NSTAGE]);
+      };
+      auto wait_prev = [&](uint64_t* bar, uint32_t& n) {  // wait #k waits for drain #(k-1): the first one passes
+        mbar_wait(bar, (n & 1) ^ 1);
+        ++n;
+      };
+      auto wait_done = [&](uint64_t* bar, uint32_t& n) {  // wait #k waits for drain #k
+        mbar_wait(bar, n & 1);
+        ++n;
       };
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         mbar_wait(a0_full, ph_a0);
         ph_a0 ^= 1;
         tc_fence_after();
-        for (int nc = 0; nc < 3; ++nc, ++chunk) {  // layer 1: K = [z | n'_j] (4 blocks), A in shared memory
-          const uint32_t buf = claim();
-          for (int kb = 0; kb < 4; ++kb) blk(tmem + COL_ACC + buf * 128, a0 + kb * TILE_BYTES, false, kb == 0);
-          umma_commit(&acc_full[buf]);
+        // ---- layer 1: three 128-column chunks in R0+R1, R2, R0+R1; A = [z | n'_j] from shared memory ----
+        for (int nc = 0; nc < 3; ++nc) {
+          uint32_t d;
+          if (nc == 1) { wait_prev(empty2, n2); d = tmem + 128; }
+          else { wait_prev(emptyE, nE); d = tmem; }
+          tc_fence_after();
+          for (int kb = 0; kb < 4; ++kb, ++cnt) {
+            const uint32_t wb = next_block();
+            if (elect_one()) {
+              if (do_mma) kblock_ss(d, a0 + kb * BLK, wb, IDESC128, kb == 0);
+              release_block();
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit(nc == 1 ? full2 : fullE);
+          __syncwarp();
         }
+        // ---- layer 2: six 64-column chunks alternating R0 / R1; A = h1 from tensor memory ----
         mbar_wait(h1_full, ph_h1);
         ph_h1 ^= 1;
-        mbar_wait(h2_empty, ph_h2 ^ 1);  // previous tile's final layer has consumed h2
         tc_fence_after();
-        for (int nc = 0; nc < 3; ++nc, ++chunk) {  // layer 2: K = h1 (6 blocks), A in tensor memory
-          const uint32_t buf = claim();
-          for (int kb = 0; kb < 6; ++kb) blk(tmem + COL_ACC + buf * 128, tmem + COL_H1 + kb * 32, true, kb == 0);
-          umma_commit(&acc_full[buf]);
-        }
-        {  // final layer: [z | n'_j] terms first (frees the activation tile for the next TMA), then h2
-          const uint32_t buf = claim();
-          for (int kb = 0; kb < 4; ++kb) blk(tmem + COL_ACC + buf * 128, a0 + kb * TILE_BYTES, false, kb == 0);
-          umma_commit(a0_empty);
-          mbar_wait(h2_full, ph_h2);
-          ph_h2 ^= 1;
+        wait_prev(emptyE, nE);  // layer-1 chunk 2 has left R0+R1
+        for (int c = 0; c < 6; ++c) {
+          if (c >= 2) { if (c & 1) wait_done(&emptyG[1], nG1); else wait_done(&emptyG[0], nG0); }
           tc_fence_after();
-          for (int kb = 0; kb < 6; ++kb) blk(tmem + COL_ACC + buf * 128, h2b + kb * TILE_BYTES, false, false);
-          umma_commit(&acc_full[buf]);
-          umma_commit(h2_empty);
-          ++chunk;
+          const uint32_t d = tmem + (c & 1) * 64;
+          for (int kp = 0; kp < 3; ++kp, ++cnt) {  // one block = [64 n x 128 k]: two 64-row K-blocks of 8 KB
+            const uint32_t wb = next_block();
+            if (elect_one()) {
+              if (do_mma) {
+                kblock_ts(d, tmem + COL_H1 + kp * 64, wb, IDESC64, kp == 0);
+                kblock_ts(d, tmem + COL_H1 + kp * 64 + 32, wb + BLK / 2, IDESC64, false);
+              }
+              release_block();
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit(&fullG[c & 1]);
+          __syncwarp();
         }
+        // ---- final layer into R0+R1: [z | n'_j] terms (A in shared memory), then h2 (A in tensor memory) ----
+        wait_done(&emptyG[0], nG0);  // layer-2 chunks 4 and 5 have left R0 / R1
+        wait_done(&emptyG[1], nG1);
+        tc_fence_after();
+        for (int kb = 0; kb < 4; ++kb, ++cnt) {
+          const uint32_t wb = next_block();
+          if (elect_one()) {
+            if (do_mma) kblock_ss(tmem, a0 + kb * BLK, wb, IDESC128, kb == 0);
+            release_block();
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(a0_empty);  // the activation tile is free: the next tile's TMA overlaps the rest of this layer
+        __syncwarp();
+        mbar_wait(h2_full, ph_h2);
+        ph_h2 ^= 1;
+        tc_fence_after();
+        for (int c = 0; c < 6; ++c, ++cnt) {
+          const uint32_t wb = next_block();
+          if (elect_one()) {
+            if (do_mma) kblock_ts(tmem, tmem + h2_col(c), wb, IDESC128, false);
+            release_block();
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(fullE);
+        __syncwarp();
       }
     }
   } else {
-    // ===== 8 epilogue warps: TMEM lane quarter = warp % 4, two warps per quarter split each chunk's 128 columns =====
+    // ===== 8 epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter split each chunk's columns =====
     const int ew = warp - 2, q = warp & 3, hf = ew >> 2, r = q * 32 + lane;
     const int et = threadIdx.x - 64;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const bool do_epi = !(a.dbg & 4);
-    uint32_t chunk = 0;
+    uint32_t fE = 0, f2 = 0, fG = 0;  // completed uses seen per "full" barrier
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
       const int b = bi / a.L;
@@ -198,67 +246,70 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
       if (et < C_Z) p_s[et] = a.p[(size_t)bi * C_Z + et];
       named_bar_sync(1, 256);
       const float m = a.mask[bi] * a.mask[(size_t)b * a.L + j0 + r];
-      float y[64];  // this thread's half (64 columns) of one accumulator chunk of its row
-      auto fetch = [&]() -> uint32_t {  // wait for the next chunk and pull it into registers
-        const uint32_t buf = chunk & 1, ph = (chunk >> 1) & 1;
-        ++chunk;
-        mbar_wait(&acc_full[buf], ph);
+      float y[64];
+      auto wait_full = [&](uint64_t* bar, uint32_t& n) {
+        mbar_wait(bar, n & 1);
+        ++n;
         tc_fence_after();
-        if (do_epi) {
-          tmem_ld32_issue(tmem + lane_off + COL_ACC + buf * 128 + hf * 64, y);
-          tmem_ld32_issue(tmem + lane_off + COL_ACC + buf * 128 + hf * 64 + 32, y + 32);
-          tmem_wait_ld();
-        }
-        return buf;
       };
-      auto add_vec = [&](const float* vec) {  // y += vec[0..64) (broadcast shared-memory reads, 128-bit)
+      auto add_vec = [&](const float* vec, int n) {  // y[0..n) += vec[0..n) (128-bit broadcast shared-memory reads)
 #pragma unroll
         for (int e = 0; e < 64; e += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(vec + e);
-          y[e] += t.x; y[e + 1] += t.y; y[e + 2] += t.z; y[e + 3] += t.w;
+          if (e < n) {
+            const float4 t = *reinterpret_cast<const float4*>(vec + e);
+            y[e] += t.x; y[e + 1] += t.y; y[e + 2] += t.z; y[e + 3] += t.w;
+          }
         }
       };
-      // layer 1: + u_i, relu, pack to bf16 pairs, back into tensor memory as layer 2's A operand
+      // ---- layer 1: + u_i, relu, pack, into tensor memory as layer 2's A operand ----
       for (int nc = 0; nc < 3; ++nc) {
-        const uint32_t buf = fetch();
+        const uint32_t base = nc == 1 ? 128u : 0u;
+        if (nc == 1) wait_full(full2, f2); else wait_full(fullE, fE);
         if (do_epi) {
-          add_vec(u_s + nc * 128 + hf * 64);
+          tmem_ld32_issue(tmem + lane_off + base + hf * 64, y);
+          tmem_ld32_issue(tmem + lane_off + base + hf * 64 + 32, y + 32);
+          tmem_wait_ld();
+          add_vec(u_s + nc * 128 + hf * 64, 64);
           uint32_t pk[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) pk[e] = pack_bf16(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
           tmem_st32(tmem + lane_off + COL_H1 + nc * 64 + hf * 32, pk);
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        mbar_arrive(nc == 1 ? empty2 : emptyE);
       }
       mbar_arrive(h1_full);
-      // layer 2: + b2, relu, stage h2 as swizzled K-blocks for the final layer
-      for (int nc = 0; nc < 3; ++nc) {
-        const uint32_t buf = fetch();
+      // ---- layer 2: + b2, relu, pack, into tensor memory as the final layer's A operand.  The two epilogue groups
+      //      (hf = 0 / 1) take the even / odd chunks, so each has two chunk-MMA times to turn one chunk around ----
+      for (int c = hf; c < 6; c += 2) {
+        wait_full(&fullG[hf], fG);
         if (do_epi) {
-          add_vec(b2_s + nc * 128 + hf * 64);
-          unsigned char* kblk = smem + OFF_H2 + (nc * 2 + hf) * TILE_BYTES;  // this half is exactly one 64-wide K-block
+          tmem_ld32_issue(tmem + lane_off + hf * 64, y);
+          tmem_ld32_issue(tmem + lane_off + hf * 64 + 32, y + 32);
+          tmem_wait_ld();
+          add_vec(b2_s + c * 64, 64);
+          uint32_t pk[32];
 #pragma unroll
-          for (int gq = 0; gq < 8; ++gq) {
-            float h[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) h[e] = fmaxf(y[gq * 8 + e], 0.f);
-            store8_sw128(kblk, r, gq * 8, h);
-          }
+          for (int e = 0; e < 32; ++e) pk[e] = pack_bf16(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
+          tmem_st32(tmem + lane_off + h2_col(c), pk);
         }
-        fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        mbar_arrive(&emptyG[hf]);
       }
       mbar_arrive(h2_full);
-      // output: + p_i, LayerNorm over 128 channels (exact two-pass; the two half-row threads exchange partial sums
-      // through shared memory), * edge mask, bf16 store
+      // ---- output: + p_i, LayerNorm over 128 channels (exact two-pass; the two half-row threads exchange partial sums
+      //      through shared memory), * edge mask, bf16 store ----
       {
-        const uint32_t buf = fetch();
+        wait_full(fullE, fE);
+        if (do_epi) {
+          tmem_ld32_issue(tmem + lane_off + hf * 64, y);
+          tmem_ld32_issue(tmem + lane_off + hf * 64 + 32, y + 32);
+          tmem_wait_ld();
+        }
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);  // accumulator is in registers: the tensor pipe may reuse it
+        mbar_arrive(emptyE);  // accumulator is in registers: the tensor pipe may reuse it
         if (!do_epi) continue;
-        add_vec(p_s + hf * 64);
+        add_vec(p_s + hf * 64, 64);
         float sum = 0.f;
 #pragma unroll
         for (int e = 0; e < 64; ++e) sum += y[e];
@@ -293,9 +344,10 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-__global__ void build_wtile128_kernel(const float* __restrict__ src, int ld, int n0, int k0, unsigned char* __restrict__ dst) {
+// one [rows x 64] bf16 block in the SW128 K-major layout
+__global__ void build_wblock_kernel(const float* __restrict__ src, int ld, int n0, int k0, int rows, unsigned char* __restrict__ dst) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= TM * KBLK) return;
+  if (idx >= rows * KBLK) return;
   const int r = idx / KBLK, c = idx % KBLK;
   *reinterpret_cast<bf16*>(dst + sw128_offset(r, c)) = __float2bfloat16_rn(src[(size_t)(n0 + r) * ld + k0 + c]);
 }
@@ -304,21 +356,24 @@ __global__ void build_wtile128_kernel(const float* __restrict__ src, int ld, int
 
 size_t et2_wimg_elems() { return (size_t)WTILES * TM * KBLK; }
 
-// Weight blocks in exactly the order the MMA issuer consumes them.
+// Weight blocks (16 KB each) in exactly the order the MMA issuer consumes them.
 void build_et2_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st) {
   unsigned char* d = reinterpret_cast<unsigned char*>(dst);
-  auto tile = [&](const float* src, int n0, int k0) {
-    build_wtile128_kernel<<<TM * KBLK / 256, 256, 0, st>>>(src, D_ET, n0, k0, d);
+  auto block = [&](const float* src, int n0, int k0, int rows) {
+    build_wblock_kernel<<<ceil_div(rows * KBLK, 256), 256, 0, st>>>(src, D_ET, n0, k0, rows, d);
     S2S_LAUNCH_CHECK();
-    d += TILE_BYTES;
+    d += rows * KBLK * 2;
   };
   auto aug = [](int kb) { return kb < 2 ? kb * KBLK : 256 + (kb - 2) * KBLK; };  // [z | n'_j] columns of a 384-wide weight
-  for (int nc = 0; nc < 3; ++nc)
-    for (int kb = 0; kb < 4; ++kb) tile(W1, nc * 128, aug(kb));
-  for (int nc = 0; nc < 3; ++nc)
-    for (int kb = 0; kb < 6; ++kb) tile(W2, nc * 128, kb * KBLK);
-  for (int kb = 0; kb < 4; ++kb) tile(Wf, 0, aug(kb));
-  for (int kb = 0; kb < 6; ++kb) tile(Wf, 0, kb * KBLK);
+  for (int nc = 0; nc < 3; ++nc)  // layer 1: [128 n x 64 k]
+    for (int kb = 0; kb < 4; ++kb) block(W1, nc * 128, aug(kb), 128);
+  for (int c = 0; c < 6; ++c)     // layer 2: [64 n x 128 k] as two 64-row K-blocks
+    for (int kp = 0; kp < 3; ++kp) {
+      block(W2, c * 64, (2 * kp) * KBLK, 64);
+      block(W2, c * 64, (2 * kp + 1) * KBLK, 64);
+    }
+  for (int kb = 0; kb < 4; ++kb) block(Wf, 0, aug(kb), 128);   // final: [z | n'_j] terms
+  for (int kb = 0; kb < 6; ++kb) block(Wf, 0, kb * KBLK, 128);  // final: h2 terms
 }
 
 void edge_transition_tc2(const EdgeTransitionArgs& a, cudaStream_t st) {

@@ -19,6 +19,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* b, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(n) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
@@ -143,6 +146,68 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[31])
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// One lane of a converged warp.  tcgen05.mma / tcgen05.commit take uniform-register operands: issued from code the
+// compiler sees as divergent (e.g. under `if (lane == 0)`) every operand goes through an ELECT / R2UR.BROADCAST waterfall
+// loop (~12 extra instructions per MMA, measured).  Role loops therefore run on the whole warp with warp-uniform values and
+// only the instruction itself is predicated on the elected lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- lean issue path ----------------------------------------------------------------------------------------------------
+// The MMA-issuing thread is a single lane with no latency hiding: every instruction between two tcgen05.mma costs issue
+// slots the tensor pipe then idles for (measured: ~25 instructions per MMA capped a 128x64x16 MMA at ~90 cycles instead of
+// 32).  The SW128 K-major descriptor only varies in its 14-bit start-address field, so callers keep the low word and
+// bump it by (bytes >> 4); the constant high word and the 64-bit assembly happen inside the asm statement.
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(DESC_HI_SW128)
+      : "memory");
+}
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(DESC_HI_SW128)
+      : "memory");
+}
+// K-block (64 k = 4 MMAs) helpers: `first` clears the accumulator with the very first MMA
+__device__ __forceinline__ void kblock_ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool first) {
+  if (first) umma_ss<false>(d, a_lo, b_lo, idesc); else umma_ss<true>(d, a_lo, b_lo, idesc);
+  umma_ss<true>(d, a_lo + 2, b_lo + 2, idesc);
+  umma_ss<true>(d, a_lo + 4, b_lo + 4, idesc);
+  umma_ss<true>(d, a_lo + 6, b_lo + 6, idesc);
+}
+__device__ __forceinline__ void kblock_ts(uint32_t d, uint32_t a_col, uint32_t b_lo, uint32_t idesc, bool first) {
+  if (first) umma_ts<false>(d, a_col, b_lo, idesc); else umma_ts<true>(d, a_col, b_lo, idesc);
+  umma_ts<true>(d, a_col + 8, b_lo + 2, idesc);
+  umma_ts<true>(d, a_col + 16, b_lo + 4, idesc);
+  umma_ts<true>(d, a_col + 24, b_lo + 6, idesc);
 }
 
 }  // namespace tc
