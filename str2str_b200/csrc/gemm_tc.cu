@@ -38,8 +38,8 @@ struct TcKernelArgs {
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, TcKernelArgs a) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B operand blocks need 1024-byte alignment
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
   uint64_t* s_full = bars;        // [6]
   uint64_t* s_empty = bars + 6;   // [6]
@@ -95,31 +95,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t cnt = 0, it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t ab = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(&acc_empty[ab], aph ^ 1);
+    // MMA issuer: the whole warp runs the loop with warp-uniform values; one elected lane issues (see tc_common.cuh)
+    uint32_t cnt = 0, it = 0;
+    const uint32_t ring = desc_lo_sw128(smem_u32(smem));
+    constexpr uint32_t BLK = TILE_BYTES >> 4;
+    const uint32_t stage_units = blocks_per_stage * BLK;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&acc_empty[ab], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem + ab * 128;
+      for (int kb = 0; kb < KB; ++kb, ++cnt) {
+        const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
+        mbar_wait(&s_full[s], ph);
         tc_fence_after();
-        const uint32_t d = tmem + ab * 128;
-        for (int kb = 0; kb < KB; ++kb, ++cnt) {
-          const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
-          mbar_wait(&s_full[s], ph);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + s * stage_bytes);
-          const int ksteps = (min(KBLK, a.K - kb * KBLK) + 15) / 16;
-          for (int k = 0; k < ksteps && !(a.dbg & 16); ++k) {
-            const uint64_t dah = smem_desc_sw128(st + k * 32), dbh = smem_desc_sw128(st + TILE_BYTES + k * 32);
-            umma_bf16(d, dah, dbh, IDESC, (kb | k) ? 1u : 0u);
-            if (a.passes == 3) {
-              umma_bf16(d, smem_desc_sw128(st + 2 * TILE_BYTES + k * 32), dbh, IDESC, 1u);
-              umma_bf16(d, dah, smem_desc_sw128(st + 3 * TILE_BYTES + k * 32), IDESC, 1u);
+        const uint32_t st = ring + s * stage_units;
+        const int ksteps = (min(KBLK, a.K - kb * KBLK) + 15) / 16;
+        if (elect_one()) {
+          if (!(a.dbg & 16)) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t ah = st + 2 * k, bh = st + BLK + 2 * k;
+              if (kb | k) umma_ss<true>(d, ah, bh, IDESC); else umma_ss<false>(d, ah, bh, IDESC);
+              if (a.passes == 3) {
+                umma_ss<true>(d, st + 2 * BLK + 2 * k, bh, IDESC);
+                umma_ss<true>(d, ah, st + 3 * BLK + 2 * k, IDESC);
+              }
             }
           }
           umma_commit(&s_empty[s]);
         }
-        umma_commit(&acc_full[ab]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&acc_full[ab]);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3, r = q * 32 + lane;

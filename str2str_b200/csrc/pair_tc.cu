@@ -248,8 +248,8 @@ constexpr int EE_OFF_BAR = EE_OFF_VEC + EE_VEC_FLOATS * 4;
 constexpr int EE_SMEM = EE_OFF_BAR + 8 * 8 + 16;
 
 __global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   float* ti_s = reinterpret_cast<float*>(smem + EE_OFF_VEC);
   float* b2_s = ti_s + C_Z;
   float* b3_s = b2_s + C_Z;
@@ -288,21 +288,27 @@ __global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
   constexpr uint32_t IDESC = make_idesc(128, 128);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // loader + MMA issuer: whole warp runs the loop, one elected lane issues
+    if (elect_one()) {
       mbar_expect_tx(w_full, 4 * TILE_BYTES);
       for (int t = 0; t < 4; ++t) tma_bulk_1d(smem + EE_OFF_W + t * TILE_BYTES, a.wimg + (size_t)t * (TILE_BYTES / 2), TILE_BYTES, w_full);
-      mbar_wait(w_full, 0);
-      const uint32_t ab = smem_u32(smem + EE_OFF_A), wb = smem_u32(smem + EE_OFF_W);
-      uint32_t ph_a = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        for (int layer = 0; layer < 2; ++layer) {
-          mbar_wait(a_full, ph_a);
-          ph_a ^= 1;
-          tc_fence_after();
-          mma_kblock(tmem, ab, wb + (2 * layer) * TILE_BYTES, IDESC, true);
-          mma_kblock(tmem, ab + TILE_BYTES, wb + (2 * layer + 1) * TILE_BYTES, IDESC, false);
+    }
+    __syncwarp();
+    mbar_wait(w_full, 0);
+    const uint32_t ab = desc_lo_sw128(smem_u32(smem + EE_OFF_A)), wb = desc_lo_sw128(smem_u32(smem + EE_OFF_W));
+    constexpr uint32_t BLK = TILE_BYTES >> 4;
+    uint32_t ph_a = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      for (int layer = 0; layer < 2; ++layer) {
+        mbar_wait(a_full, ph_a);
+        ph_a ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
+          kblock_ss(tmem, ab, wb + (2 * layer) * BLK, IDESC, true);
+          kblock_ss(tmem, ab + BLK, wb + (2 * layer + 1) * BLK, IDESC, false);
           umma_commit(acc_full);
         }
+        __syncwarp();
       }
     }
   } else {
