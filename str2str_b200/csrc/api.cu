@@ -135,6 +135,9 @@ struct s2s_ctx {
   std::map<const float*, std::pair<size_t, std::pair<bf16*, bf16*>>> wsplit;  // fp32 base -> (numel, (hi, lo))
   bf16 *sa_hi, *sa_lo, *qkv_bf16, *vT, *P_bf16;
   bf16 *tq_hi, *tq_lo, *tvT_hi, *tvT_lo, *tP_lo;  // sequence-transformer attention operands (split bf16)
+  // split-bf16 companions of the node-track activations, written by the producing kernel's epilogue
+  bf16 *node_hi, *node_lo, *init_hi, *init_lo, *a256_hi, *a256_lo, *b256_hi, *b256_lo;
+  bf16 *x320_hi, *x320_lo, *t320_hi, *t320_lo, *y320_hi, *y320_lo, *nprime_hi, *nprime_lo;
 
   const float* P(const std::string& n) const {
     auto it = params.find(n);
@@ -146,6 +149,7 @@ struct s2s_ctx {
 namespace {
 
 enum Prec { EXACT = 0, TC3 = 3, TC1 = 1 };
+struct Split { bf16* hi = nullptr; bf16* lo = nullptr; };  // split-bf16 image of an fp32 activation (dense, pitch = width)
 
 // bf16 (hi, lo) image of a weight (or of a sub-block of one) registered at finalize
 std::pair<const bf16*, const bf16*> weight_split(const s2s_ctx* c, const float* W) {
@@ -161,13 +165,18 @@ std::pair<const bf16*, const bf16*> weight_split(const s2s_ctx* c, const float* 
 // (3-pass split-bf16 / single bf16) when the context runs with node_gemm = 1.
 void linear(const s2s_ctx* c, const float* x, long ldx, const float* W, long ldw, const float* bias, float* y, long ldy,
             int M, int N, int K, cudaStream_t st, int relu = 0, const float* res = nullptr, long ldres = 0,
-            const float* row_pre = nullptr, const float* row_post = nullptr, int prec_arg = -1) {
+            const float* row_pre = nullptr, const float* row_post = nullptr, int prec_arg = -1, Split in = Split(),
+            Split out = Split()) {
   const Prec prec = (Prec)(prec_arg < 0 ? c->cur_prec : prec_arg);
   if (prec != EXACT && c->opt_node == 1 && K % 16 == 0 && ldx % 4 == 0 && ldw % 8 == 0) {
-    split_bf16(x, ldx, M, K, c->sa_hi, prec == TC3 ? c->sa_lo : nullptr, st);
+    if (!in.hi) {  // no image from the producer: split here
+      split_bf16(x, ldx, M, K, c->sa_hi, prec == TC3 ? c->sa_lo : nullptr, st);
+      in.hi = c->sa_hi; in.lo = c->sa_lo;
+    }
     const auto w = weight_split(c, W);
     TcGemm g;
-    g.A_hi = c->sa_hi; g.A_lo = c->sa_lo; g.a_rows = M; g.a_cols = K; g.a_pitch = K;
+    g.A_hi = in.hi; g.A_lo = in.lo; g.a_rows = M; g.a_cols = K; g.a_pitch = K;
+    g.out_hi = out.hi; g.out_lo = out.lo; g.ldo = N;
     g.B_hi = w.first; g.B_lo = w.second; g.b_rows = N; g.b_cols = K; g.b_pitch = ldw;
     g.M = M; g.N = N; g.K = K; g.passes = (int)prec; g.relu = relu;
     g.bias = bias; g.row_pre = row_pre; g.row_post = row_post; g.res = res; g.ldres = ldres;
@@ -180,6 +189,7 @@ void linear(const s2s_ctx* c, const float* x, long ldx, const float* W, long ldw
   g.bias = bias; g.res = res; g.ldres = ldres; g.row_pre = row_pre; g.row_post = row_post;
   g.M = M; g.N = N; g.K = K; g.relu = relu;
   gemm_f32(g, st);
+  if (out.hi) split_bf16(y, ldy, M, N, out.hi, out.lo, st);  // exact path taken although an image was requested
 }
 
 struct ParamSpec { std::string name; int64_t numel; };
@@ -341,6 +351,9 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     add(R * L * C_Z, 2); add(R * 128, 2);
     add(R * IPA_FEAT, 2); add(R * IPA_FEAT, 2); add(R * 6144, 2); add(R * 2048, 2); add((size_t)B * N_H * L * L, 2);
     add(R * 960, 2); add(R * 960, 2); add(R * 320, 2); add(R * 320, 2); add((size_t)B * TFM_H * L * L, 2);
+    for (int k = 0; k < 8; ++k) add(R * 256, 2);
+    for (int k = 0; k < 6; ++k) add(R * 320, 2);
+    add(R * 128, 2);
     c->ws.cap = bytes + 4096;
     S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
     Slab& w = c->ws;
@@ -362,6 +375,11 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->qkv_bf16 = w.take<bf16>(R * 6144); c->vT = w.take<bf16>(R * 2048); c->P_bf16 = w.take<bf16>((size_t)B * N_H * L * L);
     c->tq_hi = w.take<bf16>(R * 960); c->tq_lo = w.take<bf16>(R * 960); c->tvT_hi = w.take<bf16>(R * 320); c->tvT_lo = w.take<bf16>(R * 320);
     c->tP_lo = w.take<bf16>((size_t)B * TFM_H * L * L);
+    c->node_hi = w.take<bf16>(R * 256); c->node_lo = w.take<bf16>(R * 256); c->init_hi = w.take<bf16>(R * 256); c->init_lo = w.take<bf16>(R * 256);
+    c->a256_hi = w.take<bf16>(R * 256); c->a256_lo = w.take<bf16>(R * 256); c->b256_hi = w.take<bf16>(R * 256); c->b256_lo = w.take<bf16>(R * 256);
+    c->x320_hi = w.take<bf16>(R * 320); c->x320_lo = w.take<bf16>(R * 320); c->t320_hi = w.take<bf16>(R * 320); c->t320_lo = w.take<bf16>(R * 320);
+    c->y320_hi = w.take<bf16>(R * 320); c->y320_lo = w.take<bf16>(R * 320);
+    c->nprime_hi = c->nprime_bf16; c->nprime_lo = w.take<bf16>(R * 128);
     c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
   }
   // relative-position table: Tpos[r] = W1[:,66:98] pos(d_min + r)   (denoising_ipa.py:144-149)
@@ -402,7 +420,7 @@ void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, c
 
 // InvariantPointAttention.forward of block blk -> out (linear_out result; not yet masked)
 void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z, const float* quat, const float* trans,
-            const float* rmask, float* out, const float* res, const float* row_post, cudaStream_t st) {
+            const float* rmask, float* out, const float* res, const float* row_post, cudaStream_t st, Split node_sp = Split()) {
   const int R = B * L;
   const IpaW& w = c->ipa[blk];
   const std::string ip = "translator.trunk.ipa_" + std::to_string(blk) + ".";
@@ -411,17 +429,20 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   if (tc) {
     // q | k | v projection in one bf16 tensor-core GEMM whose epilogue writes the attention operands directly:
     // row-major bf16 q,k (K-major for q.k^T) and the transposed v (K-major for P.v); no fp32 copy is needed.
-    split_bf16(node, 256, R, 256, c->sa_hi, c->sa_lo, st);
+    if (!node_sp.hi) {
+      split_bf16(node, 256, R, 256, c->sa_hi, c->sa_lo, st);
+      node_sp.hi = c->sa_hi; node_sp.lo = c->sa_lo;
+    }
     const auto ws = weight_split(c, w.proj_w);
     TcGemm g;
-    g.A_hi = c->sa_hi; g.a_rows = R; g.a_cols = 256; g.a_pitch = 256;
+    g.A_hi = node_sp.hi; g.a_rows = R; g.a_cols = 256; g.a_pitch = 256;
     g.B_hi = ws.first; g.b_rows = 6144; g.b_cols = 256; g.b_pitch = 256;
     g.M = R; g.N = 6144; g.K = 256; g.passes = 1; g.bias = w.proj_b;
     g.out_hi = c->qkv_bf16; g.ldo = 6144; g.out_vt = c->vT; g.vt_L = L;
     gemm_tc(g, st);
     // point projections keep split-bf16 accuracy (they become nm-scale coordinates)
     TcGemm p;
-    p.A_hi = c->sa_hi; p.A_lo = c->sa_lo; p.a_rows = R; p.a_cols = 256; p.a_pitch = 256;
+    p.A_hi = node_sp.hi; p.A_lo = node_sp.lo; p.a_rows = R; p.a_cols = 256; p.a_pitch = 256;
     p.B_hi = ws.first + (size_t)6144 * 256; p.B_lo = ws.second + (size_t)6144 * 256; p.b_rows = 672; p.b_cols = 256; p.b_pitch = 256;
     p.M = R; p.N = 672; p.K = 256; p.passes = 3; p.bias = w.proj_b + 6144;
     p.C = c->proj + 6144; p.ldc = 6816;
@@ -482,19 +503,22 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
 }
 
 void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z_in, const float* rmask,
-                        bf16* z_out, cudaStream_t st) {
+                        bf16* z_out, cudaStream_t st, Split node_sp = Split()) {
   const int R = B * L;
   const std::string e = "translator.trunk.edge_transition_" + std::to_string(blk) + ".";
   const float *W1 = c->P(e + "trunk.0.weight"), *Wf = c->P(e + "final_layer.weight");
-  linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st);
+  const bool tcn = c->opt_node == 1 && c->cur_prec != EXACT && L % 16 == 0;
+  const Split np = tcn ? Split{c->nprime_hi, c->nprime_lo} : Split();
+  linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st, 0,
+         nullptr, 0, nullptr, nullptr, -1, node_sp, np);
   const bool tc = c->opt_pair >= 1 && L % 128 == 0;
-  linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st);
-  linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st);
-  if (tc) {  // the n'_j terms ride along as extra K columns of the MMAs
-    f32_to_bf16(c->nprime, c->nprime_bf16, (long)R * 128, st);
+  linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
+  linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
+  if (tc) {  // the n'_j terms ride along as extra K columns of the MMAs: they need n' in bf16 (= the hi image)
+    if (!np.hi) f32_to_bf16(c->nprime, c->nprime_bf16, (long)R * 128, st);
   } else {
-    linear(c, c->nprime, 128, W1 + 256, 384, nullptr, c->v384, 384, R, 384, 128, st);
-    linear(c, c->nprime, 128, Wf + 256, 384, nullptr, c->q128, 128, R, 128, 128, st);
+    linear(c, c->nprime, 128, W1 + 256, 384, nullptr, c->v384, 384, R, 384, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
+    linear(c, c->nprime, 128, Wf + 256, 384, nullptr, c->q128, 128, R, 128, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
   }
   EdgeTransitionArgs a;
   a.B = B; a.L = L; a.z_in = z_in; a.u = c->u384; a.v = c->v384; a.p = c->p128; a.q = c->q128; a.mask = rmask;
@@ -514,10 +538,9 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
   const bool tc = c->opt_node == 1 && L % 16 == 0;
   if (tc) {
     // in_proj on the tensor cores; its epilogue emits the split-bf16 attention operands: q|k row-major, v transposed per head
-    split_bf16(c->x320, 320, R, 320, c->sa_hi, c->sa_lo, st);
     const auto w = weight_split(c, c->P(tl + "self_attn.in_proj_weight"));
-    TcGemm g;
-    g.A_hi = c->sa_hi; g.A_lo = c->sa_lo; g.a_rows = R; g.a_cols = 320; g.a_pitch = 320;
+    TcGemm g;  // A = x320's split image, written by the producer (concat / norm2 of the previous layer)
+    g.A_hi = c->x320_hi; g.A_lo = c->x320_lo; g.a_rows = R; g.a_cols = 320; g.a_pitch = 320;
     g.B_hi = w.first; g.B_lo = w.second; g.b_rows = 960; g.b_cols = 320; g.b_pitch = 320;
     g.M = R; g.N = 960; g.K = 320; g.passes = 3; g.bias = c->P(tl + "self_attn.in_proj_bias");
     g.out_hi = c->tq_hi; g.out_lo = c->tq_lo; g.ldo = 960;
@@ -536,6 +559,7 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     p.B_hi = c->tvT_hi; p.B_lo = c->tvT_lo; p.b_rows = (size_t)B * TFM_H * TFM_HD; p.b_cols = L; p.b_pitch = L; p.b_rb = TFM_H * TFM_HD; p.b_rh = TFM_HD;
     p.M = L; p.N = TFM_HD; p.K = L; p.nb = B; p.nh = TFM_H; p.passes = 3;
     p.C = c->y320; p.ldc = 320; p.sCb = (long)L * 320; p.sCh = TFM_HD;
+    p.out_hi = c->y320_hi; p.out_lo = c->y320_lo; p.ldo = 320;
     gemm_tc(p, st);
   } else {
     linear(c, c->x320, 320, c->P(tl + "self_attn.in_proj_weight"), 320, c->P(tl + "self_attn.in_proj_bias"), c->qkv, 960, R, 960, 320, st);
@@ -553,11 +577,15 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     h.M = L; h.N = TFM_HD; h.K = L; h.nb = B; h.nh = TFM_H;
     gemm_f32(h, st);
   }
-  linear(c, c->y320, 320, c->P(tl + "self_attn.out_proj.weight"), 320, c->P(tl + "self_attn.out_proj.bias"), c->t320, 320, R, 320, 320, st, 0, c->x320, 320);
-  layernorm(c->t320, nullptr, c->P(tl + "norm1.weight"), c->P(tl + "norm1.bias"), nullptr, c->x320, R, 320, st);
-  linear(c, c->x320, 320, c->P(tl + "linear1.weight"), 320, c->P(tl + "linear1.bias"), c->t320, 320, R, 320, 320, st, 1);
-  linear(c, c->t320, 320, c->P(tl + "linear2.weight"), 320, c->P(tl + "linear2.bias"), c->y320, 320, R, 320, 320, st, 0, c->x320, 320);
-  layernorm(c->y320, nullptr, c->P(tl + "norm2.weight"), c->P(tl + "norm2.bias"), nullptr, c->x320, R, 320, st);
+  const Split x_sp = tc ? Split{c->x320_hi, c->x320_lo} : Split();
+  const Split t_sp = tc ? Split{c->t320_hi, c->t320_lo} : Split();
+  const Split y_sp = tc ? Split{c->y320_hi, c->y320_lo} : Split();
+  linear(c, c->y320, 320, c->P(tl + "self_attn.out_proj.weight"), 320, c->P(tl + "self_attn.out_proj.bias"), c->t320, 320, R, 320, 320, st, 0, c->x320, 320,
+         nullptr, nullptr, -1, y_sp);
+  layernorm(c->t320, nullptr, c->P(tl + "norm1.weight"), c->P(tl + "norm1.bias"), nullptr, c->x320, R, 320, st, x_sp.hi, x_sp.lo);
+  linear(c, c->x320, 320, c->P(tl + "linear1.weight"), 320, c->P(tl + "linear1.bias"), c->t320, 320, R, 320, 320, st, 1, nullptr, 0, nullptr, nullptr, -1, x_sp, t_sp);
+  linear(c, c->t320, 320, c->P(tl + "linear2.weight"), 320, c->P(tl + "linear2.bias"), c->y320, 320, R, 320, 320, st, 0, c->x320, 320, nullptr, nullptr, -1, t_sp);
+  layernorm(c->y320, nullptr, c->P(tl + "norm2.weight"), c->P(tl + "norm2.bias"), nullptr, c->x320, R, 320, st, x_sp.hi, x_sp.lo);
 }
 
 // TranslationIPA.forward (ipa.py:331-387) on the node / pair embeddings already in c->node / c->z
@@ -567,32 +595,45 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
   const std::string tk = "translator.trunk.";
   make_masks(rmask, fixed, c->diffuse, c->keybias, R, st);
   c->cur_prec = TC3;  // residual-stream layers: split-bf16 tensor-core GEMMs (exact fp32 when node_gemm = 0)
+  // Split-bf16 images of the activations are written by whichever kernel produces them (LayerNorm, GEMM epilogue,
+  // concat), so the tensor-core GEMMs that consume them need no separate conversion pass.
+  const bool img = c->opt_node == 1 && L % 16 == 0;
+  auto sp = [&](bf16* hi, bf16* lo) { return img ? Split{hi, lo} : Split(); };
+  const Split node_sp = sp(c->node_hi, c->node_lo), init_sp = sp(c->init_hi, c->init_lo), a_sp = sp(c->a256_hi, c->a256_lo),
+              b_sp = sp(c->b256_hi, c->b256_lo), x_sp = sp(c->x320_hi, c->x320_lo);
   S2S_CUDA(cudaMemcpyAsync(c->init_node, c->node, (size_t)R * 256 * 4, cudaMemcpyDeviceToDevice, st));
+  if (img) {
+    split_bf16(c->node, 256, R, 256, c->node_hi, c->node_lo, st);
+    S2S_CUDA(cudaMemcpyAsync(c->init_hi, c->node_hi, (size_t)R * 256 * 2, cudaMemcpyDeviceToDevice, st));
+    S2S_CUDA(cudaMemcpyAsync(c->init_lo, c->node_lo, (size_t)R * 256 * 2, cudaMemcpyDeviceToDevice, st));
+  }
   split_rigids(rigids_t, c->quat, c->trans, R, st);
   for (int b = 0; b < N_BLK; ++b) {
     const std::string s = std::to_string(b);
     // node = LN(node + ipa(node, z, T) * mask)          (ipa.py:344-351)
-    do_ipa(c, b, B, L, c->node, c->z, c->quat, c->trans, rmask, c->a256, c->node, rmask, st);
+    do_ipa(c, b, B, L, c->node, c->z, c->quat, c->trans, rmask, c->a256, c->node, rmask, st, node_sp);
     layernorm(c->a256, nullptr, c->P(tk + "ipa_ln_" + s + ".weight"), c->P(tk + "ipa_ln_" + s + ".bias"), nullptr, c->node, R, 256, st);
     // sequence transformer on [node | skip(init_node)]   (ipa.py:353-360)
-    linear(c, c->init_node, 256, c->P(tk + "skip_embed_" + s + ".weight"), 256, c->P(tk + "skip_embed_" + s + ".bias"), c->skip64, 64, R, 64, 256, st);
-    concat_skip(c->node, c->skip64, c->x320, R, st);
+    linear(c, c->init_node, 256, c->P(tk + "skip_embed_" + s + ".weight"), 256, c->P(tk + "skip_embed_" + s + ".bias"), c->skip64, 64, R, 64, 256, st, 0,
+           nullptr, 0, nullptr, nullptr, -1, init_sp);
+    concat_skip(c->node, c->skip64, c->x320, R, st, x_sp.hi, x_sp.lo);
     for (int l = 0; l < 2; ++l) do_transformer_layer(c, tk + "transformer_" + s + ".layers." + std::to_string(l) + ".", B, L, st);
-    linear(c, c->x320, 320, c->P(tk + "linear_" + s + ".weight"), 320, c->P(tk + "linear_" + s + ".bias"), c->node, 256, R, 256, 320, st, 0, c->node, 256);
+    linear(c, c->x320, 320, c->P(tk + "linear_" + s + ".weight"), 320, c->P(tk + "linear_" + s + ".bias"), c->node, 256, R, 256, 320, st, 0, c->node, 256,
+           nullptr, nullptr, -1, x_sp, node_sp);
     // node transition + mask                              (layers.py:138-145, ipa.py:363-365)
     const std::string nt = tk + "node_transition_" + s + ".";
-    linear(c, c->node, 256, c->P(nt + "linear_1.weight"), 256, c->P(nt + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1);
-    linear(c, c->a256, 256, c->P(nt + "linear_2.weight"), 256, c->P(nt + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 1);
-    linear(c, c->b256, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), c->a256, 256, R, 256, 256, st, 0, c->node, 256);
-    layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, R, 256, st);
+    linear(c, c->node, 256, c->P(nt + "linear_1.weight"), 256, c->P(nt + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, node_sp, a_sp);
+    linear(c, c->a256, 256, c->P(nt + "linear_2.weight"), 256, c->P(nt + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, a_sp, b_sp);
+    linear(c, c->b256, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), c->a256, 256, R, 256, 256, st, 0, c->node, 256, nullptr, nullptr, -1, b_sp);
+    layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, R, 256, st, node_sp.hi, node_sp.lo);
     // backbone update on node * diffuse_mask, exact fp32    (ipa.py:367-369)
     linear(c, c->node, 256, c->P(tk + "bb_update_" + s + ".linear.weight"), 256, c->P(tk + "bb_update_" + s + ".linear.bias"), c->upd6, 6, R, 6, 256, st, 0, nullptr, 0, c->diffuse, nullptr, EXACT);
     frame_update(c->quat, c->trans, c->upd6, c->diffuse, R, st);
-    if (b < N_BLK - 1) do_edge_transition(c, b, B, L, c->node, c->z, rmask, c->z, st);
+    if (b < N_BLK - 1) do_edge_transition(c, b, B, L, c->node, c->z, rmask, c->z, st, node_sp);
   }
   const std::string tp = "translator.torsion_pred.";
-  linear(c, c->node, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1);
-  linear(c, c->a256, 256, c->P(tp + "linear_2.weight"), 256, c->P(tp + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 0, c->node, 256);
+  linear(c, c->node, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, node_sp, a_sp);
+  linear(c, c->a256, 256, c->P(tp + "linear_2.weight"), 256, c->P(tp + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 0, c->node, 256, nullptr, nullptr, -1, a_sp);
   linear(c, c->b256, 256, c->P(tp + "linear_final.weight"), 256, c->P(tp + "linear_final.bias"), c->psi_u, 2, R, 2, 256, st, 0, nullptr, 0, nullptr, nullptr, EXACT);
   c->cur_prec = EXACT;
   psi_finalize(c->psi_u, gt_psi, fixed, out_psi, R, st);

@@ -199,8 +199,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
           }
         }
         if (a.out_hi) {
-          bf16* hrow = a.out_hi + (long)m * a.ldo + n0;
-          bf16* lrow = a.out_lo ? a.out_lo + (long)m * a.ldo + n0 : nullptr;
+          const long ooff = ib * a.sCb + ih * a.sCh + (long)m * a.ldo + n0;
+          bf16* hrow = a.out_hi + ooff;
+          bf16* lrow = a.out_lo ? a.out_lo + ooff : nullptr;
           if (full && (a.ldo & 7) == 0) {
 #pragma unroll
             for (int e = 0; e < 32; e += 8) {

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) ipa_point_logits_kernel(float* __restrict__ S, const float* __restrict__ q_pts,
                                                                const float* __restrict__ k_pts,
                                                                const float* __restrict__ pt_w, int L) {
-  __shared__ float qs[32][P_Q * 3];
+  __shared__ __align__(16) float qs[32][P_Q * 3];
   const int bh = blockIdx.z, b = bh / N_H, h = bh % N_H;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 64;
   const int tid = threadIdx.x;
@@ -74,19 +74,24 @@ __global__ void __launch_bounds__(256) ipa_point_logits_kernel(float* __restrict
   __syncthreads();
   if (j >= L) return;
   const float w = pt_w[h];
+  float* Sp = S + (((long)b * N_H + h) * L + i0 + ig * 8) * L + j;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const int il = ig * 8 + u, i = i0 + il;
-    if (i >= L) break;
+    const int il = ig * 8 + u;
+    if (i0 + il >= L) break;
+    float q[24];
+#pragma unroll
+    for (int v4 = 0; v4 < 6; ++v4) {  // warp-uniform address: one broadcast 128-bit read per 4 coordinates
+      const float4 t = *reinterpret_cast<const float4*>(&qs[il][4 * v4]);
+      q[4 * v4] = t.x; q[4 * v4 + 1] = t.y; q[4 * v4 + 2] = t.z; q[4 * v4 + 3] = t.w;
+    }
     float acc = 0.f;
 #pragma unroll
     for (int p = 0; p < P_Q; ++p) {
-      const float dx = qs[il][p * 3] - kp[p * 3];
-      const float dy = qs[il][p * 3 + 1] - kp[p * 3 + 1];
-      const float dz = qs[il][p * 3 + 2] - kp[p * 3 + 2];
+      const float dx = q[p * 3] - kp[p * 3], dy = q[p * 3 + 1] - kp[p * 3 + 1], dz = q[p * 3 + 2] - kp[p * 3 + 2];
       acc += (dx * dx + dy * dy + dz * dz) * w;
     }
-    S[(((long)b * N_H + h) * L + i) * L + j] += acc * (-0.5f);
+    Sp[(long)u * L] += acc * (-0.5f);
   }
 }
 
@@ -102,6 +107,8 @@ __global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) 
   bf16* Ph = reinterpret_cast<bf16*>(P_s + 8 * LP4);                   // [8][LP8] bf16 hi part of P
   bf16* Pl = Ph + 8 * LP8;                                             // [8][LP8] bf16 lo part of P
   float* zsum = reinterpret_cast<float*>(Pl + 8 * LP8);                // [8][C_Z+4]  sum_j P[h][j] z[j][:]
+  float* mask_s = zsum + 8 * (C_Z + 4);                                // [Lp] key mask of this decoy
+  float* wdz_s = mask_s + Lp;                                          // [128][32] down_z weight (transposed)
 
   const int b = blockIdx.x / L, i = blockIdx.x % L;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -113,7 +120,9 @@ __global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) 
     const int j = idx / (C_Z / 8), c8 = idx % (C_Z / 8);
     cp_async16(z_s + j * ZP + c8 * 8, zg + (long)j * C_Z + c8 * 8);
   }
+  for (int idx = tid; idx < C_Z * 32 / 4; idx += 256) cp_async16(wdz_s + idx * 4, a.Wdz_t + idx * 4);
   cp_async_commit();
+  for (int j = tid; j < Lp; j += 256) mask_s[j] = j < L ? a.mask[(long)b * L + j] : 0.f;
   for (int idx = tid; idx < (Lp - L) * (C_Z / 8); idx += 256) {
     const int j = L + idx / (C_Z / 8), c8 = idx % (C_Z / 8);
     *reinterpret_cast<uint4*>(z_s + j * ZP + c8 * 8) = make_uint4(0, 0, 0, 0);
@@ -133,6 +142,7 @@ __global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) 
     wbl[ks][1] = *reinterpret_cast<const uint32_t*>(a.Wb_lo + g * C_Z + k0 + 8);
   }
   const float m_i = a.mask[(long)b * L + i];
+  const float bias_h[2] = {a.bb[2 * t], a.bb[2 * t + 1]};  // this lane's two heads in the bias MMA fragment
   cp_async_wait<0>();
   __syncthreads();
 
@@ -152,10 +162,7 @@ __global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) 
     for (int e = 0; e < 4; ++e) {
       const int h = 2 * t + (e & 1);
       const int j = mt * 16 + g + (e >> 1) * 8;
-      if (j < L) {
-        const float m_j = a.mask[(long)b * L + j];
-        P_s[h * LP4 + j] += SQRT1_3 * (d[e] + a.bb[h]) + 1e5f * (m_i * m_j - 1.f);
-      }
+      if (j < L) P_s[h * LP4 + j] += SQRT1_3 * (d[e] + bias_h[e & 1]) + 1e5f * (m_i * mask_s[j] - 1.f);
     }
   }
   __syncthreads();
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) 
     float acc = a.bdz[dd];
     const float* zs = zsum + h * (C_Z + 4);
 #pragma unroll 8
-    for (int c = 0; c < C_Z; ++c) acc = fmaf(a.Wdz_t[c * 32 + dd], zs[c], acc);
+    for (int c = 0; c < C_Z; ++c) acc = fmaf(wdz_s[c * 32 + dd], zs[c], acc);
     a.o_pair[((long)b * L + i) * a.ld_opair + h * 32 + dd] = acc;
   }
 }
@@ -271,8 +278,8 @@ void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const fl
 
 void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st) {
   const int Lp = (a.L + 15) & ~15;
-  const size_t smem = (size_t)Lp * ZP * 2 + 8 * (Lp + 4) * 4 + 2 * 8 * (Lp + 8) * 2 + 8 * (C_Z + 4) * 4;
-  S2S_CHECK(smem <= 227 * 1024, "ipa_pair_attention: chain too long for one shared-memory slab (L <= 768)");
+  const size_t smem = (size_t)Lp * ZP * 2 + 8 * (Lp + 4) * 4 + 2 * 8 * (Lp + 8) * 2 + 8 * (C_Z + 4) * 4 + Lp * 4 + C_Z * 32 * 4;
+  S2S_CHECK(smem <= 227 * 1024, "ipa_pair_attention: chain too long for one shared-memory slab (L <= 704)");
   static size_t configured = 0;
   if (smem > configured) {
     S2S_CUDA(cudaFuncSetAttribute(ipa_pair_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

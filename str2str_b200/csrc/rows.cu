@@ -11,7 +11,7 @@ template <int D>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         const float* __restrict__ rowscale, float* __restrict__ y,
-                                                        int rows) {
+                                                        int rows, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo) {
   constexpr int PER = D / 32;
   const int row = blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -37,7 +37,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int c = lane + 32 * i;
-    y[(long)row * D + c] = ((v[i] - mean) * rstd * w[c] + b[c]) * sc;
+    const float o = ((v[i] - mean) * rstd * w[c] + b[c]) * sc;
+    y[(long)row * D + c] = o;
+    if (y_hi) {  // split-bf16 image for a following tensor-core GEMM
+      const bf16 hi = __float2bfloat16_rn(o);
+      y_hi[(long)row * D + c] = hi;
+      y_lo[(long)row * D + c] = __float2bfloat16_rn(o - __bfloat162float(hi));
+    }
   }
 }
 
@@ -142,12 +148,19 @@ __global__ void psi_finalize_kernel(const float* __restrict__ u, const float* __
 }
 
 __global__ void concat_skip_kernel(const float* __restrict__ node, const float* __restrict__ skip,
-                                   float* __restrict__ out, long rows) {
+                                   float* __restrict__ out, long rows, bf16* __restrict__ out_hi,
+                                   bf16* __restrict__ out_lo) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * D_TFM) return;
   const long r = i / D_TFM;
   const int c = (int)(i % D_TFM);
-  out[i] = c < C_S ? node[r * C_S + c] : skip[r * D_SKIP + (c - C_S)];
+  const float v = c < C_S ? node[r * C_S + c] : skip[r * D_SKIP + (c - C_S)];
+  out[i] = v;
+  if (out_hi) {
+    const bf16 hi = __float2bfloat16_rn(v);
+    out_hi[i] = hi;
+    out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
 }
 
 __global__ void masks_kernel(const float* __restrict__ rmask, const float* __restrict__ fixed,
@@ -161,15 +174,15 @@ __global__ void masks_kernel(const float* __restrict__ rmask, const float* __res
 }  // namespace
 
 void layernorm(const float* x, const float* res, const float* w, const float* b, const float* rowscale, float* y,
-               int rows, int D, cudaStream_t st) {
+               int rows, int D, cudaStream_t st, bf16* y_hi, bf16* y_lo) {
   S2S_PROF("layernorm", st);
   const int grid = ceil_div(rows, 8);
   if (D == 128)
-    layernorm_kernel<128><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows);
+    layernorm_kernel<128><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows, y_hi, y_lo);
   else if (D == 256)
-    layernorm_kernel<256><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows);
+    layernorm_kernel<256><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows, y_hi, y_lo);
   else if (D == 320)
-    layernorm_kernel<320><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows);
+    layernorm_kernel<320><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows, y_hi, y_lo);
   else
     S2S_CHECK(false, "layernorm: unsupported width");
   S2S_LAUNCH_CHECK();
@@ -198,9 +211,9 @@ void psi_finalize(const float* u, const float* gt_psi, const float* fixed, float
   S2S_LAUNCH_CHECK();
 }
 
-void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st) {
+void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st, bf16* out_hi, bf16* out_lo) {
   S2S_PROF("concat_skip", st);
-  concat_skip_kernel<<<ceil_div(rows * D_TFM, 256), 256, 0, st>>>(node, skip, out, rows);
+  concat_skip_kernel<<<ceil_div(rows * D_TFM, 256), 256, 0, st>>>(node, skip, out, rows, out_hi, out_lo);
   S2S_LAUNCH_CHECK();
 }
 

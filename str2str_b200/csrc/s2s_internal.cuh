@@ -30,7 +30,8 @@ struct TcGemm {
   float alpha = 1.f;
   const float *bias = nullptr, *row_pre = nullptr, *row_post = nullptr, *res = nullptr; long ldres = 0;
   float* C = nullptr; long ldc = 0, sCb = 0, sCh = 0;
-  bf16 *out_hi = nullptr, *out_lo = nullptr; long ldo = 0;  // optional bf16 (split) copies of the result
+  bf16 *out_hi = nullptr, *out_lo = nullptr; long ldo = 0;  // optional bf16 (split) copies of the result; batched calls
+                                                            // index them like C (sCb / sCh), so ldo must equal ldc there
   // optional transposed (per head) bf16 copy of the 'v' columns of a fused q|k|v projection: column n is v of head
   // h = (n - vt_col0) / vt_stride, channel c = (n - vt_col0) % vt_stride - vt_off when 0 <= c < vt_width
   bf16 *out_vt = nullptr, *out_vt_lo = nullptr;
@@ -41,14 +42,15 @@ void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* l
 
 // ---- rows.cu ------------------------------------------------------------------------------------------
 void layernorm(const float* x, const float* res, const float* w, const float* b, const float* rowscale, float* y,
-               int rows, int D, cudaStream_t st);
+               int rows, int D, cudaStream_t st, bf16* y_hi = nullptr, bf16* y_lo = nullptr);
 void softmax_keybias(float* S, const float* keybias, int nb, int nh, int L, cudaStream_t st, bf16* P_hi = nullptr,
                      bf16* P_lo = nullptr);
 void node_features(const float* t, const long long* ridx, const float* fixed, const float* tfreq,
                    const float* pdenom, float* feat, float* tf, int B, int L, cudaStream_t st);
 void relpos_features(const float* pdenom, float* out, int d_min, int n, cudaStream_t st);
 void psi_finalize(const float* u, const float* gt_psi, const float* fixed, float* psi, int rows, cudaStream_t st);
-void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st);
+void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st, bf16* out_hi = nullptr,
+                 bf16* out_lo = nullptr);
 void make_masks(const float* rmask, const float* fixed, float* diffuse, float* keybias, int n, cudaStream_t st);
 
 // ---- pair kernels -------------------------------------------------------------------------------------
