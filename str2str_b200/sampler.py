@@ -192,6 +192,30 @@ class ForwardBackwardSampler:
         return all_gather_decoys(torch.as_tensor(local), share).numpy()
 
 
+def plan_mixed_lengths(counts: Dict[int, int], world: int, replica_per_batch: int = 64):
+    """Mixed-length workload (BASELINE cfg 5): split every (length, n_decoys) request into batches of at most
+    `replica_per_batch` decoys (and no more than an even share per rank, so that one long chain cannot unbalance the
+    plan) and assign the batches to ranks by longest-processing-time-first on the cost model
+    cost(L, B) = B * L^2 (the pair track dominates).  Returns one list of (L, B) batches per rank.
+    Lengths are never padded against each other: each batch runs un-padded at its own L, which is also what defines
+    the reference result for this configuration."""
+    batches = []
+    for L, n in counts.items():
+        share = max(1, -(-n // world))
+        while n > 0:
+            b = min(replica_per_batch, share, n)
+            batches.append((L, b))
+            n -= b
+    batches.sort(key=lambda lb: -(lb[1] * lb[0] ** 2))
+    load = [0] * world
+    plan = [[] for _ in range(world)]
+    for L, b in batches:
+        r = min(range(world), key=lambda k: load[k])
+        plan[r].append((L, b))
+        load[r] += b * L * L
+    return plan
+
+
 def shard_bounds(n: int, world: int):
     """Contiguous, balanced split of n decoys over `world` ranks: bounds[r] .. bounds[r+1]."""
     base, rem = divmod(n, world)

@@ -198,7 +198,7 @@ def test_trajectory_masked_vs_reference_golden(golden_dir, params):
     _run_traj(golden_dir, params, "traj_masked_L24_n6.npz", (1, 1), True)
 
 
-@pytest.mark.parametrize("L", [128, 256])
+@pytest.mark.parametrize("L", [128, 256, 384])
 def test_pair_kernels_tc_vs_simt(params, L):
     """tcgen05 pair kernels against the SIMT restatement with identical rounding points, full forward."""
     B = 2
@@ -287,4 +287,23 @@ def test_forward_tensor_core_vs_exact_L128(params):
     valid = feats["residue_mask"].bool()
     r = rel(outs[1][valid][:, 4:], outs[0][valid][:, 4:])
     print(f"forward L=128 tensor-core vs exact: C-alpha rel {r:.2e}")
+    assert r < 2e-5
+
+
+def test_long_chain_forward_L512(params):
+    """BASELINE cfg 4 chain length (512 residues): the whole forward runs (IPA slab = 128 KB of shared memory, 1 CTA/SM)
+    and agrees between the tcgen05 path and the SIMT/exact path."""
+    B, L = 1, 512
+    feats = synthetic.make_features(B, L, seed=23)
+    q, x = synthetic.make_backbone(L, seed=23)
+    feats["rigids_t"] = torch.cat([q, x], -1)[None].repeat(B, 1, 1).float()
+    feats["sc_ca_t"] = x[None].repeat(B, 1, 1).float()
+    feats["t"] = torch.tensor([0.5])
+    outs = []
+    for mode in ((0, 0), (1, 1)):
+        net = make_net(params, mode)
+        with torch.no_grad():
+            outs.append(net(cuda(feats), as_tensor_7=True)["rigids"].cpu())
+    r = rel(outs[1][..., 4:], outs[0][..., 4:])
+    print(f"forward L=512 tensor-core vs exact: C-alpha rel {r:.2e}")
     assert r < 2e-5

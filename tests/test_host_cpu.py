@@ -97,6 +97,18 @@ def test_shard_bounds():
     assert shard_bounds(2, 4) == [0, 1, 2, 2, 2]
 
 
+def test_mixed_length_plan_is_balanced():
+    from str2str_b200.sampler import plan_mixed_lengths
+
+    plan = plan_mixed_lengths({64: 64, 128: 64, 256: 64, 384: 64}, world=8, replica_per_batch=16)  # BASELINE cfg 5
+    assert len(plan) == 8
+    flat = [lb for r in plan for lb in r]
+    assert sum(b for L, b in flat if L == 384) == 64 and sum(b for _, b in flat) == 256
+    loads = [sum(b * L * L for L, b in r) for r in plan]
+    assert max(loads) <= 1.25 * (sum(loads) / 8)  # LPT keeps ranks within 25 % of the mean cost
+    assert plan_mixed_lengths({64: 3}, world=2, replica_per_batch=2) in ([[(64, 2)], [(64, 1)]], [[(64, 1)], [(64, 2)]])
+
+
 _GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
