@@ -99,7 +99,7 @@ struct Slab {  // bump allocator over one cudaMalloc
 
 struct IpaW {
   float *proj_w, *proj_b;  // [6816][256], [6816]: q | kv | q_points | kv_points
-  bf16 *Wb_hi, *Wb_lo;
+  bf16 *Wb_hi, *Wb_lo, *wb_img;
   float *Wdz_t, *pt_w;
 };
 struct EtW {
@@ -115,7 +115,7 @@ using namespace s2s;
 struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
-  int opt_pair = 1, opt_node = 0;
+  int opt_pair = 1, opt_node = 0, opt_ipa = 1;
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
   float *tfreq = nullptr, *pdenom = nullptr, *bin_lower = nullptr, *backbone = nullptr;
@@ -134,6 +134,8 @@ struct s2s_ctx {
   // tensor-core node track: bf16 hi/lo images of every weight matrix, scratch split buffers, attention operands
   std::map<const float*, std::pair<size_t, std::pair<bf16*, bf16*>>> wsplit;  // fp32 base -> (numel, (hi, lo))
   bf16 *sa_hi, *sa_lo, *qkv_bf16, *vT, *P_bf16;
+  bf16 *qp_aug, *kp_aug, *vpT_hi, *vpT_lo, *P_lo;  // fused-logits / split-P operands of the second-generation IPA path
+  float* colbias;
   bf16 *tq_hi, *tq_lo, *tvT_hi, *tvT_lo, *tP_lo;  // sequence-transformer attention operands (split bf16)
   // split-bf16 companions of the node-track activations, written by the producing kernel's epilogue
   bf16 *node_hi, *node_lo, *init_hi, *init_lo, *a256_hi, *a256_lo, *b256_hi, *b256_lo;
@@ -267,6 +269,8 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
     w.Wb_hi = c->wslab.take<bf16>(8 * 128);
     w.Wb_lo = c->wslab.take<bf16>(8 * 128);
     prep_split(c->P(ip + "linear_b.weight"), 128, 8, 0, 128, w.Wb_hi, w.Wb_lo, st);
+    w.wb_img = c->wslab.take<bf16>(ipa_wb_img_elems());
+    build_ipa_wb_img(c->P(ip + "linear_b.weight"), w.wb_img, st);
     w.Wdz_t = c->wslab.take<float>(128 * 32);
     prep_t_f32(c->P(ip + "down_z.weight"), 128, 32, 0, 128, w.Wdz_t, st);
     w.pt_w = c->wslab.take<float>(8);
@@ -354,6 +358,8 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     for (int k = 0; k < 8; ++k) add(R * 256, 2);
     for (int k = 0; k < 6; ++k) add(R * 320, 2);
     add(R * 128, 2);
+    add(R * N_H * PT_K, 2); add(R * N_H * PT_K, 2); add(R * N_H * P_V * 3, 2); add(R * N_H * P_V * 3, 2);
+    add((size_t)B * N_H * L * L, 2); add(R * N_H, 4);
     c->ws.cap = bytes + 4096;
     S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
     Slab& w = c->ws;
@@ -380,6 +386,9 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->x320_hi = w.take<bf16>(R * 320); c->x320_lo = w.take<bf16>(R * 320); c->t320_hi = w.take<bf16>(R * 320); c->t320_lo = w.take<bf16>(R * 320);
     c->y320_hi = w.take<bf16>(R * 320); c->y320_lo = w.take<bf16>(R * 320);
     c->nprime_hi = c->nprime_bf16; c->nprime_lo = w.take<bf16>(R * 128);
+    c->qp_aug = w.take<bf16>(R * N_H * PT_K); c->kp_aug = w.take<bf16>(R * N_H * PT_K);
+    c->vpT_hi = w.take<bf16>(R * N_H * P_V * 3); c->vpT_lo = w.take<bf16>(R * N_H * P_V * 3);
+    c->P_lo = w.take<bf16>((size_t)B * N_H * L * L); c->colbias = w.take<float>(R * N_H);
     c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
   }
   // relative-position table: Tpos[r] = W1[:,66:98] pos(d_min + r)   (denoising_ipa.py:144-149)
@@ -450,13 +459,26 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   } else {
     linear(c, node, 256, w.proj_w, 256, w.proj_b, c->proj, 6816, R, 6816, 256, st, 0, nullptr, 0, nullptr, nullptr, EXACT);
   }
-  ipa_points(c->proj + 6144, 6816, c->proj + 6336, 6816, quat, trans, c->q_pts, c->k_pts, c->v_pts, R, st);
+  // second-generation path: point term folded into the logits GEMM, tcgen05 pair kernel, split-bf16 P
+  const bool fused = tc && c->opt_ipa == 1 && ipa_pair_attention_tc_supported(L);
+  IpaPointsAug aug;
+  if (fused) {
+    aug.qp_aug = c->qp_aug; aug.kp_aug = c->kp_aug; aug.colbias = c->colbias; aug.vpT_hi = c->vpT_hi; aug.vpT_lo = c->vpT_lo;
+    aug.pt_w = w.pt_w; aug.inv_alpha = 1.f / qk_scale; aug.L = L;
+  }
+  ipa_points(c->proj + 6144, 6816, c->proj + 6336, 6816, quat, trans, c->q_pts, c->k_pts, c->v_pts, R, st, aug);
   if (tc) {  // S = scale * q.k^T, batched over (decoy, head)
     TcGemm g;
     g.A_hi = c->qkv_bf16; g.a_rows = R; g.a_cols = 6144; g.a_pitch = 6144; g.a_rb = L; g.a_ch = 256;
     g.B_hi = c->qkv_bf16 + 2048; g.b_rows = R; g.b_cols = 4096; g.b_pitch = 6144; g.b_rb = L; g.b_ch = 512;
     g.M = L; g.N = L; g.K = 256; g.nb = B; g.nh = N_H; g.passes = 1; g.alpha = qk_scale;
     g.C = c->S; g.ldc = L; g.sCb = (long)N_H * L * L; g.sCh = (long)L * L;
+    if (fused) {  // + w_h q_pts.k_pts - 0.5 w_h |k_pts|^2  (= the point term up to a per-query constant)
+      g.A2 = c->qp_aug; g.a2_rows = R; g.a2_cols = N_H * PT_K; g.a2_pitch = N_H * PT_K; g.a2_rb = L; g.a2_ch = PT_K;
+      g.B2 = c->kp_aug; g.b2_rows = R; g.b2_cols = N_H * PT_K; g.b2_pitch = N_H * PT_K; g.b2_rb = L; g.b2_ch = PT_K;
+      g.K2 = PT_K;
+      g.bias = c->colbias; g.bias_sb = (long)N_H * L; g.bias_sh = L;
+    }
     gemm_tc(g, st);
   } else {
     GemmArgs g;
@@ -466,14 +488,15 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
     g.M = L; g.N = L; g.K = 256; g.nb = B; g.nh = N_H; g.alpha = qk_scale;
     gemm_f32(g, st);
   }
-  ipa_point_logits(c->S, c->q_pts, c->k_pts, w.pt_w, B, L, st);
+  if (!fused) ipa_point_logits(c->S, c->q_pts, c->k_pts, w.pt_w, B, L, st);
   IpaPairArgs p;
   p.B = B; p.L = L; p.z = z; p.S = c->S; p.mask = rmask;
   p.Wb_hi = w.Wb_hi; p.Wb_lo = w.Wb_lo; p.bb = c->P(ip + "linear_b.bias");
   p.Wdz_t = w.Wdz_t; p.bdz = c->P(ip + "down_z.bias");
   p.o_pair = c->feats + (N_H * C_H + 4 * N_H * P_V); p.ld_opair = IPA_FEAT;
   p.P_bf16 = tc ? c->P_bf16 : nullptr;
-  ipa_pair_attention(p, st);
+  p.P_lo = c->P_lo; p.wb_img = w.wb_img;
+  if (fused) ipa_pair_attention_tc(p, st); else ipa_pair_attention(p, st);
   if (tc) {  // o = P v -> feats[:, h*256 + c]
     TcGemm g;
     g.A_hi = c->P_bf16; g.a_rows = (size_t)B * N_H * L; g.a_cols = L; g.a_pitch = L; g.a_rb = N_H * L; g.a_rh = L;
@@ -482,7 +505,14 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
     g.C = c->feats; g.ldc = IPA_FEAT; g.sCb = (long)L * IPA_FEAT; g.sCh = C_H;
     gemm_tc(g, st);
   }
-  {
+  if (fused) {  // o_pt (global frame) = P v_pts, split-bf16 on the tensor cores
+    TcGemm g;
+    g.A_hi = c->P_bf16; g.A_lo = c->P_lo; g.a_rows = (size_t)B * N_H * L; g.a_cols = L; g.a_pitch = L; g.a_rb = N_H * L; g.a_rh = L;
+    g.B_hi = c->vpT_hi; g.B_lo = c->vpT_lo; g.b_rows = (size_t)B * N_H * P_V * 3; g.b_cols = L; g.b_pitch = L; g.b_rb = N_H * P_V * 3; g.b_rh = P_V * 3;
+    g.M = L; g.N = P_V * 3; g.K = L; g.nb = B; g.nh = N_H; g.passes = 3;
+    g.C = c->opt; g.ldc = N_H * P_V * 3; g.sCb = (long)L * N_H * P_V * 3; g.sCh = P_V * 3;
+    gemm_tc(g, st);
+  } else {
     GemmArgs g;
     g.A = c->S; g.lda = L; g.sAb = (long)N_H * L * L; g.sAh = (long)L * L;
     g.M = L; g.K = L; g.nb = B; g.nh = N_H; g.b_kn = 1;
@@ -728,6 +758,7 @@ int s2s_set_option(s2s_ctx* c, const char* key, int value) {
     const std::string k = key;
     if (k == "pair_kernels") { S2S_CHECK(value >= 0 && value <= 2, "pair_kernels: 0|1|2"); c->opt_pair = value; }
     else if (k == "node_gemm") { S2S_CHECK(value == 0 || value == 1, "node_gemm: 0|1"); c->opt_node = value; }
+    else if (k == "ipa_kernels") { S2S_CHECK(value == 0 || value == 1, "ipa_kernels: 0|1"); c->opt_ipa = value; }
     else S2S_CHECK(false, "unknown option " + k);
   });
 }

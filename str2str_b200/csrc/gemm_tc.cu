@@ -33,6 +33,9 @@ struct TcKernelArgs {
   long ldo;
   bf16 *out_vt, *out_vt_lo;  // optional transposed bf16 (hi, lo) copy of the v columns of a fused q|k|v projection
   int dbg;                // timing experiments only (S2S_GEMM_DEBUG): 8 no TMA, 16 no MMA, 32 no epilogue
+  // second K segment (passes == 1 only): K2 more reduction columns fetched through the mAl / mBl maps
+  int K2, a2_cb, a2_ch, a2_rb, a2_rh, b2_cb, b2_ch, b2_rb, b2_rh;
+  long bias_sb, bias_sh;  // batch strides of `bias` (0: one bias vector for every batch)
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -68,6 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int MT = (a.M + TM - 1) / TM, NT = (a.N + 127) / 128, KB = (a.K + KBLK - 1) / KBLK;
+  const int KB2 = (a.K2 + KBLK - 1) / KBLK, KBT = KB + KB2;
   const int n_tiles = a.nb * a.nh * MT * NT;
   constexpr uint32_t IDESC = make_idesc(128, 128);
 
@@ -79,12 +83,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         const int ib = bz / a.nh, ih = bz % a.nh;
         const int arow = ib * a.a_rb + ih * a.a_rh + mt * TM, acol = ib * a.a_cb + ih * a.a_ch;
         const int brow = ib * a.b_rb + ih * a.b_rh + nt * 128, bcol = ib * a.b_cb + ih * a.b_ch;
-        for (int kb = 0; kb < KB; ++kb, ++cnt) {
+        for (int kb = 0; kb < KBT; ++kb, ++cnt) {
           const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
           mbar_wait(&s_empty[s], ph ^ 1);
           if (a.dbg & 8) { mbar_arrive(&s_full[s]); continue; }
           mbar_expect_tx(&s_full[s], stage_bytes);
           unsigned char* st = smem + s * stage_bytes;
+          if (kb >= KB) {  // second K segment
+            const int k2 = (kb - KB) * KBLK;
+            tma_load_2d(st, &mAl, ib * a.a2_cb + ih * a.a2_ch + k2, ib * a.a2_rb + ih * a.a2_rh + mt * TM, &s_full[s]);
+            tma_load_2d(st + TILE_BYTES, &mBl, ib * a.b2_cb + ih * a.b2_ch + k2, ib * a.b2_rb + ih * a.b2_rh + nt * 128, &s_full[s]);
+            continue;
+          }
           tma_load_2d(st, &mAh, acol + kb * KBLK, arow, &s_full[s]);
           tma_load_2d(st + TILE_BYTES, &mBh, bcol + kb * KBLK, brow, &s_full[s]);
           if (a.passes == 3) {
@@ -105,12 +115,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
       mbar_wait(&acc_empty[ab], aph ^ 1);
       tc_fence_after();
       const uint32_t d = tmem + ab * 128;
-      for (int kb = 0; kb < KB; ++kb, ++cnt) {
+      for (int kb = 0; kb < KBT; ++kb, ++cnt) {
         const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
         mbar_wait(&s_full[s], ph);
         tc_fence_after();
         const uint32_t st = ring + s * stage_units;
-        const int ksteps = (min(KBLK, a.K - kb * KBLK) + 15) / 16;
+        const int ksteps = (min(KBLK, kb < KB ? a.K - kb * KBLK : a.K2 - (kb - KB) * KBLK) + 15) / 16;
         if (elect_one()) {
           if (!(a.dbg & 16)) {
             for (int k = 0; k < ksteps; ++k) {
@@ -142,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
       const float post = (row_ok && a.row_post) ? a.row_post[m] : 1.f;
       float* crow = a.C ? a.C + ib * a.sCb + ih * a.sCh + (long)m * a.ldc : nullptr;
       const float* rrow = a.res ? a.res + ib * a.sCb + ih * a.sCh + (long)m * a.ldres : nullptr;
+      const float* bias = a.bias ? a.bias + ib * a.bias_sb + ih * a.bias_sh : nullptr;
       mbar_wait(&acc_full[ab], aph);
       tc_fence_after();
       const uint32_t taddr = tmem + ab * 128 + ((uint32_t)(q * 32) << 16);
@@ -156,17 +167,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         const bool vec_ok = full && (a.ldres & 3) == 0;
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] *= pre;
-        if (a.bias) {
+        if (bias) {
           if (full) {
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + e));
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + e));
               v[e] += bv.x; v[e + 1] += bv.y; v[e + 2] += bv.z; v[e + 3] += bv.w;
             }
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (n0 + e < a.N) v[e] += a.bias[n0 + e];
+              if (n0 + e < a.N) v[e] += bias[n0 + e];
           }
         }
         if (a.relu) {
@@ -299,11 +310,17 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   S2S_CHECK(g.passes == 1 || g.passes == 3, "gemm_tc: passes must be 1 or 3");
   S2S_CHECK(g.A_hi && g.B_hi && (g.passes == 1 || (g.A_lo && g.B_lo)), "gemm_tc: missing operand");
   const CUtensorMap mAh = make_bf16_2d_map(g.A_hi, g.a_rows, g.a_cols, g.a_pitch);
-  const CUtensorMap mAl = g.passes == 3 ? make_bf16_2d_map(g.A_lo, g.a_rows, g.a_cols, g.a_pitch) : mAh;
+  S2S_CHECK(g.K2 == 0 || (g.passes == 1 && g.A2 && g.B2 && g.K2 % 16 == 0), "gemm_tc: a second K segment needs passes == 1 and both operands");
+  const CUtensorMap mAl = g.passes == 3 ? make_bf16_2d_map(g.A_lo, g.a_rows, g.a_cols, g.a_pitch)
+                          : g.K2     ? make_bf16_2d_map(g.A2, g.a2_rows, g.a2_cols, g.a2_pitch) : mAh;
   const CUtensorMap mBh = make_bf16_2d_map(g.B_hi, g.b_rows, g.b_cols, g.b_pitch);
-  const CUtensorMap mBl = g.passes == 3 ? make_bf16_2d_map(g.B_lo, g.b_rows, g.b_cols, g.b_pitch) : mBh;
+  const CUtensorMap mBl = g.passes == 3 ? make_bf16_2d_map(g.B_lo, g.b_rows, g.b_cols, g.b_pitch)
+                          : g.K2     ? make_bf16_2d_map(g.B2, g.b2_rows, g.b2_cols, g.b2_pitch) : mBh;
   TcKernelArgs k;
   k.dbg = 0;
+  k.K2 = g.K2; k.a2_cb = g.a2_cb; k.a2_ch = g.a2_ch; k.a2_rb = g.a2_rb; k.a2_rh = g.a2_rh;
+  k.b2_cb = g.b2_cb; k.b2_ch = g.b2_ch; k.b2_rb = g.b2_rb; k.b2_rh = g.b2_rh;
+  k.bias_sb = g.bias_sb; k.bias_sh = g.bias_sh;
   k.a_cb = g.a_cb; k.a_ch = g.a_ch; k.a_rb = g.a_rb; k.a_rh = g.a_rh;
   k.b_cb = g.b_cb; k.b_ch = g.b_ch; k.b_rb = g.b_rb; k.b_rh = g.b_rh;
   k.M = g.M; k.N = g.N; k.K = g.K; k.nb = g.nb; k.nh = g.nh; k.passes = g.passes; k.relu = g.relu; k.vt_L = g.vt_L;
@@ -325,7 +342,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
     configured = true;
   }
   const int tiles = g.nb * g.nh * ceil_div(g.M, TM) * ceil_div(g.N, 128);
-  S2S_PROF(g_profile_on ? prof_intern("gemm_tc M" + std::to_string(g.M) + " N" + std::to_string(g.N) + " K" + std::to_string(g.K) + " p" + std::to_string(g.passes) + " b" + std::to_string(g.nb * g.nh)) : "gemm_tc", st);
+  S2S_PROF(g_profile_on ? prof_intern("gemm_tc M" + std::to_string(g.M) + " N" + std::to_string(g.N) +  " K" + std::to_string(g.K + g.K2) + " p" + std::to_string(g.passes) + " b" + std::to_string(g.nb * g.nh)) : "gemm_tc", st);
   gemm_tc_kernel<<<tiles < sm_count() ? tiles : sm_count(), 192, smem, st>>>(mAh, mAl, mBh, mBl, k);
   S2S_LAUNCH_CHECK();
 }

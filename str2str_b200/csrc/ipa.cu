@@ -11,13 +11,20 @@ namespace s2s {
 
 namespace {
 
-// raw point projections -> global-frame points (ipa.py:144-171): x|y|z chunk layout, R p + t (t in nm)
+// raw point projections -> global-frame points (ipa.py:144-171): x|y|z chunk layout, R p + t (t in nm).
+// With `aug` set the kernel also writes the tensor-core operands of the fused logits / value GEMMs:
+//   qp_aug / kp_aug [row][head][PT_K] bf16: sqrt(w_h) * points as (hi | lo | hi) and (hi | hi | lo) split-bf16 triples, so that
+//     one bf16 MMA over these 72 (+8 zero) columns gives  w_h q_pts.k_pts  to ~2^-17 relative;
+//   colbias [b][h][j] = -0.5 w_h |k_pts_j|^2.  Together: -0.5 w_h |q - k|^2 up to a per-query constant, which the
+//     softmax over keys cancels exactly (ipa.py:191-205,215);
+//   vpT_hi / vpT_lo [b][h][36][L]: transposed split-bf16 value points (B operand of P.v_pts).
 __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict__ qp, long ld_q,
                                                          const float* __restrict__ kvp, long ld_kv,
                                                          const float* __restrict__ quat,
                                                          const float* __restrict__ trans, float* __restrict__ q_pts,
                                                          float* __restrict__ k_pts, float* __restrict__ v_pts,
-                                                         int rows) {
+                                                         int rows, IpaPointsAug aug) {
+  __shared__ float k2_s[N_H * P_Q];
   const int r = blockIdx.x;
   const int tid = threadIdx.x;
   if (r >= rows) return;
@@ -26,24 +33,70 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
   quat_to_rot(q, R);
   const float tx = trans[r * 3], ty = trans[r * 3 + 1], tz = trans[r * 3 + 2];
   constexpr int NQ = N_H * P_Q, NKV = N_H * (P_Q + P_V);
-  if (tid >= NQ + NKV) return;
-  float x, y, z;
-  float* dst;
-  if (tid < NQ) {
-    x = qp[r * ld_q + tid];
-    y = qp[r * ld_q + NQ + tid];
-    z = qp[r * ld_q + 2 * NQ + tid];
-    dst = q_pts + ((long)r * NQ + tid) * 3;
-  } else {
-    const int k = tid - NQ, h = k / (P_Q + P_V), p = k % (P_Q + P_V);
-    x = kvp[r * ld_kv + k];
-    y = kvp[r * ld_kv + NKV + k];
-    z = kvp[r * ld_kv + 2 * NKV + k];
-    dst = p < P_Q ? k_pts + (((long)r * N_H + h) * P_Q + p) * 3 : v_pts + (((long)r * N_H + h) * P_V + (p - P_Q)) * 3;
+  const bool active = tid < NQ + NKV;
+  int kind = -1, h = 0, p = 0;  // 0 query point, 1 key point, 2 value point
+  float o[3] = {0.f, 0.f, 0.f};
+  if (active) {
+    float x, y, z;
+    float* dst;
+    if (tid < NQ) {
+      x = qp[r * ld_q + tid];
+      y = qp[r * ld_q + NQ + tid];
+      z = qp[r * ld_q + 2 * NQ + tid];
+      dst = q_pts + ((long)r * NQ + tid) * 3;
+      kind = 0; h = tid / P_Q; p = tid % P_Q;
+    } else {
+      const int k = tid - NQ;
+      h = k / (P_Q + P_V); p = k % (P_Q + P_V);
+      x = kvp[r * ld_kv + k];
+      y = kvp[r * ld_kv + NKV + k];
+      z = kvp[r * ld_kv + 2 * NKV + k];
+      if (p < P_Q) { kind = 1; dst = k_pts + (((long)r * N_H + h) * P_Q + p) * 3; }
+      else { kind = 2; p -= P_Q; dst = v_pts + (((long)r * N_H + h) * P_V + p) * 3; }
+    }
+    o[0] = R[0] * x + R[1] * y + R[2] * z + tx;
+    o[1] = R[3] * x + R[4] * y + R[5] * z + ty;
+    o[2] = R[6] * x + R[7] * y + R[8] * z + tz;
+    dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
   }
-  dst[0] = R[0] * x + R[1] * y + R[2] * z + tx;
-  dst[1] = R[3] * x + R[4] * y + R[5] * z + ty;
-  dst[2] = R[6] * x + R[7] * y + R[8] * z + tz;
+  if (!aug.qp_aug) return;  // uniform
+  const int b = r / aug.L, j = r % aug.L;
+  if (kind == 0 || kind == 1) {
+    const float w = aug.pt_w[h];
+    const float sw = sqrtf(w * aug.inv_alpha);  // the GEMM epilogue multiplies the whole accumulator by alpha
+    bf16* dst = (kind == 0 ? aug.qp_aug : aug.kp_aug) + ((long)r * N_H + h) * PT_K + p * 3;
+    float k2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const float v = o[e] * sw;
+      const bf16 hi = __float2bfloat16_rn(v);
+      const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      dst[e] = hi;
+      dst[24 + e] = kind == 0 ? lo : hi;
+      dst[48 + e] = kind == 0 ? hi : lo;
+      k2 += o[e] * o[e] * w;
+    }
+    if (p == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dst[72 + e] = __float2bfloat16_rn(0.f);
+    }
+    if (kind == 1) k2_s[h * P_Q + p] = k2;
+  } else if (kind == 2) {
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const bf16 hi = __float2bfloat16_rn(o[e]);
+      const long idx = (((long)b * N_H + h) * (P_V * 3) + p * 3 + e) * aug.L + j;
+      aug.vpT_hi[idx] = hi;
+      aug.vpT_lo[idx] = __float2bfloat16_rn(o[e] - __bfloat162float(hi));
+    }
+  }
+  __syncthreads();
+  if (tid < N_H) {
+    float s = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < P_Q; ++pp) s += k2_s[tid * P_Q + pp];
+    aug.colbias[((long)b * N_H + tid) * aug.L + j] = -0.5f * s;
+  }
 }
 
 // S[b,h,i,j] += -0.5 * w_h * sum_p |q_pts[b,i,h,p] - k_pts[b,j,h,p]|^2      (ipa.py:191-205)
@@ -262,9 +315,11 @@ __global__ void softplus_point_weights_kernel(const float* __restrict__ hw, floa
 }  // namespace
 
 void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv, const float* quat,
-                const float* trans, float* q_pts, float* k_pts, float* v_pts, int rows, cudaStream_t st) {
+                const float* trans, float* q_pts, float* k_pts, float* v_pts, int rows, cudaStream_t st,
+                const IpaPointsAug& aug) {
   S2S_PROF("ipa_points", st);
-  ipa_points_kernel<<<rows, 256, 0, st>>>(qp_raw, ld_q, kvp_raw, ld_kv, quat, trans, q_pts, k_pts, v_pts, rows);
+  S2S_CHECK(!aug.qp_aug || (aug.kp_aug && aug.colbias && aug.vpT_hi && aug.vpT_lo && aug.pt_w && aug.L > 0), "ipa_points: incomplete operand set");
+  ipa_points_kernel<<<rows, 256, 0, st>>>(qp_raw, ld_q, kvp_raw, ld_kv, quat, trans, q_pts, k_pts, v_pts, rows, aug);
   S2S_LAUNCH_CHECK();
 }
 

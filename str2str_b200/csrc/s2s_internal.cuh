@@ -36,6 +36,11 @@ struct TcGemm {
   // h = (n - vt_col0) / vt_stride, channel c = (n - vt_col0) % vt_stride - vt_off when 0 <= c < vt_width
   bf16 *out_vt = nullptr, *out_vt_lo = nullptr;
   int vt_col0 = 2048, vt_stride = 512, vt_off = 256, vt_width = 256, vt_heads = 8;
+  // optional second K segment (passes == 1): C += A2 B2^T over K2 more columns, box coordinates like A / B
+  const bf16 *A2 = nullptr, *B2 = nullptr; int K2 = 0;
+  size_t a2_rows = 0, a2_cols = 0, a2_pitch = 0; int a2_cb = 0, a2_ch = 0, a2_rb = 0, a2_rh = 0;
+  size_t b2_rows = 0, b2_cols = 0, b2_pitch = 0; int b2_cb = 0, b2_ch = 0, b2_rb = 0, b2_rh = 0;
+  long bias_sb = 0, bias_sh = 0;  // batch strides of `bias` (per-(batch, head) column bias when non-zero)
 };
 void gemm_tc(const TcGemm& g, cudaStream_t st);
 void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st);
@@ -116,8 +121,18 @@ void build_ee_wimg(const float* W2, const float* W3, bf16* dst, cudaStream_t st)
 void f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t st);
 
 // ---- ipa.cu -------------------------------------------------------------------------------------------
+constexpr int PT_K = 80;  // point columns of the fused logits GEMM: 3 x 24 split-bf16 coordinates + 8 zeros
+struct IpaPointsAug {     // optional tensor-core operand outputs of ipa_points (see the kernel)
+  bf16 *qp_aug = nullptr, *kp_aug = nullptr;  // [rows][N_H][PT_K]
+  float* colbias = nullptr;                   // [B][N_H][L]
+  bf16 *vpT_hi = nullptr, *vpT_lo = nullptr;  // [B][N_H][36][L]
+  const float* pt_w = nullptr;                // [N_H] softplus(head_weights) * sqrt(1/108)
+  float inv_alpha = 1.f;                      // 1 / (alpha of the logits GEMM): the point columns are pre-divided by it
+  int L = 0;
+};
 void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv, const float* quat,
-                const float* trans, float* q_pts, float* k_pts, float* v_pts, int rows, cudaStream_t st);
+                const float* trans, float* q_pts, float* k_pts, float* v_pts, int rows, cudaStream_t st,
+                const IpaPointsAug& aug = IpaPointsAug());
 void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const float* pt_w, int B, int L,
                       cudaStream_t st);
 struct IpaPairArgs {
@@ -132,8 +147,15 @@ struct IpaPairArgs {
   float* o_pair;       // [B*L] rows, H*32 wide, row stride ld_opair
   long ld_opair;
   bf16* P_bf16 = nullptr;  // optional bf16 copy of the attention weights [B,H,L,L] (A operand of the tensor-core P.V)
+  // second-generation kernel (ipa_tc.cu): P leaves as split bf16 (P_bf16 = hi part, P_lo), S is read only
+  bf16* P_lo = nullptr;
+  const bf16* wb_img = nullptr;  // build_ipa_wb_img
 };
 void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st);
+void ipa_pair_attention_tc(const IpaPairArgs& a, cudaStream_t st);
+bool ipa_pair_attention_tc_supported(int L);
+size_t ipa_wb_img_elems();
+void build_ipa_wb_img(const float* Wb, bf16* dst, cudaStream_t st);
 void ipa_finalize_points(const float* opt_glob, const float* quat, const float* trans, float* feats, int rows,
                          cudaStream_t st);
 void softplus_point_weights(const float* head_w, float* pt_w, cudaStream_t st);

@@ -307,3 +307,32 @@ def test_long_chain_forward_L512(params):
     r = rel(outs[1][..., 4:], outs[0][..., 4:])
     print(f"forward L=512 tensor-core vs exact: C-alpha rel {r:.2e}")
     assert r < 2e-5
+
+
+@pytest.mark.parametrize("L", [64, 128, 208, 256])
+def test_ipa_second_generation_vs_first_and_oracle(params, L):
+    """Second-generation IPA path (point term folded into the logits GEMM, persistent tcgen05 pair kernel, split-bf16
+    attention weights) against the first-generation kernels on the same engine and against the fp32 oracle.
+    L=208 exercises a ragged second key block, L=64 a ragged first one."""
+    B = 3
+    g = torch.Generator().manual_seed(29)
+    node = torch.randn(B, L, 256, generator=g)
+    edge = torch.randn(B, L, L, 128, generator=g).bfloat16()
+    q, x = synthetic.make_backbone(L, seed=29)
+    rig = torch.cat([q, 0.1 * x], -1)[None].repeat(B, 1, 1) + 0.05 * torch.randn(B, L, 7, generator=g)
+    nm = torch.ones(B, L)
+    nm[1, -5:] = 0
+    nm[2, :3] = 0
+    net = make_net(params, 1, 1)
+    eng = net.native("cuda")
+    eng.reserve(B, L, torch.arange(L)[None].repeat(B, 1))
+    outs = []
+    for gen in (0, 1):
+        eng.set_option("ipa_kernels", gen)
+        outs.append(eng.ipa(2, node.cuda(), edge.cuda(), rig[..., :4].contiguous().cuda(), rig[..., 4:].contiguous().cuda(), nm.cuda()).cpu())
+    ref = O.ipa(params, "translator.trunk.ipa_2.", node, edge.float(), rig[..., :4], rig[..., 4:], nm)
+    valid = nm.bool()
+    r01 = rel(outs[1][valid], outs[0][valid])
+    r0, r1 = rel(outs[0][valid], ref[valid]), rel(outs[1][valid], ref[valid])
+    print(f"ipa L={L}: gen2 vs gen1 {r01:.2e}; vs oracle gen1 {r0:.2e} gen2 {r1:.2e}")
+    assert r01 < 2e-3 and r1 < 5e-3 and r1 < 2 * r0 + 1e-4
