@@ -496,13 +496,17 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   p.o_pair = c->feats + (N_H * C_H + 4 * N_H * P_V); p.ld_opair = IPA_FEAT;
   p.P_bf16 = tc ? c->P_bf16 : nullptr;
   p.P_lo = c->P_lo; p.wb_img = w.wb_img;
+  // fused path: the three producers of the 2688-wide feature row write its split-bf16 image (sa_hi / sa_lo) directly
+  const long pair_col = N_H * C_H + 4 * N_H * P_V;
+  if (fused) { p.opair_hi = c->sa_hi + pair_col; p.opair_lo = c->sa_lo + pair_col; }
   if (fused) ipa_pair_attention_tc(p, st); else ipa_pair_attention(p, st);
   if (tc) {  // o = P v -> feats[:, h*256 + c]
     TcGemm g;
     g.A_hi = c->P_bf16; g.a_rows = (size_t)B * N_H * L; g.a_cols = L; g.a_pitch = L; g.a_rb = N_H * L; g.a_rh = L;
     g.B_hi = c->vT; g.b_rows = (size_t)B * N_H * C_H; g.b_cols = L; g.b_pitch = L; g.b_rb = N_H * C_H; g.b_rh = C_H;
     g.M = L; g.N = C_H; g.K = L; g.nb = B; g.nh = N_H; g.passes = 1;
-    g.C = c->feats; g.ldc = IPA_FEAT; g.sCb = (long)L * IPA_FEAT; g.sCh = C_H;
+    g.ldc = IPA_FEAT; g.sCb = (long)L * IPA_FEAT; g.sCh = C_H;
+    if (fused) { g.out_hi = c->sa_hi; g.out_lo = c->sa_lo; g.ldo = IPA_FEAT; } else g.C = c->feats;
     gemm_tc(g, st);
   }
   if (fused) {  // o_pt (global frame) = P v_pts, split-bf16 on the tensor cores
@@ -527,9 +531,9 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
     g.N = P_V * 3;
     gemm_f32(g, st);
   }
-  ipa_finalize_points(c->opt, quat, trans, c->feats, R, st);
+  ipa_finalize_points(c->opt, quat, trans, c->feats, R, st, fused ? c->sa_hi : nullptr, fused ? c->sa_lo : nullptr);
   linear(c, c->feats, IPA_FEAT, c->P(ip + "linear_out.weight"), IPA_FEAT, c->P(ip + "linear_out.bias"), out, 256, R, 256,
-         IPA_FEAT, st, 0, res, 256, nullptr, row_post, TC3);
+         IPA_FEAT, st, 0, res, 256, nullptr, row_post, TC3, fused ? Split{c->sa_hi, c->sa_lo} : Split());
 }
 
 void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z_in, const float* rmask,

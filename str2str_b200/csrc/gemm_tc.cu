@@ -1,6 +1,7 @@
 // Tensor-core GEMM for the node track:  C = epilogue(A * B^T)  with A [M][K] and B [N][K] bf16, K-major, fetched by
 // TMA tensor maps into SWIZZLE_128B operand blocks, tcgen05.mma (128x128x16) into double-buffered TMEM accumulators,
-// epilogue from TMEM by four warps.  Persistent CTAs loop over 128x128 output tiles.
+// epilogue from TMEM by eight warps (the epilogue is issue-bound per warp: ncu shows one warp per scheduler stalling on
+// its own dependent instructions, so two warps per scheduler halve its time).  Persistent CTAs loop over 128x128 output tiles.
 //
 // passes = 1: plain bf16 product (IPA q/k/v projections, q.k^T, P.V — tools/precision_probe.py shows these tolerate it)
 // passes = 3: split-bf16 product  A_hi B_hi + A_lo B_hi + A_hi B_lo  accumulated in fp32 (≈16 mantissa bits per operand)
@@ -16,9 +17,11 @@ using namespace tc;
 
 namespace {
 
+constexpr int G_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, 64 columns each)
 constexpr int G_SMEM_RING = 12 * TILE_BYTES;  // 192 KiB of operand blocks: 6 stages x 2 blocks, or 3 stages x 4 blocks
 constexpr int G_OFF_BAR = G_SMEM_RING;
-constexpr int G_SMEM = G_OFF_BAR + 32 * 8 + 16;
+constexpr int G_OFF_BIAS = G_OFF_BAR + 32 * 8 + 16;  // per-epilogue-warp bias slice of the current tile, [8][64] fp32
+constexpr int G_SMEM = G_OFF_BIAS + 8 * 128 * 4;
 
 struct TcKernelArgs {
   int a_cb, a_ch, a_rb, a_rh;  // A box coordinates: col = ib*a_cb + ih*a_ch + kb*64, row = ib*a_rb + ih*a_rh + m0
@@ -36,9 +39,10 @@ struct TcKernelArgs {
   // second K segment (passes == 1 only): K2 more reduction columns fetched through the mAl / mBl maps
   int K2, a2_cb, a2_ch, a2_rb, a2_rh, b2_cb, b2_ch, b2_rb, b2_rh;
   long bias_sb, bias_sh;  // batch strides of `bias` (0: one bias vector for every batch)
+  int epi_warps;          // 4 or 8 epilogue warps (blockDim = 64 + 32 * epi_warps)
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, TcKernelArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B operand blocks need 1024-byte alignment
@@ -61,7 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 128);
+      mbar_init(&acc_empty[s], 32 * a.epi_warps);
     }
     fence_barrier_init();
   }
@@ -140,7 +144,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
       __syncwarp();
     }
   } else {
-    const int q = warp & 3, r = q * 32 + lane;
+    const int q = warp & 3, r = q * 32 + lane, hf = (warp - 2) >> 2;
+    float* bias_s = reinterpret_cast<float*>(smem + G_OFF_BIAS) + (warp - 2) * 128;
+    const int cw = a.epi_warps == 8 ? 64 : 128;  // columns of a tile per epilogue warp
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % NT, mt = (tile / NT) % MT, bz = tile / (NT * MT);
@@ -153,11 +159,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
       float* crow = a.C ? a.C + ib * a.sCb + ih * a.sCh + (long)m * a.ldc : nullptr;
       const float* rrow = a.res ? a.res + ib * a.sCb + ih * a.sCh + (long)m * a.ldres : nullptr;
       const float* bias = a.bias ? a.bias + ib * a.bias_sb + ih * a.bias_sh : nullptr;
+      if (bias) {
+        // This warp's 64 bias values go to shared memory BEFORE the accumulator wait: a global load issued inside the
+        // chunk loop queues behind the previous chunk's scattered stores and its latency is fully exposed (ncu: the
+        // dependent FADD was the top long-scoreboard stall of the kernel).
+        const int nb0 = nt * 128 + hf * cw + lane;
+        float bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bv[u] = (u * 32 < cw && nb0 + u * 32 < a.N) ? __ldg(bias + nb0 + u * 32) : 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bias_s[u * 32 + lane] = bv[u];
+        __syncwarp();
+      }
       mbar_wait(&acc_full[ab], aph);
       tc_fence_after();
       const uint32_t taddr = tmem + ab * 128 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128 && !(a.dbg & 32); c0 += 32) {
+      for (int c0 = hf * cw; c0 < hf * cw + cw && !(a.dbg & 32); c0 += 32) {
         const int n0 = nt * 128 + c0;
         if (n0 >= a.N) break;  // warp-uniform
         float v[32];  // static indexing only below: stays in registers
@@ -168,16 +187,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] *= pre;
         if (bias) {
-          if (full) {
+          const float* bs = bias_s + (c0 - hf * cw);
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + e));
-              v[e] += bv.x; v[e + 1] += bv.y; v[e + 2] += bv.z; v[e + 3] += bv.w;
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (n0 + e < a.N) v[e] += bias[n0 + e];
+          for (int e = 0; e < 32; e += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bs + e);
+            v[e] += bv.x; v[e + 1] += bv.y; v[e + 2] += bv.z; v[e + 3] += bv.w;
           }
         }
         if (a.relu) {
@@ -321,6 +335,8 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   k.K2 = g.K2; k.a2_cb = g.a2_cb; k.a2_ch = g.a2_ch; k.a2_rb = g.a2_rb; k.a2_rh = g.a2_rh;
   k.b2_cb = g.b2_cb; k.b2_ch = g.b2_ch; k.b2_rb = g.b2_rb; k.b2_rh = g.b2_rh;
   k.bias_sb = g.bias_sb; k.bias_sh = g.bias_sh;
+  k.epi_warps = 8;
+  if (const char* e = getenv("S2S_GEMM_EPI")) k.epi_warps = atoi(e) == 4 ? 4 : 8;  // timing experiments only
   k.a_cb = g.a_cb; k.a_ch = g.a_ch; k.a_rb = g.a_rb; k.a_rh = g.a_rh;
   k.b_cb = g.b_cb; k.b_ch = g.b_ch; k.b_rb = g.b_rb; k.b_rh = g.b_rh;
   k.M = g.M; k.N = g.N; k.K = g.K; k.nb = g.nb; k.nh = g.nh; k.passes = g.passes; k.relu = g.relu; k.vt_L = g.vt_L;
@@ -343,7 +359,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   }
   const int tiles = g.nb * g.nh * ceil_div(g.M, TM) * ceil_div(g.N, 128);
   S2S_PROF(g_profile_on ? prof_intern("gemm_tc M" + std::to_string(g.M) + " N" + std::to_string(g.N) +  " K" + std::to_string(g.K + g.K2) + " p" + std::to_string(g.passes) + " b" + std::to_string(g.nb * g.nh)) : "gemm_tc", st);
-  gemm_tc_kernel<<<tiles < sm_count() ? tiles : sm_count(), 192, smem, st>>>(mAh, mAl, mBh, mBl, k);
+  gemm_tc_kernel<<<tiles < sm_count() ? tiles : sm_count(), 64 + 32 * k.epi_warps, smem, st>>>(mAh, mAl, mBh, mBl, k);
   S2S_LAUNCH_CHECK();
 }
 

@@ -17,7 +17,7 @@ namespace {
 //     one bf16 MMA over these 72 (+8 zero) columns gives  w_h q_pts.k_pts  to ~2^-17 relative;
 //   colbias [b][h][j] = -0.5 w_h |k_pts_j|^2.  Together: -0.5 w_h |q - k|^2 up to a per-query constant, which the
 //     softmax over keys cancels exactly (ipa.py:191-205,215);
-//   vpT_hi / vpT_lo [b][h][36][L]: transposed split-bf16 value points (B operand of P.v_pts).
+//   (vpT_hi / vpT_lo, the transposed split-bf16 value points, are written by ipa_vpts_transpose_kernel below.)
 __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict__ qp, long ld_q,
                                                          const float* __restrict__ kvp, long ld_kv,
                                                          const float* __restrict__ quat,
@@ -81,14 +81,6 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
       for (int e = 0; e < 8; ++e) dst[72 + e] = __float2bfloat16_rn(0.f);
     }
     if (kind == 1) k2_s[h * P_Q + p] = k2;
-  } else if (kind == 2) {
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {
-      const bf16 hi = __float2bfloat16_rn(o[e]);
-      const long idx = (((long)b * N_H + h) * (P_V * 3) + p * 3 + e) * aug.L + j;
-      aug.vpT_hi[idx] = hi;
-      aug.vpT_lo[idx] = __float2bfloat16_rn(o[e] - __bfloat162float(hi));
-    }
   }
   __syncthreads();
   if (tid < N_H) {
@@ -96,6 +88,28 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
 #pragma unroll
     for (int pp = 0; pp < P_Q; ++pp) s += k2_s[tid * P_Q + pp];
     aug.colbias[((long)b * N_H + tid) * aug.L + j] = -0.5f * s;
+  }
+}
+
+// v_pts [b][j][288] fp32 -> vpT_hi / vpT_lo [b][288][L] split bf16 (K-major B operand of the P.v_pts GEMM), 32 keys per block
+__global__ void __launch_bounds__(256) ipa_vpts_transpose_kernel(const float* __restrict__ v_pts, bf16* __restrict__ hi,
+                                                                 bf16* __restrict__ lo, int L) {
+  constexpr int NV = N_H * P_V * 3;
+  __shared__ float tile[32][NV + 1];
+  const int b = blockIdx.y, j0 = blockIdx.x * 32;
+  for (int idx = threadIdx.x; idx < 32 * NV; idx += 256) {
+    const int jl = idx / NV, c = idx % NV;
+    tile[jl][c] = j0 + jl < L ? v_pts[((long)b * L + j0 + jl) * NV + c] : 0.f;
+  }
+  __syncthreads();
+  const int jl = threadIdx.x % 32;
+  if (j0 + jl >= L) return;
+  for (int c = threadIdx.x / 32; c < NV; c += 8) {
+    const float v = tile[jl][c];
+    const bf16 h = __float2bfloat16_rn(v);
+    const long o = ((long)b * NV + c) * L + j0 + jl;
+    hi[o] = h;
+    lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
 
@@ -285,7 +299,8 @@ __global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) 
 __global__ void __launch_bounds__(96) ipa_finalize_points_kernel(const float* __restrict__ opt,
                                                                   const float* __restrict__ quat,
                                                                   const float* __restrict__ trans,
-                                                                  float* __restrict__ feats, int rows) {
+                                                                  float* __restrict__ feats, int rows,
+                                                                  bf16* __restrict__ f_hi, bf16* __restrict__ f_lo) {
   const int r = blockIdx.x, k = threadIdx.x;  // k = h*12 + p
   if (r >= rows) return;
   float q[4] = {quat[r * 4], quat[r * 4 + 1], quat[r * 4 + 2], quat[r * 4 + 3]};
@@ -296,12 +311,20 @@ __global__ void __launch_bounds__(96) ipa_finalize_points_kernel(const float* __
   const float lx = R[0] * x + R[3] * y + R[6] * z;
   const float ly = R[1] * x + R[4] * y + R[7] * z;
   const float lz = R[2] * x + R[5] * y + R[8] * z;
-  float* f = feats + (long)r * IPA_FEAT + N_H * C_H;
   constexpr int NP = N_H * P_V;
-  f[k] = lx;
-  f[NP + k] = ly;
-  f[2 * NP + k] = lz;
-  f[3 * NP + k] = sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f);
+  const float ov[4] = {lx, ly, lz, sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f)};
+  const long base = (long)r * IPA_FEAT + N_H * C_H + k;
+  if (f_hi) {  // split-bf16 image for linear_out on the tensor cores (no fp32 copy needed)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bf16 h = __float2bfloat16_rn(ov[e]);
+      f_hi[base + e * NP] = h;
+      f_lo[base + e * NP] = __float2bfloat16_rn(ov[e] - __bfloat162float(h));
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) feats[base + e * NP] = ov[e];
+  }
 }
 
 __global__ void softplus_point_weights_kernel(const float* __restrict__ hw, float* __restrict__ out) {
@@ -321,6 +344,10 @@ void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv
   S2S_CHECK(!aug.qp_aug || (aug.kp_aug && aug.colbias && aug.vpT_hi && aug.vpT_lo && aug.pt_w && aug.L > 0), "ipa_points: incomplete operand set");
   ipa_points_kernel<<<rows, 256, 0, st>>>(qp_raw, ld_q, kvp_raw, ld_kv, quat, trans, q_pts, k_pts, v_pts, rows, aug);
   S2S_LAUNCH_CHECK();
+  if (aug.qp_aug) {
+    ipa_vpts_transpose_kernel<<<dim3(ceil_div(aug.L, 32), rows / aug.L), 256, 0, st>>>(v_pts, aug.vpT_hi, aug.vpT_lo, aug.L);
+    S2S_LAUNCH_CHECK();
+  }
 }
 
 void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const float* pt_w, int B, int L,
@@ -346,9 +373,9 @@ void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st) {
 }
 
 void ipa_finalize_points(const float* opt_glob, const float* quat, const float* trans, float* feats, int rows,
-                         cudaStream_t st) {
+                         cudaStream_t st, bf16* f_hi, bf16* f_lo) {
   S2S_PROF("ipa_finalize_points", st);
-  ipa_finalize_points_kernel<<<rows, 96, 0, st>>>(opt_glob, quat, trans, feats, rows);
+  ipa_finalize_points_kernel<<<rows, 96, 0, st>>>(opt_glob, quat, trans, feats, rows, f_hi, f_lo);
   S2S_LAUNCH_CHECK();
 }
 

@@ -49,6 +49,7 @@ struct P2Args {
   const bf16* wb_img;
   bf16 *P_hi, *P_lo;
   float* o_pair;
+  bf16 *opair_hi, *opair_lo;
   long ld_opair;
   int L, n_slabs;
   uint32_t a2_lbo, a2_sbo;  // MN-major descriptor fields of the zsum A operand (16-byte units)
@@ -301,9 +302,17 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
         acc0 = fmaf(w0, u0.x, acc0); acc0 = fmaf(w1, u0.y, acc0); acc0 = fmaf(w2, u0.z, acc0); acc0 = fmaf(w3, u0.w, acc0);
         acc1 = fmaf(w0, u1.x, acc1); acc1 = fmaf(w1, u1.y, acc1); acc1 = fmaf(w2, u1.z, acc1); acc1 = fmaf(w3, u1.w, acc1);
       }
-      float* orow = a.o_pair + ((long)b * L + i) * a.ld_opair;
-      orow[hq * 32 + dd] = acc0;
-      orow[(hq + 4) * 32 + dd] = acc1;
+      const long o0 = ((long)b * L + i) * a.ld_opair + hq * 32 + dd;
+      if (a.opair_hi) {
+        const bf16 h0 = __float2bfloat16_rn(acc0), h1 = __float2bfloat16_rn(acc1);
+        a.opair_hi[o0] = h0;
+        a.opair_hi[o0 + 128] = h1;
+        a.opair_lo[o0] = __float2bfloat16_rn(acc0 - __bfloat162float(h0));
+        a.opair_lo[o0 + 128] = __float2bfloat16_rn(acc1 - __bfloat162float(h1));
+      } else {
+        a.o_pair[o0] = acc0;
+        a.o_pair[o0 + 128] = acc1;
+      }
     }
   }
   tc_fence_before();
@@ -355,6 +364,7 @@ void ipa_pair_attention_tc(const IpaPairArgs& a, cudaStream_t st) {
   P2Args k;
   k.S = a.S; k.mask = a.mask; k.bb = a.bb; k.Wdz_t = a.Wdz_t; k.bdz = a.bdz; k.wb_img = a.wb_img;
   k.P_hi = a.P_bf16; k.P_lo = a.P_lo; k.o_pair = a.o_pair; k.ld_opair = a.ld_opair;
+  k.opair_hi = a.opair_hi; k.opair_lo = a.opair_lo;
   k.L = a.L; k.n_slabs = a.B * a.L;
   k.a2_lbo = TILE_BYTES >> 4;  // between the two 64-channel blocks of a key block
   k.a2_sbo = 1024 >> 4;        // between 8-key groups

@@ -150,6 +150,7 @@ struct IpaPairArgs {
   // second-generation kernel (ipa_tc.cu): P leaves as split bf16 (P_bf16 = hi part, P_lo), S is read only
   bf16* P_lo = nullptr;
   const bf16* wb_img = nullptr;  // build_ipa_wb_img
+  bf16 *opair_hi = nullptr, *opair_lo = nullptr;  // optional split-bf16 image of o_pair (same indexing); replaces the fp32 write
 };
 void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st);
 void ipa_pair_attention_tc(const IpaPairArgs& a, cudaStream_t st);
@@ -157,7 +158,7 @@ bool ipa_pair_attention_tc_supported(int L);
 size_t ipa_wb_img_elems();
 void build_ipa_wb_img(const float* Wb, bf16* dst, cudaStream_t st);
 void ipa_finalize_points(const float* opt_glob, const float* quat, const float* trans, float* feats, int rows,
-                         cudaStream_t st);
+                         cudaStream_t st, bf16* f_hi = nullptr, bf16* f_lo = nullptr);
 void softplus_point_weights(const float* head_w, float* pt_w, cudaStream_t st);
 
 // ---- rigid.cu -----------------------------------------------------------------------------------------
