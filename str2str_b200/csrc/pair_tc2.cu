@@ -32,7 +32,11 @@ constexpr int WTILES = 40;                  // 12 (layer 1) + 18 (layer 2) + 10 
 constexpr int OFF_A0 = 0;                   // [z | n'_j] tile: 4 K-blocks
 constexpr int OFF_W = 4 * TILE_BYTES;       // weight ring
 constexpr int OFF_VEC = OFF_W + NSTAGE * TILE_BYTES;
-constexpr int VEC_FLOATS = D_ET + C_Z + D_ET + C_Z + C_Z + 512;  // u_i, p_i, b2, ln_w, ln_b, LayerNorm partial sums
+constexpr int NEW = 16;                     // epilogue warps: NEW/4 per TMEM lane quarter, each owning 128/(NEW/4) columns of a 128-column chunk
+constexpr int NPART = NEW / 4;
+constexpr int CW = 128 / NPART;             // accumulator columns per thread per 128-column chunk
+constexpr int ET2_THREADS = 64 + 32 * NEW;
+constexpr int VEC_FLOATS = D_ET + C_Z + D_ET + C_Z + C_Z + 2 * NPART * 128;  // u_i, p_i, b2, ln_w, ln_b, LayerNorm partial sums
 constexpr int OFF_BAR = OFF_VEC + VEC_FLOATS * 4;
 constexpr int N_BARS = 2 * NSTAGE + 12;
 constexpr int SMEM_BYTES = OFF_BAR + N_BARS * 8 + 16;
@@ -48,7 +52,32 @@ struct Args {
   int dbg;  // timing experiments only (S2S_ET_DEBUG): 1 no weight TMA, 2 no MMA, 4 no epilogue math
 };
 
-__global__ void __launch_bounds__(320, 1)
+// MC = true: the kernel runs as clusters of two CTAs that share the weight stream: each 16 KB weight block is fetched from
+// L2 once per PAIR (the CTAs alternate as loader) and TMA-multicast into both rings, so the L2 -> SM weight traffic — the
+// resource this kernel saturates, ~8 TB/s measured — halves.  A ring slot is released by both CTAs' MMA issuers
+// (multicast tcgen05.commit, barrier count 2).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_1d_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+template <bool MC>
+__global__ void __launch_bounds__(ET2_THREADS, 1)
 edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_n, Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B operand blocks need 1024-byte alignment
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
@@ -57,7 +86,7 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   float* b2_s = p_s + C_Z;
   float* lnw_s = b2_s + D_ET;
   float* lnb_s = lnw_s + C_Z;
-  float* red_s = lnb_s + C_Z;  // [2 stats][2 halves][128 rows]
+  float* red_s = lnb_s + C_Z;  // [2 stats][NPART column parts][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* w_full = bars;
   uint64_t* w_empty = bars + NSTAGE;
@@ -80,7 +109,7 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], 1);
+      mbar_init(&w_empty[s], MC ? 2 : 1);
     }
     mbar_init(a0_full, 1);
     mbar_init(a0_empty, 1);
@@ -88,12 +117,12 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
     mbar_init(full2, 1);
     mbar_init(&fullG[0], 1);
     mbar_init(&fullG[1], 1);
-    mbar_init(emptyE, 256);
-    mbar_init(empty2, 256);
-    mbar_init(&emptyG[0], 128);
-    mbar_init(&emptyG[1], 128);
-    mbar_init(h1_full, 256);
-    mbar_init(h2_full, 256);
+    mbar_init(emptyE, 32 * NEW);
+    mbar_init(empty2, 32 * NEW);
+    mbar_init(&emptyG[0], 16 * NEW);
+    mbar_init(&emptyG[1], 16 * NEW);
+    mbar_init(h1_full, 32 * NEW);
+    mbar_init(h2_full, 32 * NEW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -104,10 +133,12 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int tiles_per_i = a.L / TM;
   constexpr uint32_t IDESC128 = make_idesc(128, 128), IDESC64 = make_idesc(128, 64);
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -129,7 +160,12 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
           mbar_wait(&w_empty[s], ph ^ 1);
           if (a.dbg & 1) { mbar_arrive(&w_full[s]); continue; }
           mbar_expect_tx(&w_full[s], TILE_BYTES);
-          tma_bulk_1d(smem + OFF_W + s * TILE_BYTES, wimg + (size_t)wt * (TILE_BYTES / 2), TILE_BYTES, &w_full[s]);
+          if constexpr (MC) {
+            if ((cnt & 1u) == crank)
+              tma_bulk_1d_mc(smem + OFF_W + s * TILE_BYTES, wimg + (size_t)wt * (TILE_BYTES / 2), TILE_BYTES, &w_full[s], (uint16_t)3);
+          } else {
+            tma_bulk_1d(smem + OFF_W + s * TILE_BYTES, wimg + (size_t)wt * (TILE_BYTES / 2), TILE_BYTES, &w_full[s]);
+          }
         }
       }
     }
@@ -148,7 +184,7 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
         return wr + s * BLK;
       };
       auto release_block = [&]() {  // called by the elected lane
-        umma_commit(&w_empty[cnt % NSTAGE]);
+        if constexpr (MC) umma_commit_mc(&w_empty[cnt % NSTAGE], (uint16_t)3); else umma_commit(&w_empty[cnt % NSTAGE]);
       };
       auto wait_prev = [&](uint64_t* bar, uint32_t& n) {  // wait #k waits for drain #(k-1): the first one passes
         mbar_wait(bar, (n & 1) ^ 1);
@@ -232,21 +268,26 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
       }
     }
   } else {
-    // ===== 8 epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter split each chunk's columns =====
-    const int ew = warp - 2, q = warp & 3, hf = ew >> 2, r = q * 32 + lane;
+    // ===== NEW epilogue warps: TMEM lane quarter = warp % 4; the NPART warps of a quarter split each chunk's columns.
+    //       (ablation, S2S_ET_DEBUG: MMAs alone 2.05 ms, epilogue alone 2.2 ms at 8 warps — the epilogue is a chain of
+    //        TMEM round trips per warp, so it is bought down with more warps in flight, not with fewer instructions) =====
+    const int ew = warp - 2, q = warp & 3, part = ew >> 2, r = q * 32 + lane;
     const int et = threadIdx.x - 64;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const bool do_epi = !(a.dbg & 4);
+    constexpr int GW = NPART / 2;        // warps per quarter in one layer-2 group
+    const int grp = part / GW, sub = part % GW;  // layer 2: group grp drains chunks grp, grp+2, grp+4; sub splits the 64 columns
+    constexpr int CW2 = 64 / GW;
     uint32_t fE = 0, f2 = 0, fG = 0;  // completed uses seen per "full" barrier
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
       const int b = bi / a.L;
-      named_bar_sync(1, 256);
-      for (int c = et; c < D_ET; c += 256) u_s[c] = a.u[(size_t)bi * D_ET + c];
+      named_bar_sync(1, 32 * NEW);
+      for (int c = et; c < D_ET; c += 32 * NEW) u_s[c] = a.u[(size_t)bi * D_ET + c];
       if (et < C_Z) p_s[et] = a.p[(size_t)bi * C_Z + et];
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 32 * NEW);
       const float m = a.mask[bi] * a.mask[(size_t)b * a.L + j0 + r];
-      float y[64];
+      float y[CW];
       auto wait_full = [&](uint64_t* bar, uint32_t& n) {
         mbar_wait(bar, n & 1);
         ++n;
@@ -254,82 +295,95 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
       };
       auto add_vec = [&](const float* vec, int n) {  // y[0..n) += vec[0..n) (128-bit broadcast shared-memory reads)
 #pragma unroll
-        for (int e = 0; e < 64; e += 4) {
+        for (int e = 0; e < CW; e += 4) {
           if (e < n) {
             const float4 t = *reinterpret_cast<const float4*>(vec + e);
             y[e] += t.x; y[e + 1] += t.y; y[e + 2] += t.z; y[e + 3] += t.w;
           }
         }
       };
+      auto load_cols = [&](uint32_t col, int n) {  // y[0..n) <- accumulator columns [col, col+n) of this thread's row
+#pragma unroll
+        for (int e = 0; e < CW; e += 32)
+          if (e < n) tmem_ld32_issue(tmem + lane_off + col + e, y + e);
+        tmem_wait_ld();
+      };
+      auto store_packed = [&](uint32_t col, int n) {  // relu, pack pairs to bf16, into tensor memory as the next A operand
+        if constexpr (CW == 64) {
+          if (n == 64) {
+            uint32_t pk[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) pk[e] = pack_bf16(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
+            tmem_st32(tmem + lane_off + col, pk);
+            return;
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
+        tmem_st16(tmem + lane_off + col, pk);
+      };
       // ---- layer 1: + u_i, relu, pack, into tensor memory as layer 2's A operand ----
       for (int nc = 0; nc < 3; ++nc) {
         const uint32_t base = nc == 1 ? 128u : 0u;
         if (nc == 1) wait_full(full2, f2); else wait_full(fullE, fE);
         if (do_epi) {
-          tmem_ld32_issue(tmem + lane_off + base + hf * 64, y);
-          tmem_ld32_issue(tmem + lane_off + base + hf * 64 + 32, y + 32);
-          tmem_wait_ld();
-          add_vec(u_s + nc * 128 + hf * 64, 64);
-          uint32_t pk[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) pk[e] = pack_bf16(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
-          tmem_st32(tmem + lane_off + COL_H1 + nc * 64 + hf * 32, pk);
+          load_cols(base + part * CW, CW);
+          add_vec(u_s + nc * 128 + part * CW, CW);
+          store_packed(COL_H1 + nc * 64 + part * (CW / 2), CW);
         }
         tc_fence_before();
         mbar_arrive(nc == 1 ? empty2 : emptyE);
       }
       mbar_arrive(h1_full);
       // ---- layer 2: + b2, relu, pack, into tensor memory as the final layer's A operand.  The two epilogue groups
-      //      (hf = 0 / 1) take the even / odd chunks, so each has two chunk-MMA times to turn one chunk around ----
-      for (int c = hf; c < 6; c += 2) {
-        wait_full(&fullG[hf], fG);
+      //      take the even / odd chunks, so each has two chunk-MMA times to turn one chunk around ----
+      for (int c = grp; c < 6; c += 2) {
+        wait_full(&fullG[grp], fG);
         if (do_epi) {
-          tmem_ld32_issue(tmem + lane_off + hf * 64, y);
-          tmem_ld32_issue(tmem + lane_off + hf * 64 + 32, y + 32);
-          tmem_wait_ld();
-          add_vec(b2_s + c * 64, 64);
-          uint32_t pk[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) pk[e] = pack_bf16(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
-          tmem_st32(tmem + lane_off + h2_col(c), pk);
+          load_cols(grp * 64 + sub * CW2, CW2);
+          add_vec(b2_s + c * 64 + sub * CW2, CW2);
+          store_packed(h2_col(c) + sub * (CW2 / 2), CW2);
         }
         tc_fence_before();
-        mbar_arrive(&emptyG[hf]);
+        mbar_arrive(&emptyG[grp]);
       }
       mbar_arrive(h2_full);
-      // ---- output: + p_i, LayerNorm over 128 channels (exact two-pass; the two half-row threads exchange partial sums
+      // ---- output: + p_i, LayerNorm over 128 channels (exact two-pass; the NPART threads of a row exchange partial sums
       //      through shared memory), * edge mask, bf16 store ----
       {
         wait_full(fullE, fE);
-        if (do_epi) {
-          tmem_ld32_issue(tmem + lane_off + hf * 64, y);
-          tmem_ld32_issue(tmem + lane_off + hf * 64 + 32, y + 32);
-          tmem_wait_ld();
-        }
+        if (do_epi) load_cols(part * CW, CW);
         tc_fence_before();
         mbar_arrive(emptyE);  // accumulator is in registers: the tensor pipe may reuse it
         if (!do_epi) continue;
-        add_vec(p_s + hf * 64, 64);
+        add_vec(p_s + part * CW, CW);
         float sum = 0.f;
 #pragma unroll
-        for (int e = 0; e < 64; ++e) sum += y[e];
-        red_s[hf * 128 + r] = sum;
-        named_bar_sync(2 + q, 64);
-        const float mean = (sum + red_s[(hf ^ 1) * 128 + r]) * (1.f / C_Z);
+        for (int e = 0; e < CW; ++e) sum += y[e];
+        red_s[part * 128 + r] = sum;
+        named_bar_sync(2 + q, 32 * NPART);
+        float tot = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NPART; ++pp) tot += red_s[pp * 128 + r];
+        const float mean = tot * (1.f / C_Z);
         float sq = 0.f;
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {
+        for (int e = 0; e < CW; ++e) {
           const float d = y[e] - mean;
           sq += d * d;
         }
-        red_s[256 + hf * 128 + r] = sq;
-        named_bar_sync(2 + q, 64);
-        const float rstd = rsqrtf((sq + red_s[256 + (hf ^ 1) * 128 + r]) * (1.f / C_Z) + 1e-5f);
-        bf16* orow = a.z_out + ((size_t)tile * TM + r) * C_Z + hf * 64;
-        const float* lw = lnw_s + hf * 64;
-        const float* lb = lnb_s + hf * 64;
+        red_s[(NPART + part) * 128 + r] = sq;
+        named_bar_sync(2 + q, 32 * NPART);
+        float tsq = 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 8) {
+        for (int pp = 0; pp < NPART; ++pp) tsq += red_s[(NPART + pp) * 128 + r];
+        const float rstd = rsqrtf(tsq * (1.f / C_Z) + 1e-5f);
+        bf16* orow = a.z_out + ((size_t)tile * TM + r) * C_Z + part * CW;
+        const float* lw = lnw_s + part * CW;
+        const float* lb = lnb_s + part * CW;
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 8) {
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = ((y[c0 + e] - mean) * rstd * lw[c0 + e] + lb[c0 + e]) * m;
@@ -341,6 +395,7 @@ edge_transition_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -392,12 +447,34 @@ void edge_transition_tc2(const EdgeTransitionArgs& a, cudaStream_t st) {
   static bool configured = false;
   const int smem = SMEM_BYTES + 1024;
   if (!configured) {
-    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   S2S_PROF("edge_transition", st);
-  const int grid = k.n_tiles < sm_count() ? k.n_tiles : sm_count();
-  edge_transition_tc2_kernel<<<grid, 320, smem, st>>>(mz, mn, k);
+  int grid = k.n_tiles < sm_count() ? k.n_tiles : sm_count();
+  static const int mc_env = [] { const char* e = getenv("S2S_ET_MULTICAST"); return e ? atoi(e) : 1; }();
+  const bool mc = mc_env && grid >= 2 && k.n_tiles % 2 == 0;
+  if (mc) {
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ET2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    // persistent kernel: never launch more clusters than can be co-resident (GPCs with an odd SM count strand one SM)
+    static int max_clusters = 0;
+    if (!max_clusters) {
+      S2S_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, edge_transition_tc2_kernel<true>, &cfg));
+      S2S_CHECK(max_clusters > 0, "edge_transition_tc2: no 2-CTA cluster fits");
+    }
+    if (grid > 2 * max_clusters) grid = 2 * max_clusters;
+    cfg.gridDim = dim3(grid);
+    S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_tc2_kernel<true>, mz, mn, k));
+  } else {
+    edge_transition_tc2_kernel<false><<<grid, ET2_THREADS, smem, st>>>(mz, mn, k);
+  }
   S2S_LAUNCH_CHECK();
 }
 
