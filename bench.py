@@ -130,6 +130,32 @@ def algorithmic(B, L):
                 edge_embed=("tensor", ee_flops, rows * 128 * 2))
 
 
+def ncu_traffic(B, L):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/r01b_ncu_full_*.csv, made with tools/ncu_summary.py at cfg2).  None for any other shape."""
+    if (B, L) != (64, 256):
+        return {}
+    import csv
+
+    out = {}
+    for fn, names in (("r01b_ncu_full_edge_transition.csv", {"edge_transition_tc2_kernel": "edge_transition"}),
+                      ("r01b_ncu_full_ipa_stage_kernels.csv", {"ipa_pair_tc_kernel": "ipa_pair_attention", "edge_embed_tc_kernel": "edge_embed"})):
+        path = os.path.join(ROOT, "profiles", fn)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        ir = next(i for i, h in enumerate(hdr) if h.startswith("dram_read"))
+        iw = next(i for i, h in enumerate(hdr) if h.startswith("dram_write"))
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        ur, uw = hdr[ir].split("[")[1].rstrip("]"), hdr[iw].split("[")[1].rstrip("]")
+        for r in rows[1:]:
+            key = next((v for k, v in names.items() if r[0].startswith(k)), None)
+            if key:
+                out[key] = float(r[ir]) * scale[ur] + float(r[iw]) * scale[uw]
+    return out
+
+
 def run_ours(a):
     import torch.distributed as dist
 
@@ -223,6 +249,7 @@ def run_ours(a):
         lib.s2s_profile_enable(0)
         hbm, tf, src = peaks()
         alg = algorithmic(B, L)
+        traffic = ncu_traffic(B, L)
         per = {}
         for name in ("edge_transition", "ipa_pair_attention", "edge_embed", "gemm", "gemm_tc"):
             tot, cnt = C.c_double(0), C.c_int64(0)
@@ -240,11 +267,15 @@ def run_ours(a):
                 else:
                     ach = work / (avg * 1e-3) / 1e9
                     rec.update(bound="hbm", achieved=round(ach, 1), peak=hbm, unit="GB/s", frac=round(ach / hbm, 3))
+            if name in alg:
+                rec["algorithmic_bytes"] = alg[name][2]
+                rec["traffic"] = traffic.get(name)
             extra[name] = rec
         dom = max((k for k in per if k in alg), key=lambda k: per[k][0], default=None)
         if dom:
             roof = {k: extra[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-            roof.update(kernel=dom, traffic=None, peak_source=src, timing="CUDA events around each launch, one eager step")
+            roof.update(kernel=dom, traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/r01b_ncu_full_*.csv (dram read + write per launch)",
+                        peak_source=src, timing="CUDA events around each launch, one eager step")
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
