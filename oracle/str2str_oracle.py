@@ -357,7 +357,7 @@ def discrete_sigma() -> torch.Tensor:
 
 def sigma_index(t: torch.Tensor) -> torch.Tensor:
     """so3.py:211-214,236-238: np.digitize(sigma(t), grid) - 1 (integer bucket; must be bit-exact)."""
-    return torch.as_tensor(np.digitize(sigma_of_t(t).cpu().numpy(), discrete_sigma().numpy()) - 1, dtype=torch.long)
+    return torch.as_tensor(np.digitize(sigma_of_t(t).cpu().numpy(), discrete_sigma().cpu().numpy()) - 1, dtype=torch.long)
 
 
 def rot_g2(t: torch.Tensor) -> torch.Tensor:

@@ -116,6 +116,7 @@ struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
   int opt_pair = 1, opt_node = 0, opt_ipa = 1;
+  int tfm_passes = 1;  // sequence-transformer in_proj + attention GEMMs: 1 = single bf16 (default; trajectory error unchanged, tools/traj_parity.py), 3 = split-bf16 (S2S_TFM_PASSES=3)
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
   float *tfreq = nullptr, *pdenom = nullptr, *bin_lower = nullptr, *backbone = nullptr;
@@ -574,24 +575,26 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     // in_proj on the tensor cores; its epilogue emits the split-bf16 attention operands: q|k row-major, v transposed per head
     const auto w = weight_split(c, c->P(tl + "self_attn.in_proj_weight"));
     TcGemm g;  // A = x320's split image, written by the producer (concat / norm2 of the previous layer)
+    const bool sp = c->tfm_passes == 3;  // single-pass attention (measured: no change of the trajectory error) needs no lo images
+    // in_proj itself stays split-bf16: single pass costs 2.4x of the trajectory error budget (3.0e-5 vs 1.27e-5) for 0.14 ms
     g.A_hi = c->x320_hi; g.A_lo = c->x320_lo; g.a_rows = R; g.a_cols = 320; g.a_pitch = 320;
     g.B_hi = w.first; g.B_lo = w.second; g.b_rows = 960; g.b_cols = 320; g.b_pitch = 320;
     g.M = R; g.N = 960; g.K = 320; g.passes = 3; g.bias = c->P(tl + "self_attn.in_proj_bias");
-    g.out_hi = c->tq_hi; g.out_lo = c->tq_lo; g.ldo = 960;
-    g.out_vt = c->tvT_hi; g.out_vt_lo = c->tvT_lo; g.vt_L = L;
+    g.out_hi = c->tq_hi; g.out_lo = sp ? c->tq_lo : nullptr; g.ldo = 960;
+    g.out_vt = c->tvT_hi; g.out_vt_lo = sp ? c->tvT_lo : nullptr; g.vt_L = L;
     g.vt_col0 = 640; g.vt_stride = TFM_HD; g.vt_off = 0; g.vt_width = TFM_HD; g.vt_heads = TFM_H;
     gemm_tc(g, st);
     TcGemm s;  // logits = q.k^T / sqrt(80), batched over (decoy, head), split-bf16
     s.A_hi = c->tq_hi; s.A_lo = c->tq_lo; s.a_rows = R; s.a_cols = 960; s.a_pitch = 960; s.a_rb = L; s.a_ch = TFM_HD;
     s.B_hi = c->tq_hi + 320; s.B_lo = c->tq_lo + 320; s.b_rows = R; s.b_cols = 640; s.b_pitch = 960; s.b_rb = L; s.b_ch = TFM_HD;
-    s.M = L; s.N = L; s.K = TFM_HD; s.nb = B; s.nh = TFM_H; s.passes = 3; s.alpha = scale;
+    s.M = L; s.N = L; s.K = TFM_HD; s.nb = B; s.nh = TFM_H; s.passes = c->tfm_passes; s.alpha = scale;
     s.C = c->S; s.ldc = L; s.sCb = (long)TFM_H * L * L; s.sCh = (long)L * L;
     gemm_tc(s, st);
-    softmax_keybias(c->S, c->keybias, B, TFM_H, L, st, c->P_bf16, c->tP_lo);
+    softmax_keybias(c->S, c->keybias, B, TFM_H, L, st, c->P_bf16, sp ? c->tP_lo : nullptr);
     TcGemm p;  // y = P v
     p.A_hi = c->P_bf16; p.A_lo = c->tP_lo; p.a_rows = (size_t)B * TFM_H * L; p.a_cols = L; p.a_pitch = L; p.a_rb = TFM_H * L; p.a_rh = L;
     p.B_hi = c->tvT_hi; p.B_lo = c->tvT_lo; p.b_rows = (size_t)B * TFM_H * TFM_HD; p.b_cols = L; p.b_pitch = L; p.b_rb = TFM_H * TFM_HD; p.b_rh = TFM_HD;
-    p.M = L; p.N = TFM_HD; p.K = L; p.nb = B; p.nh = TFM_H; p.passes = 3;
+    p.M = L; p.N = TFM_HD; p.K = L; p.nb = B; p.nh = TFM_H; p.passes = c->tfm_passes;
     p.C = c->y320; p.ldc = 320; p.sCb = (long)L * 320; p.sCh = TFM_HD;
     p.out_hi = c->y320_hi; p.out_lo = c->y320_lo; p.ldo = 320;
     gemm_tc(p, st);
@@ -725,6 +728,7 @@ s2s_ctx* s2s_create(const float* tfreq, const float* pdenom, const float* bin_lo
     S2S_CHECK(tfreq && pdenom && bin_lower && backbone, "s2s_create: null table");
     c = new s2s_ctx();
     if (const char* e = getenv("S2S_WIMG_COPIES")) c->wimg_copies = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("S2S_TFM_PASSES")) c->tfm_passes = atoi(e) == 3 ? 3 : 1;
     auto up = [&](const float* h, size_t n) {
       float* d;
       S2S_CUDA(cudaMalloc(&d, n * 4));

@@ -217,10 +217,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
           if (full && (a.ldc & 3) == 0) {
 #pragma unroll
             for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(crow + n0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-          } else {
+          } else {  // ragged last chunk (N = 80, 36, ...): whole groups of 4 columns still go out as one 16-byte store
+            const bool vec = (a.ldc & 3) == 0;
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (n0 + e < a.N) crow[n0 + e] = v[e];
+            for (int e = 0; e < 32; e += 4) {
+              if (vec && n0 + e + 4 <= a.N) {
+                *reinterpret_cast<float4*>(crow + n0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (n0 + e + u < a.N) crow[n0 + e + u] = v[e + u];
+              }
+            }
           }
         }
         if (a.out_hi) {
@@ -241,12 +249,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
               if (lrow) *reinterpret_cast<uint4*>(lrow + e) = make_uint4(l[0], l[1], l[2], l[3]);
             }
           } else {
+            const bool vec = (a.ldo & 3) == 0 && (a.sCh & 3) == 0 && (a.sCb & 3) == 0;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              if (n0 + e < a.N) {
-                const bf16 h = __float2bfloat16_rn(v[e]);
-                hrow[e] = h;
-                if (lrow) lrow[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h));
+            for (int e = 0; e < 32; e += 4) {
+              if (vec && n0 + e + 4 <= a.N) {
+                *reinterpret_cast<uint2*>(hrow + e) = make_uint2(pack_bf16(v[e], v[e + 1]), pack_bf16(v[e + 2], v[e + 3]));
+                if (lrow)
+                  *reinterpret_cast<uint2*>(lrow + e) = make_uint2(pack_bf16(v[e] - bf16_round(v[e]), v[e + 1] - bf16_round(v[e + 1])),
+                                                                  pack_bf16(v[e + 2] - bf16_round(v[e + 2]), v[e + 3] - bf16_round(v[e + 3])));
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (n0 + e + u < a.N) {
+                    const bf16 h = __float2bfloat16_rn(v[e + u]);
+                    hrow[e + u] = h;
+                    if (lrow) lrow[e + u] = __float2bfloat16_rn(v[e + u] - __bfloat162float(h));
+                  }
+                }
               }
             }
           }

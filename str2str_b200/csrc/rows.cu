@@ -57,6 +57,38 @@ __global__ void __launch_bounds__(256) softmax_keybias_kernel(float* __restrict_
   const int b = (int)(row / rows_per_batch);
   float* p = S + row * L;
   const float* kb = keybias ? keybias + (long)b * L : nullptr;
+  if (L <= 32 * 16) {  // the row stays in registers: one read of S, one write of the result
+    float v[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = lane + 32 * u;
+      v[u] = j < L ? p[j] + (kb ? kb[j] : 0.f) : -INFINITY;
+      mx = fmaxf(mx, v[u]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      v[u] = __expf(v[u] - mx);
+      sum += v[u];
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = lane + 32 * u;
+      if (j >= L) break;
+      const float pv = v[u] * inv;
+      if (P_hi) {  // split-bf16 copy for the tensor-core P.V (the fp32 row is then not needed any more)
+        const bf16 hi = __float2bfloat16_rn(pv);
+        P_hi[row * L + j] = hi;
+        if (P_lo) P_lo[row * L + j] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+      } else {
+        p[j] = pv;
+      }
+    }
+    return;
+  }
   float mx = -INFINITY;
   for (int j = lane; j < L; j += 32) {
     float v = p[j] + (kb ? kb[j] : 0.f);
@@ -71,12 +103,12 @@ __global__ void __launch_bounds__(256) softmax_keybias_kernel(float* __restrict_
     sum += e;
   }
   const float inv = 1.f / warp_sum(sum);
-  if (P_hi) {  // split-bf16 copy for the tensor-core P.V (the fp32 row is then not needed any more)
+  if (P_hi) {
     for (int j = lane; j < L; j += 32) {
       const float pv = p[j] * inv;
       const bf16 hi = __float2bfloat16_rn(pv);
       P_hi[row * L + j] = hi;
-      P_lo[row * L + j] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+      if (P_lo) P_lo[row * L + j] = __float2bfloat16_rn(pv - __bfloat162float(hi));
     }
     return;
   }
