@@ -243,11 +243,12 @@ constexpr int WD_PITCH = C_Z + 4;
 constexpr int EE_OFF_A = 0;                      // activation tile: 2 K-blocks
 constexpr int EE_OFF_W = 2 * TILE_BYTES;         // 4 resident weight blocks
 constexpr int EE_OFF_VEC = EE_OFF_W + 4 * TILE_BYTES;
-constexpr int EE_VEC_FLOATS = C_Z * 5 + N_BINS * WD_PITCH + 32;  // Ti, b2, b3, ln_w, ln_b, Wd, bin edges
+constexpr int EE_VEC_FLOATS = C_Z * 5 + N_BINS * WD_PITCH + 32 + 4 * 128;  // Ti, b2, b3, ln_w, ln_b, Wd, bin edges, LayerNorm partials
+constexpr int EE_THREADS = 288;  // MMA/loader warp + 8 worker warps (two per TMEM lane quarter: 16 rows of layer 1, 64 columns of the epilogues each)
 constexpr int EE_OFF_BAR = EE_OFF_VEC + EE_VEC_FLOATS * 4;
 constexpr int EE_SMEM = EE_OFF_BAR + 8 * 8 + 16;
 
-__global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
+__global__ void __launch_bounds__(EE_THREADS, 2) edge_embed_tc_kernel(EeTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   float* ti_s = reinterpret_cast<float*>(smem + EE_OFF_VEC);
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
   float* lnb_s = lnw_s + C_Z;
   float* wd_s = lnb_s + C_Z;
   float* edge_s = wd_s + N_BINS * WD_PITCH;
+  float* red_s = edge_s + 32;  // [2 stats][2 column halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EE_OFF_BAR);
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
-    mbar_init(a_full, 128);
+    mbar_init(a_full, 256);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -312,7 +314,10 @@ __global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
       }
     }
   } else {
-    const int q = warp & 3, r = q * 32 + lane;
+    // 8 worker warps: TMEM lane quarter q = warp % 4, hf = which of the quarter's two warps.  (ncu: with 4 workers the
+    // kernel was a chain of exposed latencies — layer-1 table reads 45 %, MMA round trips 12 %, TMEM passes 35 % of
+    // the samples — so the remedy is more warps in flight and one TMEM pass for the LayerNorm.)
+    const int q = warp & 3, hf = (warp - 1) >> 2, r = q * 32 + lane;
     const int wt = threadIdx.x - 32;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     unsigned char* abuf = smem + EE_OFF_A;
@@ -321,20 +326,21 @@ __global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
       const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
       const int b = bi / e.L;
       const size_t bj = (size_t)b * e.L + j0 + r;
-      named_bar_sync(1, 128);
-      ti_s[wt] = e.Ti[(size_t)bi * C_Z + wt];
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
+      if (wt < C_Z) ti_s[wt] = e.Ti[(size_t)bi * C_Z + wt];
+      named_bar_sync(1, 256);
       // layer 1 by table lookups (reference denoising_ipa.py:126-158): time/fixed features of i and j, relative
-      // position, self-conditioning distogram bin.  Each lane first classifies one of its warp's 32 rows, then the warp
-      // walks the rows together so that every table row is one coalesced 512-byte read (lane = 4 channels).
+      // position, self-conditioning distogram bin.  Each lane first classifies one of its quarter's 32 rows, then the
+      // warp walks its 16 rows together so that every table row is one coalesced 512-byte read (lane = 4 channels).
       {
         const int bin_l = pair_distogram_bin(e.sc_ca + (size_t)bi * 3, e.sc_ca + bj * 3, edge_s);
         const int off_l = (int)(e.ridx[bi] - e.ridx[bj]) - e.d_min;
         const int c = lane * 4;
         const float4 tiv = *reinterpret_cast<const float4*>(ti_s + c);
         const size_t bj0 = (size_t)b * e.L + j0 + q * 32;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
+#pragma unroll 8
+        for (int r16 = 0; r16 < 16; ++r16) {
+          const int rr = hf * 16 + r16;
           const int bin = __shfl_sync(0xffffffffu, bin_l, rr);
           const int off = __shfl_sync(0xffffffffu, off_l, rr);
           const float4 tjv = __ldg(reinterpret_cast<const float4*>(e.Tj + (bj0 + rr) * C_Z + c));
@@ -351,67 +357,64 @@ __global__ void __launch_bounds__(160, 2) edge_embed_tc_kernel(EeTcArgs a) {
       }
       fence_proxy_async();
       mbar_arrive(a_full);
-      // layer 2 epilogue: + b2, relu, restage
-      float v[32];
+      // layer 2 epilogue: + b2, relu, restage (this thread: row r, columns hf*64 .. hf*64+63 = K-block hf)
+      float v[64];
       mbar_wait(acc_full, ph_acc);
       ph_acc ^= 1;
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < C_Z; c0 += 32) {
-        tmem_ld32(lane_base + c0, v);
+      tmem_ld32_issue(lane_base + hf * 64, v);
+      tmem_ld32_issue(lane_base + hf * 64 + 32, v + 32);
+      tmem_wait_ld();
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          float h[8];
+      for (int gq = 0; gq < 8; ++gq) {
+        float h[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) h[k] = fmaxf(v[gq * 8 + k] + b2_s[c0 + gq * 8 + k], 0.f);
-          const int c = c0 + gq * 8;
-          store8_sw128(abuf + (c / KBLK) * TILE_BYTES, r, c % KBLK, h);
-        }
+        for (int k = 0; k < 8; ++k) h[k] = fmaxf(v[gq * 8 + k] + b2_s[hf * 64 + gq * 8 + k], 0.f);
+        store8_sw128(abuf + hf * TILE_BYTES, r, gq * 8, h);
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(a_full);
-      // layer 3 epilogue: + b3, LayerNorm, mask, store
+      // layer 3 epilogue: + b3, LayerNorm (exact two-pass on registers; the two half-row threads exchange partial
+      // sums through shared memory), mask, store
       mbar_wait(acc_full, ph_acc);
       ph_acc ^= 1;
       tc_fence_after();
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C_Z; c0 += 32) {
-        tmem_ld32(lane_base + c0, v);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) sum += v[k] + b3_s[c0 + k];
-      }
-      const float mean = sum * (1.f / C_Z);
-      float sq = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C_Z; c0 += 32) {
-        tmem_ld32(lane_base + c0, v);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float d = v[k] + b3_s[c0 + k] - mean;
-          sq += d * d;
-        }
-      }
-      const float rstd = rsqrtf(sq * (1.f / C_Z) + 1e-5f);
-      const float m = e.mask[bi] * e.mask[bj];
-      bf16* orow = e.z_out + ((size_t)tile * TM + r) * C_Z;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C_Z; c0 += 32) {
-        tmem_ld32(lane_base + c0, v);
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          float o[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int c = c0 + gq * 8 + k;
-            o[k] = ((v[gq * 8 + k] + b3_s[c] - mean) * rstd * lnw_s[c] + lnb_s[c]) * m;
-          }
-          *reinterpret_cast<uint4*>(orow + c0 + gq * 8) =
-              make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-        }
-      }
+      tmem_ld32_issue(lane_base + hf * 64, v);
+      tmem_ld32_issue(lane_base + hf * 64 + 32, v + 32);
+      tmem_wait_ld();
       tc_fence_before();  // TMEM reads done before the next tile's MMA (ordered by the next a_full arrive)
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        v[k] += b3_s[hf * 64 + k];
+        sum += v[k];
+      }
+      red_s[hf * 128 + r] = sum;
+      named_bar_sync(2 + q, 64);
+      const float mean = (sum + red_s[(hf ^ 1) * 128 + r]) * (1.f / C_Z);
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        const float d = v[k] - mean;
+        sq += d * d;
+      }
+      red_s[256 + hf * 128 + r] = sq;
+      named_bar_sync(2 + q, 64);
+      const float rstd = rsqrtf((sq + red_s[256 + (hf ^ 1) * 128 + r]) * (1.f / C_Z) + 1e-5f);
+      const float m = e.mask[bi] * e.mask[bj];
+      bf16* orow = e.z_out + ((size_t)tile * TM + r) * C_Z + hf * 64;
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = hf * 64 + gq * 8 + k;
+          o[k] = ((v[gq * 8 + k] - mean) * rstd * lnw_s[c] + lnb_s[c]) * m;
+        }
+        *reinterpret_cast<uint4*>(orow + gq * 8) =
+            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      }
     }
   }
   tc_fence_before();
@@ -532,14 +535,14 @@ void edge_embed_tc(const EdgeEmbedArgs& a, cudaStream_t st) {
   EeTcArgs k;
   k.e = a; k.wimg = a.wimg; k.n_tiles = (int)((size_t)a.B * a.L * a.L / TM);
   static bool configured = false;
-  const int smem = EE_SMEM + 1024;
+  const int smem = EE_SMEM;  // two CTAs per SM: 2 x (112 KB + 1 KB reserved) must stay under 228 KB
   if (!configured) {
     S2S_CUDA(cudaFuncSetAttribute(edge_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   S2S_PROF("edge_embed", st);
   const int cap = 2 * sm_count();
-  edge_embed_tc_kernel<<<k.n_tiles < cap ? k.n_tiles : cap, 160, smem, st>>>(k);
+  edge_embed_tc_kernel<<<k.n_tiles < cap ? k.n_tiles : cap, EE_THREADS, smem, st>>>(k);
   S2S_LAUNCH_CHECK();
 }
 
