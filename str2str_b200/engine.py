@@ -56,6 +56,7 @@ class NativeEngine:
             self.set_option("pair_kernels", pair_kernels)
             self.set_option("node_gemm", node_gemm)
         self.shape = None
+        self.generation = 0  # bumped whenever the workspace is (re)allocated: invalidates captured CUDA graphs
 
     def __del__(self):
         ctx, self.ctx = getattr(self, "ctx", None), None
@@ -74,6 +75,7 @@ class NativeEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.s2s_reserve(self.ctx, B, L, lo - hi, hi - lo, _lib.stream()))
         self.shape = key
+        self.generation += 1
 
     # -- stage calls; all inputs fp32/int64 contiguous CUDA tensors -------------------------------------
     def net_forward(self, rigids_t, sc_ca, t, residue_idx, residue_mask, fixed_mask, gt_psi, out_rigids=None, out_psi=None):

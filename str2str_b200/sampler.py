@@ -96,23 +96,42 @@ class ForwardBackwardSampler:
         t_dev_all = t_all[:, None].expand(n, B).contiguous().to(dev)
         sched_d = torch.tensor([[dt, np.sqrt(dt)]] * B, dtype=torch.float64, device=dev)
 
-        t_cur = torch.empty(B, device=dev, dtype=torch.float32)
-        sched_cur = torch.empty(B, 8, device=dev, dtype=torch.float32)
-        sc = torch.zeros(B, L, 3, device=dev, dtype=torch.float32)
-        out7 = torch.empty(B, L, 7, device=dev, dtype=torch.float32)
-        psi = torch.empty(B, L, 2, device=dev, dtype=torch.float32)
         sde = not cfg.probability_flow
-        rot_n = torch.empty(B, L, 3, device=dev) if sde else None
-        tr_n = torch.empty(B, L, 3, device=dev) if sde else None
+        # Static buffers + the captured iteration are cached per (shape, mode) and reused by later calls: a call then
+        # costs n graph replays and no warm-up iteration / re-capture.  The cache entry dies with the engine workspace
+        # it points into (eng.generation changes whenever s2s_reserve re-allocates).
+        key = (B, L, str(dev), sde, bool(cfg.self_conditioning), float(cfg.noise_scale), bool(self.use_cuda_graph))
+        ctx = self._graphs.get(key)
+        if ctx is not None and ctx["generation"] != eng.generation:
+            ctx = None
+        fresh = ctx is None
+        if fresh:
+            f32 = dict(device=dev, dtype=torch.float32)
+            ctx = dict(generation=eng.generation, graph=None, per_replay=0,
+                       state=torch.empty(B, L, 7, **f32), sc=torch.zeros(B, L, 3, **f32), out7=torch.empty(B, L, 7, **f32),
+                       psi=torch.empty(B, L, 2, **f32), t_cur=torch.empty(B, **f32), sched_cur=torch.empty(B, 8, **f32),
+                       sched_d=torch.empty(B, 2, device=dev, dtype=torch.float64),
+                       rot_n=torch.empty(B, L, 3, **f32) if sde else None, tr_n=torch.empty(B, L, 3, **f32) if sde else None,
+                       ridx=torch.empty_like(s["ridx"]), rmask=torch.empty_like(s["rmask"]), fixed=torch.empty_like(s["fixed"]),
+                       gt_psi=torch.empty_like(s["gt_psi"]), diffuse=torch.empty_like(s["diffuse"]))
+            self._graphs[key] = ctx
+        for name in ("ridx", "rmask", "fixed", "gt_psi", "diffuse"):
+            ctx[name].copy_(s[name])
+        ctx["sched_d"].copy_(sched_d)
+        ctx["state"].copy_(state)
+        ctx["sc"].zero_()
+        state, sc, out7, psi, t_cur, sched_cur, sched_d = (ctx[k] for k in ("state", "sc", "out7", "psi", "t_cur", "sched_cur", "sched_d"))
+        rot_n, tr_n = ctx["rot_n"], ctx["tr_n"]
+        c = ctx
 
         def net_call():
-            eng.net_forward(state, sc, t_cur, s["ridx"], s["rmask"], s["fixed"], s["gt_psi"], out7, psi)
+            eng.net_forward(state, sc, t_cur, c["ridx"], c["rmask"], c["fixed"], c["gt_psi"], out7, psi)
 
         def step_body():
             net_call()
             if cfg.self_conditioning:
                 sc.copy_(out7[..., 4:])
-            self.diffuser.score_and_reverse(out7, state, s["rmask"], s["diffuse"], sched_cur, sched_d, state,
+            self.diffuser.score_and_reverse(out7, state, c["rmask"], c["diffuse"], sched_cur, sched_d, state,
                                             noise_scale=cfg.noise_scale, probability_flow=cfg.probability_flow,
                                             rot_noise=rot_n, trans_noise=tr_n)
 
@@ -121,8 +140,7 @@ class ForwardBackwardSampler:
                 t_cur.copy_(t_dev_all[0])
                 net_call()
                 sc.copy_(out7[..., 4:])
-            graph, per_replay = None, 0
-            if self.use_cuda_graph and n > 2:
+            if ctx["graph"] is None and self.use_cuda_graph and n > 2:
                 # warm-up outside capture (lazy allocations, function attributes), then capture one iteration
                 snap = (state.clone(), sc.clone())
                 t_cur.copy_(t_dev_all[0]); sched_cur.copy_(sched_all[0])
@@ -134,8 +152,10 @@ class ForwardBackwardSampler:
                 c0 = int(eng.lib.s2s_launch_count())
                 with torch.cuda.graph(graph):
                     step_body()
-                per_replay = int(eng.lib.s2s_launch_count()) - c0
+                ctx["graph"], ctx["per_replay"] = graph, int(eng.lib.s2s_launch_count()) - c0
+                lib0 += ctx["per_replay"]  # launches recorded while capturing were not executed
                 state.copy_(snap[0]); sc.copy_(snap[1])
+            graph, per_replay = (ctx["graph"], ctx["per_replay"]) if n > 2 else (None, 0)
             replays = 0
             for k in range(n):
                 t_cur.copy_(t_dev_all[k])
@@ -156,8 +176,8 @@ class ForwardBackwardSampler:
                     step_body()
             pred = out7 if last else state
             atom37, _ = eng.backbone_atoms(pred, psi, s["aatype"], want_atom14=False)
-        # launches recorded while capturing were not executed; each replay executes them once
-        self.launches = int(eng.lib.s2s_launch_count()) - lib0 + (replays - (1 if graph is not None else 0)) * per_replay
+        # each replay executes the captured launches once
+        self.launches = int(eng.lib.s2s_launch_count()) - lib0 + replays * per_replay
         result = atom37.detach().cpu().numpy() if return_numpy else atom37
         if return_rigids:
             return result, pred.clone(), psi.clone()
