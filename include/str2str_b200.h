@@ -45,7 +45,10 @@ int s2s_set_param(s2s_ctx* ctx, const char* name, const float* data, int64_t num
 int s2s_finalize(s2s_ctx* ctx, void* stream);
 /* Options: "pair_kernels" 0 = SIMT cross-check kernels, 1 = tcgen05 kernels (default), 2 = tcgen05 with the
  *                         first-generation EdgeTransition kernel (serial MMA/epilogue; kept for A/B timing);
- *          "node_gemm"    0 = exact fp32 FFMA everywhere, 1 = tensor-core GEMMs where the parity budget allows. */
+ *          "node_gemm"    0 = exact fp32 FFMA everywhere, 1 = tensor-core GEMMs where the parity budget allows;
+ *          "ipa_kernels"  1 = second-generation IPA path (default; needs node_gemm = 1, L <= 256, L % 16 == 0, other shapes
+ *                         fall back automatically): point-attention term folded into the logits GEMM, persistent TMA +
+ *                         tcgen05 pair kernel, split-bf16 attention weights; 0 = first-generation kernels (A/B, tests). */
 int s2s_set_option(s2s_ctx* ctx, const char* key, int value);
 /* Size the workspace for (B, L) and build the relative-position table for residue-index offsets in
  * [d_min, d_max] (= min/max of residue_idx[i] - residue_idx[j]).  Must be called before s2s_net_forward and

@@ -320,6 +320,300 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// ---- long chains (256 < L <= 512) -----------------------------------------------------------------------------------
+// A slab no longer fits twice in shared memory, so the pipeline runs at key-block granularity: a ring of five 32 KB
+// blocks ([128 keys x 128 channels]) is filled by the producer; a slab's NKB blocks stay resident from their bias MMA
+// until their zsum MMA, whose per-block tcgen05.commit hands the slot straight back to the producer, which is already
+// prefetching the next slab's blocks.  One 8-warp compute group (two warps per TMEM lane quarter; a thread owns keys
+// rb*128 + its lane for rb = half, half + 2), a producer warp and a dedicated MMA-issuer warp; bias accumulators and
+// the logits / P buffers are double-buffered by slab parity so bias(n+1) can start while slab n is in its epilogue.
+constexpr int PL_THREADS = 320;
+constexpr int PL_RING = 5;
+
+template <int NKB>
+struct PLLayout {
+  static constexpr int KP = NKB * 128;
+  static constexpr int BLOCK = 2 * TILE_BYTES;            // one key block: two 64-channel SW128 sub-blocks
+  static constexpr int SP_BYTES = NKB * 4096;             // logits rows [8][KP] fp32 -> P operand [16][KP] bf16
+  static constexpr int OFF_SP = PL_RING * BLOCK;
+  static constexpr int OFF_WB = OFF_SP + 2 * SP_BYTES;
+  static constexpr int OFF_WDZ = OFF_WB + 4096;
+  static constexpr int OFF_ZS = OFF_WDZ + C_Z * 32 * 4;   // [8][ZS_PITCH]
+  static constexpr int OFF_RED = OFF_ZS + 8 * ZS_PITCH * 4;  // [2][8 warps][8]
+  static constexpr int OFF_BAR = OFF_RED + 2 * 8 * 8 * 4;
+  static constexpr int N_BARS = 2 * PL_RING + 9;
+  static constexpr int BYTES = OFF_BAR + N_BARS * 8 + 16;
+};
+
+template <int NKB>
+__global__ void __launch_bounds__(PL_THREADS, 1)
+ipa_pair_tc_long_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
+  using LY = PLLayout<NKB>;
+  constexpr int KP = LY::KP;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
+  float* wdz_s = reinterpret_cast<float*>(smem + LY::OFF_WDZ);
+  float* zs = reinterpret_cast<float*>(smem + LY::OFF_ZS);
+  float* red = reinterpret_cast<float*>(smem + LY::OFF_RED);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::OFF_BAR);
+  uint64_t* full = bars;                        // [PL_RING] key block loaded
+  uint64_t* empty = bars + PL_RING;             // [PL_RING] key block consumed by its zsum MMAs
+  uint64_t* s_full = bars + 2 * PL_RING;        // [2] logits rows loaded
+  uint64_t* sp_empty = s_full + 2;              // [2] P operand consumed
+  uint64_t* bias_bar = s_full + 4;              // [2] bias accumulators ready
+  uint64_t* p_ready = s_full + 6;               // [2] P operand written (256 arrivals)
+  uint64_t* zsum_bar = s_full + 8;              // zsum accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + LY::N_BARS);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int L = a.L;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LY::N_BARS; ++s) mbar_init(&bars[s], 1);
+    mbar_init(&p_ready[0], 256);
+    mbar_init(&p_ready[1], 256);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  for (int idx = threadIdx.x; idx < 4096 / 16; idx += PL_THREADS)
+    reinterpret_cast<uint4*>(smem + LY::OFF_WB)[idx] = reinterpret_cast<const uint4*>(a.wb_img)[idx];
+  for (int idx = threadIdx.x; idx < C_Z * 32 / 4; idx += PL_THREADS)
+    reinterpret_cast<float4*>(wdz_s)[idx] = reinterpret_cast<const float4*>(a.Wdz_t)[idx];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_local = a.n_slabs > (int)blockIdx.x ? (a.n_slabs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr uint32_t BLK = TILE_BYTES >> 4;
+
+  if (warp == 8) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t blk = 0;
+      for (int n = 0; n < n_local; ++n) {
+        const int p = n & 1;
+        const int slab = blockIdx.x + n * gridDim.x;
+        const int b = slab / L, i = slab - b * L;
+        mbar_wait(&sp_empty[p], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&s_full[p], 8 * L * 4);
+        const float* Srow = a.S + ((long)b * N_H * L + i) * L;
+        unsigned char* sp = smem + LY::OFF_SP + p * LY::SP_BYTES;
+        for (int h = 0; h < N_H; ++h) tma_bulk_1d(sp + h * KP * 4, Srow + (long)h * L * L, L * 4, &s_full[p]);
+        for (int rb = 0; rb < NKB; ++rb, ++blk) {
+          const uint32_t slot = blk % PL_RING, ph = (blk / PL_RING) & 1;
+          mbar_wait(&empty[slot], ph ^ 1);
+          mbar_expect_tx(&full[slot], LY::BLOCK);
+          unsigned char* dst = smem + slot * LY::BLOCK;
+          tma_load_2d(dst, &tmap_z, 0, slab * L + rb * 128, &full[slot]);
+          tma_load_2d(dst + TILE_BYTES, &tmap_z, KBLK, slab * L + rb * 128, &full[slot]);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer (whole warp runs the loop, one elected lane issues) =====
+    const uint32_t ring_lo = desc_lo_sw128(smem_u32(smem));
+    const uint32_t ring_mn = ((smem_u32(smem) >> 4) & 0x3FFFu) | (a.a2_lbo << 16);
+    const uint32_t mn_hi = a.a2_sbo | (1u << 14) | (2u << 29);
+    const uint32_t wb_lo = desc_lo_sw128(smem_u32(smem + LY::OFF_WB));
+    constexpr uint32_t IDESC_B = make_idesc(128, 16);
+    constexpr uint32_t IDESC_Z = make_idesc(128, 16) | (1u << 15);
+    uint32_t blk = 0;
+    for (int n = 0; n < n_local; ++n, blk += NKB) {
+      const int p = n & 1;
+      const uint32_t d1 = tmem + p * 64, d2 = tmem + 128;
+      for (int rb = 0; rb < NKB; ++rb) {
+        const uint32_t slot = (blk + rb) % PL_RING, ph = ((blk + rb) / PL_RING) & 1;
+        mbar_wait(&full[slot], ph);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t al = ring_lo + (slot * 2 + cb) * BLK + ks * 2, bl = wb_lo + cb * (2048 >> 4) + ks * 2;
+              if (cb | ks) umma_ss<true>(d1 + rb * 16, al, bl, IDESC_B); else umma_ss<false>(d1 + rb * 16, al, bl, IDESC_B);
+            }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bias_bar[p]);
+      __syncwarp();
+      mbar_wait(&p_ready[p], (n >> 1) & 1);
+      tc_fence_after();
+      const uint32_t p_lo = desc_lo_sw128(smem_u32(smem + LY::OFF_SP + p * LY::SP_BYTES));
+      for (int rb = 0; rb < NKB; ++rb) {
+        const uint32_t slot = (blk + rb) % PL_RING;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t al = ring_mn + slot * 2 * BLK + ks * (2048 >> 4);
+            const uint32_t bl = p_lo + (rb * 2 + (ks >> 2)) * (2048 >> 4) + (ks & 3) * 2;
+            if (rb | ks) umma_desc<true>(d2, al, mn_hi, bl, DESC_HI_SW128, IDESC_Z);
+            else umma_desc<false>(d2, al, mn_hi, bl, DESC_HI_SW128, IDESC_Z);
+          }
+          umma_commit(&empty[slot]);  // this key block is done: the producer may refill its slot
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        umma_commit(zsum_bar);
+        umma_commit(&sp_empty[p]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== compute group: 8 warps, TMEM lane quarter q = warp % 4, half = warp / 4 =====
+    const int q = warp & 3, half = warp >> 2, t = threadIdx.x;
+    const int kl = q * 32 + lane;  // key within a block (= TMEM lane) / channel for zsum
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    constexpr int NU = (NKB + 1) / 2;  // key blocks per thread: rb = half + 2u
+    float bbias[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) bbias[h] = a.bb[h];
+    const int dd = t & 31, hd = t >> 5;
+    const float bdz = a.bdz[dd];
+    constexpr float SQRT1_3 = 0.57735026918962576f;
+    for (int n = 0; n < n_local; ++n) {
+      const int p = n & 1;
+      const int slab = blockIdx.x + n * gridDim.x;
+      const int b = slab / L, i = slab - b * L;
+      float* S_s = reinterpret_cast<float*>(smem + LY::OFF_SP + p * LY::SP_BYTES);
+      unsigned char* P_s = smem + LY::OFF_SP + p * LY::SP_BYTES;
+      float mk[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int j = (half + 2 * u) * 128 + kl;
+        mk[u] = (half + 2 * u < NKB && j < L) ? __ldg(a.mask + (long)b * L + j) : 0.f;
+      }
+      const float m_i = __ldg(a.mask + (long)b * L + i);
+      mbar_wait(&s_full[p], (n >> 1) & 1);
+      float x[NU][8];
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int h = 0; h < 8; ++h) x[u][h] = (half + 2 * u < NKB) ? S_s[h * KP + (half + 2 * u) * 128 + kl] : 0.f;
+      mbar_wait(&bias_bar[p], (n >> 1) & 1);
+      tc_fence_after();
+      float mx[8];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) mx[h] = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int rb = half + 2 * u;
+        if (rb < NKB) {  // warp-uniform
+          float d[16];
+          tmem_ld16(tmem + p * 64 + rb * 16 + lane_off, d);
+          const bool ok = rb * 128 + kl < L;
+          const float mterm = 1e5f * (m_i * mk[u] - 1.f);
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const float v = ok ? x[u][h] + SQRT1_3 * (d[h] + d[8 + h] + bbias[h]) + mterm : -INFINITY;
+            x[u][h] = v;
+            mx[h] = fmaxf(mx[h], v);
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 8; ++h) x[u][h] = -INFINITY;
+        }
+      }
+      tc_fence_before();
+#pragma unroll
+      for (int h = 0; h < 8; ++h) mx[h] = warp_max(mx[h]);
+      if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) red[warp * 8 + h] = mx[h];
+      }
+      named_bar_sync(1, 256);
+      float sum[8];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        float m = red[h];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w * 8 + h]);
+        mx[h] = m;
+        sum[h] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const float e = __expf(x[u][h] - mx[h]);
+          x[u][h] = e;
+          sum[h] += e;
+        }
+#pragma unroll
+      for (int h = 0; h < 8; ++h) sum[h] = warp_sum(sum[h]);
+      if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) red[64 + warp * 8 + h] = sum[h];
+      }
+      named_bar_sync(1, 256);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[64 + w * 8 + h];
+        sum[h] = 1.f / s;
+      }
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int rb = half + 2 * u;
+        if (rb >= NKB) continue;
+        const int j = rb * 128 + kl;
+        unsigned char* blkp = P_s + (rb * 2 + (kl >> 6)) * 2048;
+        const int jj = kl & 63;
+        bf16* gh = a.P_hi + ((long)b * N_H * L + i) * L + j;
+        bf16* gl = a.P_lo + ((long)b * N_H * L + i) * L + j;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const float pv = x[u][h] * sum[h];
+          const bf16 hi = __float2bfloat16_rn(pv);
+          const bf16 lo = __float2bfloat16_rn(pv - __bfloat162float(hi));
+          *reinterpret_cast<bf16*>(blkp + sw128_offset(h, jj)) = hi;
+          *reinterpret_cast<bf16*>(blkp + sw128_offset(8 + h, jj)) = lo;
+          if (j < L) {
+            gh[(long)h * L * L] = hi;
+            gl[(long)h * L * L] = lo;
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&p_ready[p]);
+      mbar_wait(zsum_bar, n & 1);
+      tc_fence_after();
+      if (half == 0) {
+        float d[16];
+        tmem_ld16(tmem + 128 + lane_off, d);  // lane = channel kl
+#pragma unroll
+        for (int h = 0; h < 8; ++h) zs[h * ZS_PITCH + kl] = d[h] + d[8 + h];
+      }
+      tc_fence_before();
+      named_bar_sync(1, 256);
+      float acc = bdz;
+      const float* z0 = zs + hd * ZS_PITCH;
+#pragma unroll 8
+      for (int c = 0; c < C_Z; c += 4) {
+        const float4 u0 = *reinterpret_cast<const float4*>(z0 + c);
+        acc = fmaf(wdz_s[c * 32 + dd], u0.x, acc);
+        acc = fmaf(wdz_s[(c + 1) * 32 + dd], u0.y, acc);
+        acc = fmaf(wdz_s[(c + 2) * 32 + dd], u0.z, acc);
+        acc = fmaf(wdz_s[(c + 3) * 32 + dd], u0.w, acc);
+      }
+      const long o0 = ((long)b * L + i) * a.ld_opair + hd * 32 + dd;
+      if (a.opair_hi) {
+        const bf16 h0 = __float2bfloat16_rn(acc);
+        a.opair_hi[o0] = h0;
+        a.opair_lo[o0] = __float2bfloat16_rn(acc - __bfloat162float(h0));
+      } else {
+        a.o_pair[o0] = acc;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // [Wb_hi (8 rows); Wb_lo (8 rows)] x 128 channels -> two [16 x 64] bf16 blocks in the SW128 K-major layout
 __global__ void build_ipa_wb_kernel(const float* __restrict__ Wb, unsigned char* __restrict__ dst) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -345,6 +639,19 @@ void launch_pair_tc(const IpaPairArgs& a, const CUtensorMap& mz, const P2Args& k
   S2S_LAUNCH_CHECK();
 }
 
+template <int NKB>
+void launch_pair_tc_long(const CUtensorMap& mz, const P2Args& k, cudaStream_t st) {
+  using LY = PLLayout<NKB>;
+  static bool configured = false;
+  const int smem = LY::BYTES;
+  if (!configured) {
+    S2S_CUDA(cudaFuncSetAttribute(ipa_pair_tc_long_kernel<NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  ipa_pair_tc_long_kernel<NKB><<<k.n_slabs < sm_count() ? k.n_slabs : sm_count(), PL_THREADS, smem, st>>>(mz, k);
+  S2S_LAUNCH_CHECK();
+}
+
 }  // namespace
 
 size_t ipa_wb_img_elems() { return 2 * 16 * KBLK; }
@@ -354,10 +661,10 @@ void build_ipa_wb_img(const float* Wb, bf16* dst, cudaStream_t st) {
   S2S_LAUNCH_CHECK();
 }
 
-bool ipa_pair_attention_tc_supported(int L) { return L >= 1 && L <= 256 && L % 4 == 0; }
+bool ipa_pair_attention_tc_supported(int L) { return L >= 1 && L <= 512 && L % 4 == 0; }
 
 void ipa_pair_attention_tc(const IpaPairArgs& a, cudaStream_t st) {
-  S2S_CHECK(ipa_pair_attention_tc_supported(a.L), "ipa_pair_attention_tc: needs L <= 256 and L % 4 == 0");
+  S2S_CHECK(ipa_pair_attention_tc_supported(a.L), "ipa_pair_attention_tc: needs L <= 512 and L % 4 == 0");
   S2S_CHECK(a.wb_img && a.P_bf16 && a.P_lo, "ipa_pair_attention_tc: weight image / P outputs missing");
   const size_t rows = (size_t)a.B * a.L * a.L;
   const CUtensorMap mz = make_bf16_2d_map(a.z, rows, C_Z, C_Z);
@@ -372,7 +679,10 @@ void ipa_pair_attention_tc(const IpaPairArgs& a, cudaStream_t st) {
     if (atoi(e) & 1) { const uint32_t tmp = k.a2_lbo; k.a2_lbo = k.a2_sbo; k.a2_sbo = tmp; }
   }
   S2S_PROF("ipa_pair_attention", st);
-  if (a.L <= 128) launch_pair_tc<1>(a, mz, k, st); else launch_pair_tc<2>(a, mz, k, st);
+  if (a.L <= 128) launch_pair_tc<1>(a, mz, k, st);
+  else if (a.L <= 256) launch_pair_tc<2>(a, mz, k, st);
+  else if (a.L <= 384) launch_pair_tc_long<3>(mz, k, st);
+  else launch_pair_tc_long<4>(mz, k, st);
 }
 
 }  // namespace s2s

@@ -309,12 +309,13 @@ def test_long_chain_forward_L512(params):
     assert r < 2e-5
 
 
-@pytest.mark.parametrize("L", [64, 128, 208, 256])
+@pytest.mark.parametrize("L", [64, 128, 208, 256, 320, 384, 512])
 def test_ipa_second_generation_vs_first_and_oracle(params, L):
     """Second-generation IPA path (point term folded into the logits GEMM, persistent tcgen05 pair kernel, split-bf16
     attention weights) against the first-generation kernels on the same engine and against the fp32 oracle.
-    L=208 exercises a ragged second key block, L=64 a ragged first one."""
-    B = 3
+    L=208 exercises a ragged second key block, L=64 a ragged first one; L > 256 takes the long-chain kernel (ring of
+    128-key blocks): 320 = three blocks with a ragged last one, 384 = three full, 512 = four (BASELINE cfg 4 / cfg 5)."""
+    B = 3 if L <= 256 else 2
     g = torch.Generator().manual_seed(29)
     node = torch.randn(B, L, 256, generator=g)
     edge = torch.randn(B, L, L, 128, generator=g).bfloat16()
@@ -322,7 +323,7 @@ def test_ipa_second_generation_vs_first_and_oracle(params, L):
     rig = torch.cat([q, 0.1 * x], -1)[None].repeat(B, 1, 1) + 0.05 * torch.randn(B, L, 7, generator=g)
     nm = torch.ones(B, L)
     nm[1, -5:] = 0
-    nm[2, :3] = 0
+    nm[B - 1, :3] = 0
     net = make_net(params, 1, 1)
     eng = net.native("cuda")
     eng.reserve(B, L, torch.arange(L)[None].repeat(B, 1))

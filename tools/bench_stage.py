@@ -1,5 +1,5 @@
 """Time individual stages at benchmark size with CUDA events: python tools/bench_stage.py [B] [L]
-Env: S2S_PAIR (0/1/2), S2S_WIMG_COPIES."""
+Env: S2S_PAIR (0/1/2), S2S_IPA (0/1), S2S_WIMG_COPIES."""
 import os, sys, torch
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 from str2str_b200 import synthetic
@@ -11,6 +11,8 @@ net = DenoisingNet(EmbeddingModule(32, 256, 128), TranslationIPA(c_s=256, c_z=12
 net.load_state_dict(synthetic.make_state_dict(0, 0.02), strict=True)
 net = net.cuda().eval()
 eng = net.native("cuda")
+if "S2S_IPA" in os.environ:
+    eng.set_option("ipa_kernels", int(os.environ["S2S_IPA"]))
 f = {k: v.cuda() for k, v in synthetic.make_features(B, L, seed=7).items()}
 eng.reserve(B, L, f["residue_idx"])
 q, x = synthetic.make_backbone(L, seed=7)
