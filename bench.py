@@ -278,7 +278,7 @@ def run_ours(a):
                         peak_source=src, timing="CUDA events around each launch, one eager step")
 
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:  # reported at N=1 only (the host cores are shared by the ranks otherwise)
         cpu = cpu_baseline(L, n, a.cpu_sample_forwards)
 
     if rank == 0:

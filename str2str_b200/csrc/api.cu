@@ -448,7 +448,7 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
     g.A_hi = node_sp.hi; g.a_rows = R; g.a_cols = 256; g.a_pitch = 256;
     g.B_hi = ws.first; g.b_rows = 6144; g.b_cols = 256; g.b_pitch = 256;
     g.M = R; g.N = 6144; g.K = 256; g.passes = 1; g.bias = w.proj_b;
-    g.out_hi = c->qkv_bf16; g.ldo = 6144; g.out_vt = c->vT; g.vt_L = L;
+    g.out_hi = c->qkv_bf16; g.ldo = 6144;  // v stays row-major: P.v reads it as an MN-major B operand (no transposed copy)
     gemm_tc(g, st);
     // point projections keep split-bf16 accuracy (they become nm-scale coordinates)
     TcGemm p;
@@ -504,7 +504,7 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   if (tc) {  // o = P v -> feats[:, h*256 + c]
     TcGemm g;
     g.A_hi = c->P_bf16; g.a_rows = (size_t)B * N_H * L; g.a_cols = L; g.a_pitch = L; g.a_rb = N_H * L; g.a_rh = L;
-    g.B_hi = c->vT; g.b_rows = (size_t)B * N_H * C_H; g.b_cols = L; g.b_pitch = L; g.b_rb = N_H * C_H; g.b_rh = C_H;
+    g.B_hi = c->qkv_bf16 + 2048 + C_H; g.b_rows = R; g.b_cols = 6144 - 2048 - C_H; g.b_pitch = 6144; g.b_rb = L; g.b_ch = 2 * C_H; g.b_mn = 1;
     g.M = L; g.N = C_H; g.K = L; g.nb = B; g.nh = N_H; g.passes = 1;
     g.ldc = IPA_FEAT; g.sCb = (long)L * IPA_FEAT; g.sCh = C_H;
     if (fused) { g.out_hi = c->sa_hi; g.out_lo = c->sa_lo; g.ldo = IPA_FEAT; } else g.C = c->feats;
@@ -581,8 +581,6 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     g.B_hi = w.first; g.B_lo = w.second; g.b_rows = 960; g.b_cols = 320; g.b_pitch = 320;
     g.M = R; g.N = 960; g.K = 320; g.passes = 3; g.bias = c->P(tl + "self_attn.in_proj_bias");
     g.out_hi = c->tq_hi; g.out_lo = sp ? c->tq_lo : nullptr; g.ldo = 960;
-    g.out_vt = c->tvT_hi; g.out_vt_lo = sp ? c->tvT_lo : nullptr; g.vt_L = L;
-    g.vt_col0 = 640; g.vt_stride = TFM_HD; g.vt_off = 0; g.vt_width = TFM_HD; g.vt_heads = TFM_H;
     gemm_tc(g, st);
     TcGemm s;  // logits = q.k^T / sqrt(80), batched over (decoy, head), split-bf16
     s.A_hi = c->tq_hi; s.A_lo = c->tq_lo; s.a_rows = R; s.a_cols = 960; s.a_pitch = 960; s.a_rb = L; s.a_ch = TFM_HD;
@@ -593,7 +591,7 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     softmax_keybias(c->S, c->keybias, B, TFM_H, L, st, c->P_bf16, sp ? c->tP_lo : nullptr);
     TcGemm p;  // y = P v
     p.A_hi = c->P_bf16; p.A_lo = c->tP_lo; p.a_rows = (size_t)B * TFM_H * L; p.a_cols = L; p.a_pitch = L; p.a_rb = TFM_H * L; p.a_rh = L;
-    p.B_hi = c->tvT_hi; p.B_lo = c->tvT_lo; p.b_rows = (size_t)B * TFM_H * TFM_HD; p.b_cols = L; p.b_pitch = L; p.b_rb = TFM_H * TFM_HD; p.b_rh = TFM_HD;
+    p.B_hi = c->tq_hi + 640; p.B_lo = c->tq_lo + 640; p.b_rows = R; p.b_cols = 320; p.b_pitch = 960; p.b_rb = L; p.b_ch = TFM_HD; p.b_mn = 1;  // v columns, read MN-major
     p.M = L; p.N = TFM_HD; p.K = L; p.nb = B; p.nh = TFM_H; p.passes = c->tfm_passes;
     p.C = c->y320; p.ldc = 320; p.sCb = (long)L * 320; p.sCh = TFM_HD;
     p.out_hi = c->y320_hi; p.out_lo = c->y320_lo; p.ldo = 320;

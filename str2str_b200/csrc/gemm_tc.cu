@@ -40,6 +40,7 @@ struct TcKernelArgs {
   int K2, a2_cb, a2_ch, a2_rb, a2_rh, b2_cb, b2_ch, b2_rb, b2_rh;
   long bias_sb, bias_sh;  // batch strides of `bias` (0: one bias vector for every batch)
   int epi_warps;          // 4 or 8 epilogue warps (blockDim = 64 + 32 * epi_warps)
+  int b_mn;               // B operand is MN-major ([K][N] source), see TcGemm
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1)
@@ -100,6 +101,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             continue;
           }
           tma_load_2d(st, &mAh, acol + kb * KBLK, arow, &s_full[s]);
+          if (a.b_mn) {  // two [64 k-rows x 64 n] boxes = the 128 n columns of this tile for one 64-wide K block
+            const int r0 = ib * a.b_rb + ih * a.b_rh + kb * KBLK, c0 = bcol + nt * 128;
+            tma_load_2d(st + TILE_BYTES, &mBh, c0, r0, &s_full[s]);
+            tma_load_2d(st + TILE_BYTES + TILE_BYTES / 2, &mBh, c0 + 64, r0, &s_full[s]);
+            if (a.passes == 3) {
+              tma_load_2d(st + 2 * TILE_BYTES, &mAl, acol + kb * KBLK, arow, &s_full[s]);
+              tma_load_2d(st + 3 * TILE_BYTES, &mBl, c0, r0, &s_full[s]);
+              tma_load_2d(st + 3 * TILE_BYTES + TILE_BYTES / 2, &mBl, c0 + 64, r0, &s_full[s]);
+            }
+            continue;
+          }
           tma_load_2d(st + TILE_BYTES, &mBh, bcol + kb * KBLK, brow, &s_full[s]);
           if (a.passes == 3) {
             tma_load_2d(st + 2 * TILE_BYTES, &mAl, acol + kb * KBLK, arow, &s_full[s]);
@@ -113,6 +125,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     uint32_t cnt = 0, it = 0;
     const uint32_t ring = desc_lo_sw128(smem_u32(smem));
     constexpr uint32_t BLK = TILE_BYTES >> 4;
+    const uint32_t idesc = a.b_mn ? (IDESC | (1u << 16)) : IDESC;            // bit 16: B is MN-major
+    const uint32_t bmn_fix = ((uint32_t)(TILE_BYTES / 2) >> 4 << 16) - (1u << 16);  // LBO field 1 -> 512 (8 KB)
     const uint32_t stage_units = blocks_per_stage * BLK;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ab = it & 1, aph = (it >> 1) & 1;
@@ -128,11 +142,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         if (elect_one()) {
           if (!(a.dbg & 16)) {
             for (int k = 0; k < ksteps; ++k) {
-              const uint32_t ah = st + 2 * k, bh = st + BLK + 2 * k;
-              if (kb | k) umma_ss<true>(d, ah, bh, IDESC); else umma_ss<false>(d, ah, bh, IDESC);
+              // K-major B: k-step = +32 B inside the 128-byte rows.  MN-major B: k-step = 16 rows = +2 KB; the descriptor's
+              // leading-byte-offset field (bits 16..29) carries the 8 KB distance between the two 64-column halves.
+              const uint32_t ah = st + 2 * k;
+              const uint32_t bh = a.b_mn ? st + BLK + 128 * k + bmn_fix : st + BLK + 2 * k;
+              if (kb | k) umma_ss<true>(d, ah, bh, idesc); else umma_ss<false>(d, ah, bh, idesc);
               if (a.passes == 3) {
-                umma_ss<true>(d, st + 2 * BLK + 2 * k, bh, IDESC);
-                umma_ss<true>(d, ah, st + 3 * BLK + 2 * k, IDESC);
+                umma_ss<true>(d, st + 2 * BLK + 2 * k, bh, idesc);
+                umma_ss<true>(d, ah, bh + 2 * BLK, idesc);
               }
             }
           }
@@ -346,8 +363,10 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   S2S_CHECK(g.K2 == 0 || (g.passes == 1 && g.A2 && g.B2 && g.K2 % 16 == 0), "gemm_tc: a second K segment needs passes == 1 and both operands");
   const CUtensorMap mAl = g.passes == 3 ? make_bf16_2d_map(g.A_lo, g.a_rows, g.a_cols, g.a_pitch)
                           : g.K2     ? make_bf16_2d_map(g.A2, g.a2_rows, g.a2_cols, g.a2_pitch) : mAh;
-  const CUtensorMap mBh = make_bf16_2d_map(g.B_hi, g.b_rows, g.b_cols, g.b_pitch);
-  const CUtensorMap mBl = g.passes == 3 ? make_bf16_2d_map(g.B_lo, g.b_rows, g.b_cols, g.b_pitch)
+  S2S_CHECK(!g.b_mn || g.K2 == 0, "gemm_tc: an MN-major B operand cannot be combined with a second K segment");
+  const int b_box = g.b_mn ? 64 : 128;
+  const CUtensorMap mBh = make_bf16_2d_map(g.B_hi, g.b_rows, g.b_cols, g.b_pitch, b_box);
+  const CUtensorMap mBl = g.passes == 3 ? make_bf16_2d_map(g.B_lo, g.b_rows, g.b_cols, g.b_pitch, b_box)
                           : g.K2     ? make_bf16_2d_map(g.B2, g.b2_rows, g.b2_cols, g.b2_pitch) : mBh;
   TcKernelArgs k;
   k.dbg = 0;
@@ -355,6 +374,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   k.b2_cb = g.b2_cb; k.b2_ch = g.b2_ch; k.b2_rb = g.b2_rb; k.b2_rh = g.b2_rh;
   k.bias_sb = g.bias_sb; k.bias_sh = g.bias_sh;
   k.epi_warps = 8;
+  k.b_mn = g.b_mn;
   if (const char* e = getenv("S2S_GEMM_EPI")) k.epi_warps = atoi(e) == 4 ? 4 : 8;  // timing experiments only
   k.a_cb = g.a_cb; k.a_ch = g.a_ch; k.a_rb = g.a_rb; k.a_rh = g.a_rh;
   k.b_cb = g.b_cb; k.b_ch = g.b_ch; k.b_rb = g.b_rb; k.b_rh = g.b_rh;

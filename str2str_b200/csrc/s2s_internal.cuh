@@ -41,6 +41,9 @@ struct TcGemm {
   size_t a2_rows = 0, a2_cols = 0, a2_pitch = 0; int a2_cb = 0, a2_ch = 0, a2_rb = 0, a2_rh = 0;
   size_t b2_rows = 0, b2_cols = 0, b2_pitch = 0; int b2_cb = 0, b2_ch = 0, b2_rb = 0, b2_rh = 0;
   long bias_sb = 0, bias_sh = 0;  // batch strides of `bias` (per-(batch, head) column bias when non-zero)
+  // b_mn = 1: B is given as [K rows][N columns] (N contiguous, e.g. the v columns of a row-major q|k|v buffer) and is read
+  // as an MN-major UMMA operand: box row = ib*b_rb + ih*b_rh + kb*64, box column = ib*b_cb + ih*b_ch + n0 (+64).
+  int b_mn = 0;
 };
 void gemm_tc(const TcGemm& g, cudaStream_t st);
 void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st);
