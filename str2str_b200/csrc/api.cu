@@ -359,7 +359,7 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     for (int k = 0; k < 8; ++k) add(R * 256, 2);
     for (int k = 0; k < 6; ++k) add(R * 320, 2);
     add(R * 128, 2);
-    add(R * N_H * PT_K, 2); add(R * N_H * PT_K, 2); add(R * N_H * P_V * 3, 2); add(R * N_H * P_V * 3, 2);
+    add(R * N_H * PT_K, 2); add(R * N_H * PT_K, 2); add(R * N_H * VP_PITCH, 2); add(R * N_H * VP_PITCH, 2);
     add((size_t)B * N_H * L * L, 2); add(R * N_H, 4);
     c->ws.cap = bytes + 4096;
     S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
@@ -388,7 +388,7 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->y320_hi = w.take<bf16>(R * 320); c->y320_lo = w.take<bf16>(R * 320);
     c->nprime_hi = c->nprime_bf16; c->nprime_lo = w.take<bf16>(R * 128);
     c->qp_aug = w.take<bf16>(R * N_H * PT_K); c->kp_aug = w.take<bf16>(R * N_H * PT_K);
-    c->vpT_hi = w.take<bf16>(R * N_H * P_V * 3); c->vpT_lo = w.take<bf16>(R * N_H * P_V * 3);
+    c->vpT_hi = w.take<bf16>(R * N_H * VP_PITCH); c->vpT_lo = w.take<bf16>(R * N_H * VP_PITCH);
     c->P_lo = w.take<bf16>((size_t)B * N_H * L * L); c->colbias = w.take<float>(R * N_H);
     c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
   }
@@ -464,7 +464,7 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   const bool fused = tc && c->opt_ipa == 1 && ipa_pair_attention_tc_supported(L);
   IpaPointsAug aug;
   if (fused) {
-    aug.qp_aug = c->qp_aug; aug.kp_aug = c->kp_aug; aug.colbias = c->colbias; aug.vpT_hi = c->vpT_hi; aug.vpT_lo = c->vpT_lo;
+    aug.qp_aug = c->qp_aug; aug.kp_aug = c->kp_aug; aug.colbias = c->colbias; aug.vp_hi = c->vpT_hi; aug.vp_lo = c->vpT_lo;
     aug.pt_w = w.pt_w; aug.inv_alpha = 1.f / qk_scale; aug.L = L;
   }
   ipa_points(c->proj + 6144, 6816, c->proj + 6336, 6816, quat, trans, c->q_pts, c->k_pts, c->v_pts, R, st, aug);
@@ -513,7 +513,7 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   if (fused) {  // o_pt (global frame) = P v_pts, split-bf16 on the tensor cores
     TcGemm g;
     g.A_hi = c->P_bf16; g.A_lo = c->P_lo; g.a_rows = (size_t)B * N_H * L; g.a_cols = L; g.a_pitch = L; g.a_rb = N_H * L; g.a_rh = L;
-    g.B_hi = c->vpT_hi; g.B_lo = c->vpT_lo; g.b_rows = (size_t)B * N_H * P_V * 3; g.b_cols = L; g.b_pitch = L; g.b_rb = N_H * P_V * 3; g.b_rh = P_V * 3;
+    g.B_hi = c->vpT_hi; g.B_lo = c->vpT_lo; g.b_rows = R; g.b_cols = N_H * VP_PITCH; g.b_pitch = N_H * VP_PITCH; g.b_rb = L; g.b_ch = VP_PITCH; g.b_mn = 1;  // row-major value points
     g.M = L; g.N = P_V * 3; g.K = L; g.nb = B; g.nh = N_H; g.passes = 3;
     g.C = c->opt; g.ldc = N_H * P_V * 3; g.sCb = (long)L * N_H * P_V * 3; g.sCh = P_V * 3;
     gemm_tc(g, st);
@@ -662,8 +662,7 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
     linear(c, c->b256, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), c->a256, 256, R, 256, 256, st, 0, c->node, 256, nullptr, nullptr, -1, b_sp);
     layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, R, 256, st, node_sp.hi, node_sp.lo);
     // backbone update on node * diffuse_mask, exact fp32    (ipa.py:367-369)
-    linear(c, c->node, 256, c->P(tk + "bb_update_" + s + ".linear.weight"), 256, c->P(tk + "bb_update_" + s + ".linear.bias"), c->upd6, 6, R, 6, 256, st, 0, nullptr, 0, c->diffuse, nullptr, EXACT);
-    frame_update(c->quat, c->trans, c->upd6, c->diffuse, R, st);
+    bb_update_frame(c->node, c->P(tk + "bb_update_" + s + ".linear.weight"), c->P(tk + "bb_update_" + s + ".linear.bias"), c->quat, c->trans, c->diffuse, R, st);
     if (b < N_BLK - 1) do_edge_transition(c, b, B, L, c->node, c->z, rmask, c->z, st, node_sp);
   }
   const std::string tp = "translator.torsion_pred.";

@@ -364,6 +364,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   const CUtensorMap mAl = g.passes == 3 ? make_bf16_2d_map(g.A_lo, g.a_rows, g.a_cols, g.a_pitch)
                           : g.K2     ? make_bf16_2d_map(g.A2, g.a2_rows, g.a2_cols, g.a2_pitch) : mAh;
   S2S_CHECK(!g.b_mn || g.K2 == 0, "gemm_tc: an MN-major B operand cannot be combined with a second K segment");
+  S2S_CHECK(!g.b_mn || ((g.b_cb | g.b_ch) % 8 == 0), "gemm_tc: MN-major B boxes must start on 16-byte boundaries (column offsets % 8)");
   const int b_box = g.b_mn ? 64 : 128;
   const CUtensorMap mBh = make_bf16_2d_map(g.B_hi, g.b_rows, g.b_cols, g.b_pitch, b_box);
   const CUtensorMap mBl = g.passes == 3 ? make_bf16_2d_map(g.B_lo, g.b_rows, g.b_cols, g.b_pitch, b_box)

@@ -17,7 +17,8 @@ namespace {
 //     one bf16 MMA over these 72 (+8 zero) columns gives  w_h q_pts.k_pts  to ~2^-17 relative;
 //   colbias [b][h][j] = -0.5 w_h |k_pts_j|^2.  Together: -0.5 w_h |q - k|^2 up to a per-query constant, which the
 //     softmax over keys cancels exactly (ipa.py:191-205,215);
-//   (vpT_hi / vpT_lo, the transposed split-bf16 value points, are written by ipa_vpts_transpose_kernel below.)
+//   vp_hi / vp_lo [row][8][40]: split-bf16 value points (36 + 4 zero columns per head), row-major (read as the MN-major B operand of the P.v_pts GEMM).
+// In this mode the fp32 point arrays are not written at all.
 __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict__ qp, long ld_q,
                                                          const float* __restrict__ kvp, long ld_kv,
                                                          const float* __restrict__ quat,
@@ -57,14 +58,20 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
     o[0] = R[0] * x + R[1] * y + R[2] * z + tx;
     o[1] = R[3] * x + R[4] * y + R[5] * z + ty;
     o[2] = R[6] * x + R[7] * y + R[8] * z + tz;
-    dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+    if (!aug.qp_aug) { dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; }  // fp32 points: first-generation / exact path only
   }
   if (!aug.qp_aug) return;  // uniform
+  // tensor-core operands: built in shared memory, written out as whole 16-byte chunks (one per thread)
+  __shared__ __align__(16) bf16 row_s[2 * N_H * PT_K + 2 * N_H * VP_PITCH];  // q row | k row | v hi | v lo
+  bf16* q_row = row_s;
+  bf16* k_row = row_s + N_H * PT_K;
+  bf16* v_hi = row_s + 2 * N_H * PT_K;
+  bf16* v_lo = v_hi + N_H * VP_PITCH;
   const int b = r / aug.L, j = r % aug.L;
   if (kind == 0 || kind == 1) {
     const float w = aug.pt_w[h];
     const float sw = sqrtf(w * aug.inv_alpha);  // the GEMM epilogue multiplies the whole accumulator by alpha
-    bf16* dst = (kind == 0 ? aug.qp_aug : aug.kp_aug) + ((long)r * N_H + h) * PT_K + p * 3;
+    bf16* dst = (kind == 0 ? q_row : k_row) + h * PT_K + p * 3;
     float k2 = 0.f;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
@@ -81,35 +88,32 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
       for (int e = 0; e < 8; ++e) dst[72 + e] = __float2bfloat16_rn(0.f);
     }
     if (kind == 1) k2_s[h * P_Q + p] = k2;
+  } else if (kind == 2) {
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const bf16 hi = __float2bfloat16_rn(o[e]);
+      v_hi[h * VP_PITCH + p * 3 + e] = hi;
+      v_lo[h * VP_PITCH + p * 3 + e] = __float2bfloat16_rn(o[e] - __bfloat162float(hi));
+    }
+    if (p == 0) {  // the 4 pad columns of this head (a TMA box must start on a 16-byte boundary: 40-column head pitch)
+#pragma unroll
+      for (int e = P_V * 3; e < VP_PITCH; ++e) v_hi[h * VP_PITCH + e] = v_lo[h * VP_PITCH + e] = __float2bfloat16_rn(0.f);
+    }
   }
   __syncthreads();
+  {
+    constexpr int NQC = N_H * PT_K / 8, NVC = N_H * VP_PITCH / 8;  // 16-byte chunks per row: 80 and 40
+    const uint4* src = reinterpret_cast<const uint4*>(row_s);
+    if (tid < NQC) reinterpret_cast<uint4*>(aug.qp_aug + (long)r * N_H * PT_K)[tid] = src[tid];
+    else if (tid < 2 * NQC) reinterpret_cast<uint4*>(aug.kp_aug + (long)r * N_H * PT_K)[tid - NQC] = src[tid];
+    else if (tid < 2 * NQC + NVC) reinterpret_cast<uint4*>(aug.vp_hi + (long)r * N_H * VP_PITCH)[tid - 2 * NQC] = src[tid];
+    else if (tid < 2 * NQC + 2 * NVC) reinterpret_cast<uint4*>(aug.vp_lo + (long)r * N_H * VP_PITCH)[tid - 2 * NQC - NVC] = src[tid];
+  }
   if (tid < N_H) {
     float s = 0.f;
 #pragma unroll
     for (int pp = 0; pp < P_Q; ++pp) s += k2_s[tid * P_Q + pp];
     aug.colbias[((long)b * N_H + tid) * aug.L + j] = -0.5f * s;
-  }
-}
-
-// v_pts [b][j][288] fp32 -> vpT_hi / vpT_lo [b][288][L] split bf16 (K-major B operand of the P.v_pts GEMM), 32 keys per block
-__global__ void __launch_bounds__(256) ipa_vpts_transpose_kernel(const float* __restrict__ v_pts, bf16* __restrict__ hi,
-                                                                 bf16* __restrict__ lo, int L) {
-  constexpr int NV = N_H * P_V * 3;
-  __shared__ float tile[32][NV + 1];
-  const int b = blockIdx.y, j0 = blockIdx.x * 32;
-  for (int idx = threadIdx.x; idx < 32 * NV; idx += 256) {
-    const int jl = idx / NV, c = idx % NV;
-    tile[jl][c] = j0 + jl < L ? v_pts[((long)b * L + j0 + jl) * NV + c] : 0.f;
-  }
-  __syncthreads();
-  const int jl = threadIdx.x % 32;
-  if (j0 + jl >= L) return;
-  for (int c = threadIdx.x / 32; c < NV; c += 8) {
-    const float v = tile[jl][c];
-    const bf16 h = __float2bfloat16_rn(v);
-    const long o = ((long)b * NV + c) * L + j0 + jl;
-    hi[o] = h;
-    lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
 
@@ -341,13 +345,10 @@ void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv
                 const float* trans, float* q_pts, float* k_pts, float* v_pts, int rows, cudaStream_t st,
                 const IpaPointsAug& aug) {
   S2S_PROF("ipa_points", st);
-  S2S_CHECK(!aug.qp_aug || (aug.kp_aug && aug.colbias && aug.vpT_hi && aug.vpT_lo && aug.pt_w && aug.L > 0), "ipa_points: incomplete operand set");
+  S2S_CHECK(!aug.qp_aug || (aug.kp_aug && aug.colbias && aug.vp_hi && aug.vp_lo && aug.pt_w && aug.L > 0), "ipa_points: incomplete operand set");
   ipa_points_kernel<<<rows, 256, 0, st>>>(qp_raw, ld_q, kvp_raw, ld_kv, quat, trans, q_pts, k_pts, v_pts, rows, aug);
   S2S_LAUNCH_CHECK();
-  if (aug.qp_aug) {
-    ipa_vpts_transpose_kernel<<<dim3(ceil_div(aug.L, 32), rows / aug.L), 256, 0, st>>>(v_pts, aug.vpT_hi, aug.vpT_lo, aug.L);
-    S2S_LAUNCH_CHECK();
-  }
+
 }
 
 void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const float* pt_w, int B, int L,

@@ -165,6 +165,52 @@ __global__ void frame_update_kernel(float* __restrict__ quat, float* __restrict_
   trans[r * 3 + 2] += (R[6] * u[3] + R[7] * u[4] + R[8] * u[5]) * m;
 }
 
+// BackboneUpdate + compose_q_update_vec in one pass (layers.py:232-241, rigid_utils.py:1042-1066): one warp per residue
+// computes the six outputs of Linear(256 -> 6)(node * diffuse_mask) in exact fp32 and applies them to the frame.
+__global__ void __launch_bounds__(256) bb_update_frame_kernel(const float* __restrict__ node, const float* __restrict__ W,
+                                                              const float* __restrict__ bias, float* __restrict__ quat,
+                                                              float* __restrict__ trans, const float* __restrict__ diffuse,
+                                                              int rows) {
+  const int lane = threadIdx.x % 32;
+  const int r = blockIdx.x * 8 + threadIdx.x / 32;
+  if (r >= rows) return;
+  const float4 x0 = *reinterpret_cast<const float4*>(node + (long)r * C_S + lane * 8);
+  const float4 x1 = *reinterpret_cast<const float4*>(node + (long)r * C_S + lane * 8 + 4);
+  float u[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + k * C_S + lane * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + k * C_S + lane * 8 + 4));
+    float acc = x0.x * w0.x;
+    acc = fmaf(x0.y, w0.y, acc); acc = fmaf(x0.z, w0.z, acc); acc = fmaf(x0.w, w0.w, acc);
+    acc = fmaf(x1.x, w1.x, acc); acc = fmaf(x1.y, w1.y, acc); acc = fmaf(x1.z, w1.z, acc); acc = fmaf(x1.w, w1.w, acc);
+    u[k] = warp_sum(acc);
+  }
+  if (lane != 0) return;
+  const float m = diffuse[r];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) u[k] = u[k] * m + bias[k];
+  float q[4] = {quat[r * 4], quat[r * 4 + 1], quat[r * 4 + 2], quat[r * 4 + 3]};
+  float R[9];
+  quat_to_rot(q, R);
+  const float vq[4] = {0.f, u[0], u[1], u[2]};
+  float dq[4];
+  quat_mul(q, vq, dq);
+  float nq[4];
+  float n2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    nq[k] = q[k] + dq[k] * m;
+    n2 += nq[k] * nq[k];
+  }
+  const float n = sqrtf(n2);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) quat[r * 4 + k] = nq[k] / n;
+  trans[r * 3 + 0] += (R[0] * u[3] + R[1] * u[4] + R[2] * u[5]) * m;
+  trans[r * 3 + 1] += (R[3] * u[3] + R[4] * u[4] + R[5] * u[5]) * m;
+  trans[r * 3 + 2] += (R[6] * u[3] + R[7] * u[4] + R[8] * u[5]) * m;
+}
+
 __global__ void split_rigids_kernel(const float* __restrict__ rig, float* __restrict__ quat,
                                     float* __restrict__ trans, int rows) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,6 +462,12 @@ __global__ void backbone_atoms_kernel(const float* __restrict__ rig, const float
 
 void frame_update(float* quat, float* trans, const float* upd6, const float* diffuse, int rows, cudaStream_t st) {
   frame_update_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(quat, trans, upd6, diffuse, rows);
+  S2S_LAUNCH_CHECK();
+}
+void bb_update_frame(const float* node, const float* W, const float* bias, float* quat, float* trans, const float* diffuse,
+                     int rows, cudaStream_t st) {
+  S2S_PROF("bb_update_frame", st);
+  bb_update_frame_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(node, W, bias, quat, trans, diffuse, rows);
   S2S_LAUNCH_CHECK();
 }
 void split_rigids(const float* rig7, float* quat, float* trans_nm, int rows, cudaStream_t st) {

@@ -124,11 +124,12 @@ void build_ee_wimg(const float* W2, const float* W3, bf16* dst, cudaStream_t st)
 void f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t st);
 
 // ---- ipa.cu -------------------------------------------------------------------------------------------
+constexpr int VP_PITCH = 40;  // value-point columns per head in the split-bf16 images: 36 + 4 zeros (16-byte aligned TMA boxes)
 constexpr int PT_K = 80;  // point columns of the fused logits GEMM: 3 x 24 split-bf16 coordinates + 8 zeros
 struct IpaPointsAug {     // optional tensor-core operand outputs of ipa_points (see the kernel)
   bf16 *qp_aug = nullptr, *kp_aug = nullptr;  // [rows][N_H][PT_K]
   float* colbias = nullptr;                   // [B][N_H][L]
-  bf16 *vpT_hi = nullptr, *vpT_lo = nullptr;  // [B][N_H][36][L]
+  bf16 *vp_hi = nullptr, *vp_lo = nullptr;    // [rows][N_H][VP_PITCH]
   const float* pt_w = nullptr;                // [N_H] softplus(head_weights) * sqrt(1/108)
   float inv_alpha = 1.f;                      // 1 / (alpha of the logits GEMM): the point columns are pre-divided by it
   int L = 0;
@@ -166,6 +167,8 @@ void softplus_point_weights(const float* head_w, float* pt_w, cudaStream_t st);
 
 // ---- rigid.cu -----------------------------------------------------------------------------------------
 void frame_update(float* quat, float* trans, const float* upd6, const float* diffuse, int rows, cudaStream_t st);
+void bb_update_frame(const float* node, const float* W, const float* bias, float* quat, float* trans, const float* diffuse,
+                     int rows, cudaStream_t st);
 void split_rigids(const float* rig7, float* quat, float* trans_nm, int rows, cudaStream_t st);
 void join_rigids(const float* quat, const float* trans_nm, float* rig7, int rows, cudaStream_t st);
 struct Se3StepArgs {
