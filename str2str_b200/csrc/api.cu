@@ -104,7 +104,7 @@ struct IpaW {
 };
 struct EtW {
   bf16 *W1z, *W2, *Wfh, *Wfz, *W1zt, *W2t, *Wft, *Wfzt;
-  bf16 *wimg, *wimg2;  // tcgen05 weight images (first / second generation kernel)
+  bf16 *wimg, *wimg2, *wimg3;  // tcgen05 weight images (first / second / third generation kernel)
 };
 
 }  // namespace
@@ -292,7 +292,10 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
       build_et_wimg(W1, W2, Wf, x.wimg, st);
       x.wimg2 = c->wslab.take<bf16>(et2_wimg_elems() * c->wimg_copies);
       build_et2_wimg(W1, W2, Wf, x.wimg2, st);
+      x.wimg3 = c->wslab.take<bf16>(et3_wimg_elems() * c->wimg_copies);
+      build_et3_wimg(W1, W2, Wf, x.wimg3, st);
       for (int k = 1; k < c->wimg_copies; ++k) {
+        S2S_CUDA(cudaMemcpyAsync(x.wimg3 + k * et3_wimg_elems(), x.wimg3, et3_wimg_elems() * 2, cudaMemcpyDeviceToDevice, st));
         S2S_CUDA(cudaMemcpyAsync(x.wimg + k * et_wimg_elems(), x.wimg, et_wimg_elems() * 2, cudaMemcpyDeviceToDevice, st));
         S2S_CUDA(cudaMemcpyAsync(x.wimg2 + k * et2_wimg_elems(), x.wimg2, et2_wimg_elems() * 2, cudaMemcpyDeviceToDevice, st));
       }
@@ -561,10 +564,13 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   a.W1z = w.W1z; a.W2 = w.W2; a.Wfh = w.Wfh; a.Wfz = w.Wfz;
   a.W1zt = w.W1zt; a.W2t = w.W2t; a.Wft = w.Wft; a.Wfzt = w.Wfzt;
   a.b2 = c->P(e + "trunk.2.bias"); a.ln_w = c->P(e + "layer_norm.weight"); a.ln_b = c->P(e + "layer_norm.bias");
-  a.z_out = z_out; a.wimg = w.wimg; a.wimg2 = w.wimg2; a.wimg_copies = c->wimg_copies; a.nprime_bf16 = c->nprime_bf16;
+  a.z_out = z_out; a.wimg = w.wimg; a.wimg2 = w.wimg2; a.wimg3 = w.wimg3; a.wimg_copies = c->wimg_copies; a.nprime_bf16 = c->nprime_bf16;
   if (!tc) edge_transition_simt(a, st);
   else if (c->opt_pair == 2) edge_transition_tc(a, st);  // first-generation kernel (serial MMA / epilogue), kept for A/B
-  else edge_transition_tc2(a, st);
+  else {
+    static const int gen = [] { const char* e = getenv("S2S_ET_GEN"); return e ? atoi(e) : 3; }();  // 2: previous kernel (A/B)
+    if (gen == 2) edge_transition_tc2(a, st); else edge_transition_tc3(a, st);
+  }
 }
 
 void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {

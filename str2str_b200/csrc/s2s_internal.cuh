@@ -110,11 +110,15 @@ struct EdgeTransitionArgs {
   const bf16* wimg = nullptr;         // tcgen05 path: pre-swizzled weight blocks (build_et_wimg)
   const bf16* nprime_bf16 = nullptr;  // tcgen05 path: n' [B*L][128] in bf16 (the n'_j operand rows)
   const bf16* wimg2 = nullptr;        // second-generation kernel: 8 KB weight blocks (build_et2_wimg)
+  const bf16* wimg3 = nullptr;        // third-generation kernel (build_et3_wimg)
   int wimg_copies = 1;                // number of identical images laid out back to back (L2 hot-spot relief)
 };
 void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st);
 void edge_transition_tc(const EdgeTransitionArgs& a, cudaStream_t st);
 void edge_transition_tc2(const EdgeTransitionArgs& a, cudaStream_t st);
+void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st);
+size_t et3_wimg_elems();
+void build_et3_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);
 size_t et2_wimg_elems();
 void build_et2_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);
 size_t et_wimg_elems();
