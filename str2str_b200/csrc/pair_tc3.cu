@@ -8,8 +8,8 @@
 // fit next to h1 (192 columns) and h2 (192 columns), so every h2 chunk is stored IN PLACE over the first half of the
 // accumulator it was drained from (or into the one spare 64-column strip), and the final layer accumulates in the
 // then-dead h1 region.  TMEM map (512 columns x 128 lanes):
-//   E  = [  0,128)  accumulator: layer-1 chunks 0, 2; layer-2 chunks 0, 2      -> afterwards h2 chunk 2 in [0,64)
-//   R2 = [128,256)  accumulator: layer-1 chunk 1;     layer-2 chunk 1         -> afterwards h2 chunk 1 in [128,192)
+//   E  = [  0,128)  accumulator: layer-1 chunks 0, 2; layer-2 chunk 1         -> afterwards h2 chunk 1 in [0,64)
+//   R2 = [128,256)  accumulator: layer-1 chunk 1;     layer-2 chunks 0, 2      -> afterwards h2 chunk 2 in [128,192)
 //   H1 = [256,448)  h1 (384 packed bf16)                                      -> afterwards the final-layer accumulator [256,384)
 //   S  = [448,512)  h2 chunk 0
 // Ordering that makes the aliasing safe: tcgen05.mma instructions of one thread execute in issue order, so the final
@@ -38,14 +38,14 @@ constexpr int CW = 128 / NPART;             // accumulator columns per thread pe
 constexpr int ET3_THREADS = 64 + 32 * NEW;
 constexpr int VEC_FLOATS = D_ET + C_Z + D_ET + C_Z + C_Z + 2 * NPART * 128;  // u_i, p_i, b2, ln_w, ln_b, LayerNorm partial sums
 constexpr int OFF_BAR = OFF_VEC + VEC_FLOATS * 4;
-constexpr int N_BARS = 2 * NSTAGE + 12;
+constexpr int N_BARS = 2 * NSTAGE + 18;
 constexpr int SMEM_BYTES = OFF_BAR + N_BARS * 8 + 16;
 
 constexpr uint32_t COL_H1 = 256;
 constexpr uint32_t COL_FIN = 256;  // final-layer accumulator (over the dead h1)
 // packed h2 columns of K-block kb (64 k = 32 columns): chunk kb/2 lives in S, R2[0:64), E[0:64)
-__device__ __forceinline__ uint32_t h2_col(int kb) { return (kb < 2 ? 448u : kb < 4 ? 128u : 0u) + 32u * (kb & 1); }
-__device__ __forceinline__ uint32_t h2_chunk_col(int c) { return c == 0 ? 448u : c == 1 ? 128u : 0u; }
+__device__ __forceinline__ uint32_t h2_col(int kb) { return (kb < 2 ? 448u : kb < 4 ? 0u : 128u) + 32u * (kb & 1); }
+__device__ __forceinline__ uint32_t h2_chunk_col(int c) { return c == 0 ? 448u : c == 1 ? 0u : 128u; }
 
 struct Args {
   const bf16* wimg;
@@ -101,8 +101,8 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   uint64_t* fullF = a0_full + 4;    // final-layer accumulator ready
   uint64_t* emptyE = a0_full + 6;
   uint64_t* empty2 = a0_full + 7;
-  uint64_t* h1_full = a0_full + 10;
-  uint64_t* h2_full = a0_full + 11;
+  uint64_t* h1p = a0_full + 12;     // [3] h1 columns of layer-1 chunk nc are in tensor memory (K-blocks 2nc, 2nc+1 of layer 2)
+  uint64_t* h2p = a0_full + 15;     // [3] h2 chunk c is in tensor memory (K-blocks 2c, 2c+1 of the final layer)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -118,8 +118,10 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
     mbar_init(fullF, 1);
     mbar_init(emptyE, 32 * NEW);
     mbar_init(empty2, 32 * NEW);
-    mbar_init(h1_full, 32 * NEW);
-    mbar_init(h2_full, 32 * NEW);
+    for (int k = 0; k < 3; ++k) {
+      mbar_init(&h1p[k], 32 * NEW);
+      mbar_init(&h2p[k], 32 * NEW);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -212,16 +214,19 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
           if (elect_one()) umma_commit(nc == 1 ? full2 : fullE);
           __syncwarp();
         }
-        // ---- layer 2: three 128-column chunks in E, R2, E; A = h1 from tensor memory ----
-        mbar_wait(h1_full, ph_h1);
-        ph_h1 ^= 1;
-        tc_fence_after();
+        // ---- layer 2: three 128-column chunks in R2, E, R2; A = h1 from tensor memory.  Chunk 0 starts as soon as R2
+        //      (layer-1 chunk 1) is drained and consumes h1 K-block by K-block as the layer-1 drains deliver it, so
+        //      the tensor pipe does not idle through the drain of layer-1 chunk 2 ----
         for (int c = 0; c < 3; ++c) {
           uint32_t d;
-          if (c == 1) { wait_prev(empty2, n2); d = tmem + 128; }
-          else { wait_prev(emptyE, nE); d = tmem; }
+          if (c == 1) { wait_prev(emptyE, nE); d = tmem; }
+          else { wait_prev(empty2, n2); d = tmem + 128; }
           tc_fence_after();
           for (int kb = 0; kb < 6; ++kb, ++cnt) {  // one block = [128 n x 64 k]
+            if (c == 0 && !(kb & 1)) {
+              mbar_wait(&h1p[kb >> 1], ph_h1);
+              tc_fence_after();
+            }
             const uint32_t wb = next_block();
             if (elect_one()) {
               if (do_mma) kblock_ts(d, tmem + COL_H1 + kb * 32, wb, IDESC128, kb == 0);
@@ -229,9 +234,10 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
             }
             __syncwarp();
           }
-          if (elect_one()) umma_commit(c == 1 ? full2 : fullE);
+          if (elect_one()) umma_commit(c == 1 ? fullE : full2);
           __syncwarp();
         }
+        ph_h1 ^= 1;
         // ---- final layer into F (the h1 region: its last readers, the layer-2 MMAs above, were issued earlier):
         //      [z | n'_j] terms (A in shared memory), then h2 (A in tensor memory) ----
         for (int kb = 0; kb < 4; ++kb, ++cnt) {
@@ -244,10 +250,11 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
         }
         if (elect_one()) umma_commit(a0_empty);  // the activation tile is free: the next tile's TMA overlaps the rest of this layer
         __syncwarp();
-        mbar_wait(h2_full, ph_h2);
-        ph_h2 ^= 1;
-        tc_fence_after();
         for (int kb = 0; kb < 6; ++kb, ++cnt) {
+          if (!(kb & 1)) {
+            mbar_wait(&h2p[kb >> 1], ph_h2);
+            tc_fence_after();
+          }
           const uint32_t wb = next_block();
           if (elect_one()) {
             if (do_mma) kblock_ts(tmem + COL_FIN, tmem + h2_col(kb), wb, IDESC128, false);
@@ -255,6 +262,7 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
           }
           __syncwarp();
         }
+        ph_h2 ^= 1;
         if (elect_one()) umma_commit(fullF);
         __syncwarp();
       }
@@ -323,14 +331,14 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
         }
         tc_fence_before();
         mbar_arrive(nc == 1 ? empty2 : emptyE);
+        mbar_arrive(&h1p[nc]);
       }
-      mbar_arrive(h1_full);
       // ---- layer 2: + b2, relu, pack, into tensor memory as the final layer's A operand.  Chunk 0 goes to the spare
       //      strip; chunks 1 and 2 overwrite the first half of the accumulator they came from, so the NPART warps of a
       //      row quarter first agree that all of them have read it ----
       for (int c = 0; c < 3; ++c) {
-        const uint32_t base = c == 1 ? 128u : 0u;
-        if (c == 1) wait_full(full2, f2); else wait_full(fullE, fE);
+        const uint32_t base = c == 1 ? 0u : 128u;  // accumulators R2, E, R2
+        if (c == 1) wait_full(fullE, fE); else wait_full(full2, f2);
         if (do_epi) {
           load_cols(base + part * CW, CW);
           add_vec(b2_s + c * 128 + part * CW, CW);
@@ -342,9 +350,9 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
           store_packed(h2_chunk_col(c) + part * (CW / 2), CW);
         }
         tc_fence_before();
-        mbar_arrive(c == 1 ? empty2 : emptyE);
+        mbar_arrive(c == 1 ? emptyE : empty2);
+        mbar_arrive(&h2p[c]);
       }
-      mbar_arrive(h2_full);
       // ---- output: + p_i, LayerNorm over 128 channels (exact two-pass; the NPART threads of a row exchange partial sums
       //      through shared memory), * edge mask, bf16 store ----
       {
