@@ -138,7 +138,7 @@ def ncu_traffic(B, L):
     import csv
 
     out = {}
-    for fn, names in (("r01b_ncu_full_edge_transition.csv", {"edge_transition_tc2_kernel": "edge_transition"}),
+    for fn, names in (("r01b_ncu_full_edge_transition.csv", {"edge_transition_tc": "edge_transition"}),
                       ("r01b_ncu_full_ipa_stage_kernels.csv", {"ipa_pair_tc_kernel": "ipa_pair_attention", "edge_embed_tc_kernel": "edge_embed"})):
         path = os.path.join(ROOT, "profiles", fn)
         if not os.path.exists(path):
