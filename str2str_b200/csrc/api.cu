@@ -134,10 +134,10 @@ struct s2s_ctx {
   bf16 *z, *nprime_bf16;
   // tensor-core node track: bf16 hi/lo images of every weight matrix, scratch split buffers, attention operands
   std::map<const float*, std::pair<size_t, std::pair<bf16*, bf16*>>> wsplit;  // fp32 base -> (numel, (hi, lo))
-  bf16 *sa_hi, *sa_lo, *qkv_bf16, *vT, *P_bf16;
-  bf16 *qp_aug, *kp_aug, *vpT_hi, *vpT_lo, *P_lo;  // fused-logits / split-P operands of the second-generation IPA path
+  bf16 *sa_hi, *sa_lo, *qkv_bf16, *P_bf16;
+  bf16 *qp_aug, *kp_aug, *vp_hi, *vp_lo, *P_lo;  // fused-logits / split-P operands of the second-generation IPA path
   float* colbias;
-  bf16 *tq_hi, *tq_lo, *tvT_hi, *tvT_lo, *tP_lo;  // sequence-transformer attention operands (split bf16)
+  bf16 *tq_hi, *tq_lo, *tP_lo;  // sequence-transformer attention operands (split bf16; v is read in place, MN-major)
   // split-bf16 companions of the node-track activations, written by the producing kernel's epilogue
   bf16 *node_hi, *node_lo, *init_hi, *init_lo, *a256_hi, *a256_lo, *b256_hi, *b256_lo;
   bf16 *x320_hi, *x320_lo, *t320_hi, *t320_lo, *y320_hi, *y320_lo, *nprime_hi, *nprime_lo;
@@ -382,8 +382,8 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->z = w.take<bf16>(R * L * C_Z);
     c->nprime_bf16 = w.take<bf16>(R * 128);
     c->sa_hi = w.take<bf16>(R * IPA_FEAT); c->sa_lo = w.take<bf16>(R * IPA_FEAT);
-    c->qkv_bf16 = w.take<bf16>(R * 6144); c->vT = w.take<bf16>(R * 2048); c->P_bf16 = w.take<bf16>((size_t)B * N_H * L * L);
-    c->tq_hi = w.take<bf16>(R * 960); c->tq_lo = w.take<bf16>(R * 960); c->tvT_hi = w.take<bf16>(R * 320); c->tvT_lo = w.take<bf16>(R * 320);
+    c->qkv_bf16 = w.take<bf16>(R * 6144); c->P_bf16 = w.take<bf16>((size_t)B * N_H * L * L);
+    c->tq_hi = w.take<bf16>(R * 960); c->tq_lo = w.take<bf16>(R * 960);
     c->tP_lo = w.take<bf16>((size_t)B * TFM_H * L * L);
     c->node_hi = w.take<bf16>(R * 256); c->node_lo = w.take<bf16>(R * 256); c->init_hi = w.take<bf16>(R * 256); c->init_lo = w.take<bf16>(R * 256);
     c->a256_hi = w.take<bf16>(R * 256); c->a256_lo = w.take<bf16>(R * 256); c->b256_hi = w.take<bf16>(R * 256); c->b256_lo = w.take<bf16>(R * 256);
@@ -391,7 +391,7 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->y320_hi = w.take<bf16>(R * 320); c->y320_lo = w.take<bf16>(R * 320);
     c->nprime_hi = c->nprime_bf16; c->nprime_lo = w.take<bf16>(R * 128);
     c->qp_aug = w.take<bf16>(R * N_H * PT_K); c->kp_aug = w.take<bf16>(R * N_H * PT_K);
-    c->vpT_hi = w.take<bf16>(R * N_H * VP_PITCH); c->vpT_lo = w.take<bf16>(R * N_H * VP_PITCH);
+    c->vp_hi = w.take<bf16>(R * N_H * VP_PITCH); c->vp_lo = w.take<bf16>(R * N_H * VP_PITCH);
     c->P_lo = w.take<bf16>((size_t)B * N_H * L * L); c->colbias = w.take<float>(R * N_H);
     c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
   }
@@ -467,7 +467,7 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   const bool fused = tc && c->opt_ipa == 1 && ipa_pair_attention_tc_supported(L);
   IpaPointsAug aug;
   if (fused) {
-    aug.qp_aug = c->qp_aug; aug.kp_aug = c->kp_aug; aug.colbias = c->colbias; aug.vp_hi = c->vpT_hi; aug.vp_lo = c->vpT_lo;
+    aug.qp_aug = c->qp_aug; aug.kp_aug = c->kp_aug; aug.colbias = c->colbias; aug.vp_hi = c->vp_hi; aug.vp_lo = c->vp_lo;
     aug.pt_w = w.pt_w; aug.inv_alpha = 1.f / qk_scale; aug.L = L;
   }
   ipa_points(c->proj + 6144, 6816, c->proj + 6336, 6816, quat, trans, c->q_pts, c->k_pts, c->v_pts, R, st, aug);
@@ -516,7 +516,7 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   if (fused) {  // o_pt (global frame) = P v_pts, split-bf16 on the tensor cores
     TcGemm g;
     g.A_hi = c->P_bf16; g.A_lo = c->P_lo; g.a_rows = (size_t)B * N_H * L; g.a_cols = L; g.a_pitch = L; g.a_rb = N_H * L; g.a_rh = L;
-    g.B_hi = c->vpT_hi; g.B_lo = c->vpT_lo; g.b_rows = R; g.b_cols = N_H * VP_PITCH; g.b_pitch = N_H * VP_PITCH; g.b_rb = L; g.b_ch = VP_PITCH; g.b_mn = 1;  // row-major value points
+    g.B_hi = c->vp_hi; g.B_lo = c->vp_lo; g.b_rows = R; g.b_cols = N_H * VP_PITCH; g.b_pitch = N_H * VP_PITCH; g.b_rb = L; g.b_ch = VP_PITCH; g.b_mn = 1;  // row-major value points
     g.M = L; g.N = P_V * 3; g.K = L; g.nb = B; g.nh = N_H; g.passes = 3;
     g.C = c->opt; g.ldc = N_H * P_V * 3; g.sCb = (long)L * N_H * P_V * 3; g.sCh = P_V * 3;
     gemm_tc(g, st);
@@ -588,6 +588,11 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     g.M = R; g.N = 960; g.K = 320; g.passes = 3; g.bias = c->P(tl + "self_attn.in_proj_bias");
     g.out_hi = c->tq_hi; g.out_lo = sp ? c->tq_lo : nullptr; g.ldo = 960;
     gemm_tc(g, st);
+    static const int fused_attn = [] { const char* e = getenv("S2S_TFM_FUSED"); return e ? atoi(e) : 1; }();
+    if (fused_attn && !sp && tfm_attention_supported(L)) {
+      // q.k^T, key-biased softmax and P.v in one kernel: logits and weights never leave the SM
+      tfm_attention(c->tq_hi, c->keybias, c->y320, c->y320_hi, c->y320_lo, B, L, scale, st);
+    } else {
     TcGemm s;  // logits = q.k^T / sqrt(80), batched over (decoy, head), split-bf16
     s.A_hi = c->tq_hi; s.A_lo = c->tq_lo; s.a_rows = R; s.a_cols = 960; s.a_pitch = 960; s.a_rb = L; s.a_ch = TFM_HD;
     s.B_hi = c->tq_hi + 320; s.B_lo = c->tq_lo + 320; s.b_rows = R; s.b_cols = 640; s.b_pitch = 960; s.b_rb = L; s.b_ch = TFM_HD;
@@ -602,6 +607,7 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     p.C = c->y320; p.ldc = 320; p.sCb = (long)L * 320; p.sCh = TFM_HD;
     p.out_hi = c->y320_hi; p.out_lo = c->y320_lo; p.ldo = 320;
     gemm_tc(p, st);
+    }
   } else {
     linear(c, c->x320, 320, c->P(tl + "self_attn.in_proj_weight"), 320, c->P(tl + "self_attn.in_proj_bias"), c->qkv, 960, R, 960, 320, st);
     GemmArgs g;

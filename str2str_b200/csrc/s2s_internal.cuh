@@ -169,6 +169,10 @@ void ipa_finalize_points(const float* opt_glob, const float* quat, const float* 
                          cudaStream_t st, bf16* f_hi = nullptr, bf16* f_lo = nullptr);
 void softplus_point_weights(const float* head_w, float* pt_w, cudaStream_t st);
 
+// ---- tfm_attn.cu --------------------------------------------------------------------------------------
+bool tfm_attention_supported(int L);
+void tfm_attention(const bf16* qkv, const float* keybias, float* y, bf16* y_hi, bf16* y_lo, int B, int L, float scale, cudaStream_t st);
+
 // ---- rigid.cu -----------------------------------------------------------------------------------------
 void frame_update(float* quat, float* trans, const float* upd6, const float* diffuse, int rows, cudaStream_t st);
 void bb_update_frame(const float* node, const float* W, const float* bias, float* quat, float* trans, const float* diffuse,
