@@ -198,6 +198,16 @@ class ForwardBackwardSampler:
             done += bs
         return np.concatenate(outs, axis=0)
 
+    def sample_to_pdb(self, batch: Dict[str, torch.Tensor], t_delta: float, save_to: str, n_replica: Optional[int] = None):
+        """`sample` followed by the ensemble write of predict_step (diffusion_module.py:225-232,354-361): all replicas as
+        MODEL records of one PDB file, with the protein's own aatype / chain_index / residue_index.  The file is
+        byte-identical to the reference's `atom37_to_pdb` (str2str_b200/pdb_writer.py)."""
+        from .pdb_writer import atom37_to_pdb
+
+        atom37 = self.sample(batch, t_delta, n_replica)
+        extra = {k: batch[k][0].detach().cpu().numpy() for k in ("aatype", "chain_index", "residue_index") if k in batch}
+        return atom37_to_pdb(save_to=save_to, atom_positions=atom37, overwrite=True, **extra)
+
     def sample_sharded(self, batch: Dict[str, torch.Tensor], t_delta: float, n_replica: int):
         """Decoy-sharded sampling under torch.distributed: rank r samples its contiguous share, then ONE
         all_gather of the final atom coordinates.  Works with any backend (nccl on GPUs)."""
