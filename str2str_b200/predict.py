@@ -1,0 +1,88 @@
+"""The caller of the hot path: the δ-sweep of `DiffusionLitModule.predict_step` (reference
+src/models/diffusion_module.py:214-369) as a plain function over a `ForwardBackwardSampler`.
+
+    all_delta_dir = predict_step(sampler, batch, output_dir=...)
+
+For every δ in [delta_min, delta_max] (step delta_step, rounded to 2 decimals) it samples `n_replica` conformations in
+batches of `replica_per_batch`, writes them as one multi-MODEL PDB `<output_dir>/<δ>/<accession>.pdb`, and finally merges
+all δ files into `<output_dir>/all_delta/<accession>.pdb` — same directory layout, file names and file bytes as the
+reference (`merge_pdbfiles` below is pinned to the reference's own function, tests/golden/pdb_merged.npz).
+With `backward_only` the sweep collapses to one pure-reverse run of n_replica * len(δ) samples from the prior (:245-247).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .pdb_writer import atom37_to_pdb
+from .sampler import ForwardBackwardSampler
+
+
+def delta_range(cfg) -> np.ndarray:
+    """diffusion_module.py:231-236."""
+    return np.around(np.arange(cfg.delta_min, cfg.delta_max + 1e-5, cfg.delta_step), decimals=2)
+
+
+def merge_pdbfiles(files: List[str], output_file: str) -> int:
+    """Ordered merge of PDB files into one multi-MODEL file with renumbered models (reference
+    src/common/pdb_utils.py:31-82, including its quirk that every line starting with 'END' — ENDMDL too — is dropped and
+    an ENDMDL is re-inserted in front of each following MODEL).  Returns the number of models."""
+    if isinstance(files, str):
+        files = [os.path.join(files, f) for f in os.listdir(files) if f.endswith(".pdb")]
+    os.makedirs(os.path.dirname(output_file), exist_ok=True)
+    model_number = 0
+    out: List[str] = []
+    for path in files:
+        with open(path, "r") as f:
+            lines = f.readlines()
+        single_model = not any(ln.startswith("MODEL") or ln.startswith("ENDMDL") for ln in lines)
+        if single_model:
+            model_number += 1
+            out.append(f"MODEL     {model_number}")
+            out.extend(ln.strip() for ln in lines if ln.startswith("TER") or ln.startswith("ATOM"))
+            out.append("ENDMDL")
+        else:
+            for ln in lines:
+                if ln.startswith("MODEL"):
+                    model_number += 1
+                    if model_number > 1:
+                        out.append("ENDMDL")
+                    out.append(f"MODEL     {model_number}")
+                elif ln.startswith("END"):
+                    continue
+                elif ln.startswith("TER") or ln.startswith("ATOM"):
+                    out.append(ln.strip())
+    out.append("ENDMDL")
+    out.append("END")
+    with open(output_file, "w") as fo:
+        fo.write("\n".join(ln.ljust(80) for ln in out) + "\n")
+    return model_number
+
+
+def predict_step(sampler: ForwardBackwardSampler, batch: Dict[str, torch.Tensor], output_dir: Optional[str] = None) -> str:
+    """One protein (batch size 1, like the reference asserts) through the whole δ-sweep; returns the all_delta directory."""
+    cfg = sampler.cfg
+    output_dir = output_dir or cfg.output_dir
+    if output_dir is None:
+        raise ValueError("predict_step needs an output directory (argument or InferenceConfig.output_dir)")
+    assert batch["aatype"].shape[0] == 1, "Batch size must be 1 for correct inference."
+    n_replica = cfg.n_replica
+    deltas = [float(d) for d in delta_range(cfg)]
+    if cfg.backward_only:
+        n_replica *= len(deltas)
+        deltas = [-1.0]
+    accession = batch["accession_code"][0] if "accession_code" in batch else "protein"
+    extra = {k: batch[k][0].detach().cpu().numpy() for k in ("aatype", "chain_index", "residue_index") if k in batch}
+    saved = []
+    for t_delta in deltas:
+        atom37 = sampler.sample(batch, t_delta, n_replica)  # [n_replica, L, 37, 3], replica_per_batch at a time
+        d = os.path.join(output_dir, f"{t_delta}")
+        os.makedirs(d, exist_ok=True)
+        saved.append(atom37_to_pdb(save_to=os.path.join(d, f"{accession}.pdb"), atom_positions=atom37, **extra))
+    all_delta_dir = os.path.join(output_dir, "all_delta")
+    os.makedirs(all_delta_dir, exist_ok=True)
+    merge_pdbfiles(saved, os.path.join(all_delta_dir, f"{accession}.pdb"))
+    return all_delta_dir

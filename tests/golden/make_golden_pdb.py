@@ -71,8 +71,35 @@ def case(name, n_models, L, seed, with_aatype, chain_break=None, residue_offset=
     print(name, len(text), "bytes", text.count("\n"), "lines")
 
 
+def merged_case():
+    """merge_pdbfiles (pdb_utils.py:31-82) over two multi-model goldens and one single-model file without MODEL records."""
+    from src.common.pdb_utils import merge_pdbfiles
+
+    names = ["pdb_default_L12_m3.npz", "pdb_aatype_gly_L20_m2.npz"]
+    with tempfile.TemporaryDirectory() as d:
+        files = []
+        for n in names:
+            p = os.path.join(d, n[:-4] + ".pdb")
+            open(p, "wb").write(bytes(np.load(os.path.join(OUT, n))["text"]))
+            files.append(p)
+        txt = bytes(np.load(os.path.join(OUT, names[0]))["text"]).decode().split("\n")
+        first = []
+        for ln in (x for x in txt[1:] if x.startswith("ATOM") or x.startswith("TER")):
+            first.append(ln)
+            if ln.startswith("TER"):
+                break
+        single = os.path.join(d, "single.pdb")
+        open(single, "w").write("\n".join(first) + "\nEND\n")
+        files.append(single)
+        out = os.path.join(d, "o", "merged.pdb")
+        merge_pdbfiles(files, out, verbose=False)
+        np.savez_compressed(os.path.join(OUT, "pdb_merged.npz"), inputs=np.array(names),
+                            single=np.frombuffer(open(single, "rb").read(), np.uint8), text=np.frombuffer(open(out, "rb").read(), np.uint8))
+
+
 if __name__ == "__main__":
     case("default_L12_m3", 3, 12, 1, False)
     case("aatype_gly_L20_m2", 2, 20, 2, True, gly=True)
     case("chains_resid_L16_m2", 2, 16, 3, True, chain_break=9, residue_offset=5)
     case("wide_coords_L8_m1", 1, 8, 4, True, big=True)
+    merged_case()

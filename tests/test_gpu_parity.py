@@ -365,3 +365,34 @@ def test_sampler_graph_cache_across_shapes(params):
     a3 = run(64, 2, 1)
     assert torch.equal(a1, a2) and torch.equal(a1, a3) and torch.equal(b1, b2)
     assert torch.isfinite(a1).all() and torch.isfinite(b1).all()
+
+
+def test_predict_step_delta_sweep_layout(params, tmp_path):
+    """The caller of the path (predict_step, diffusion_module.py:214-369): directory layout, file names, model counts and
+    the merged all_delta file for a 2-delta sweep with an odd last batch (3 replicas in batches of 2)."""
+    from str2str_b200.predict import predict_step
+    from str2str_b200.sampler import ForwardBackwardSampler, InferenceConfig
+
+    L = 24
+    net = make_net(params, 1, 1)
+    cfg = InferenceConfig(delta_min=0.25, delta_max=0.5, delta_step=0.25, n_replica=3, replica_per_batch=2, num_timesteps=16, min_t=0.01)
+    smp = ForwardBackwardSampler(net, make_diffuser(), cfg)
+    feats = cuda(synthetic.make_features(1, L, seed=4, random_aatype=True))
+    q, x = synthetic.make_backbone(L, seed=4)
+    a, b, c, d = q.unbind(-1)
+    R = torch.stack([a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c), 2 * (b * c + a * d), a * a - b * b + c * c - d * d,
+                     2 * (c * d - a * b), 2 * (b * d - a * c), 2 * (c * d + a * b), a * a - b * b - c * c + d * d], -1).reshape(L, 3, 3)
+    M = torch.zeros(L, 4, 4)
+    M[:, :3, :3], M[:, :3, 3], M[:, 3, 3] = R, x, 1
+    feats["rigidgroups_gt_frames"] = M[None, :, None].repeat(1, 1, 8, 1, 1).cuda()
+    feats["chain_index"] = torch.zeros(1, L, dtype=torch.long).cuda()
+    feats["residue_index"] = (torch.arange(L)[None] + 1).cuda()
+    feats["accession_code"] = ["toy"]
+    out = predict_step(smp, feats, output_dir=str(tmp_path))
+    assert out == os.path.join(str(tmp_path), "all_delta")
+    for dname in ("0.25", "0.5"):
+        txt = open(os.path.join(str(tmp_path), dname, "toy.pdb")).read()
+        assert txt.count("MODEL") == 3 and txt.count("ENDMDL") == 3 and txt.endswith("END")
+        assert all(len(ln) == 80 for ln in txt.split("\n")[:-1])
+    merged = open(os.path.join(out, "toy.pdb")).read()
+    assert merged.count("MODEL") == 6 and merged.count("ENDMDL") == 6 and merged.endswith("END".ljust(80) + "\n")
