@@ -428,7 +428,10 @@ void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, c
   a.z_out = z_out; a.wimg = c->ee_wimg;
   // the tcgen05 kernels work on 128-row tiles of one (b, i): chain lengths that are not a multiple of 128 take the
   // SIMT kernels (same inputs, same rounding points)
-  if (c->opt_pair >= 1 && L % 128 == 0) edge_embed_tc(a, st); else edge_embed_simt(a, st);
+  static const int ee_gen = [] { const char* e = getenv("S2S_EE_GEN"); return e ? atoi(e) : 2; }();  // 1: first-generation kernel (A/B)
+  if (c->opt_pair >= 1 && L % 128 == 0) {
+    if (c->opt_pair == 2 || ee_gen == 1) edge_embed_tc(a, st); else edge_embed_tc2(a, st);
+  } else edge_embed_simt(a, st);
 }
 
 // InvariantPointAttention.forward of block blk -> out (linear_out result; not yet masked)

@@ -21,7 +21,8 @@ constexpr int G_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (two per
 constexpr int G_SMEM_RING = 12 * TILE_BYTES;  // 192 KiB of operand blocks: 6 stages x 2 blocks, or 3 stages x 4 blocks
 constexpr int G_OFF_BAR = G_SMEM_RING;
 constexpr int G_OFF_BIAS = G_OFF_BAR + 32 * 8 + 16;  // per-epilogue-warp bias slice of the current tile, [8][64] fp32
-constexpr int G_SMEM = G_OFF_BIAS + 8 * 128 * 4;
+constexpr int G_OFF_XP = G_OFF_BIAS + 8 * 64 * 4;    // per-epilogue-warp 32 x 32 fp32 transposition buffer (see the epilogue)
+constexpr int G_SMEM = G_OFF_XP + 8 * 32 * 32 * 4;   // 231 696 B of the 232 448 B a CTA can have
 
 struct TcKernelArgs {
   int a_cb, a_ch, a_rb, a_rh;  // A box coordinates: col = ib*a_cb + ih*a_ch + kb*64, row = ib*a_rb + ih*a_rh + m0
@@ -39,10 +40,15 @@ struct TcKernelArgs {
   // second K segment (passes == 1 only): K2 more reduction columns fetched through the mAl / mBl maps
   int K2, a2_cb, a2_ch, a2_rb, a2_rh, b2_cb, b2_ch, b2_rb, b2_rh;
   long bias_sb, bias_sh;  // batch strides of `bias` (0: one bias vector for every batch)
-  int epi_warps;          // 4 or 8 epilogue warps (blockDim = 64 + 32 * epi_warps)
+  int coalesced;          // 1: outputs / residual go through the per-warp transposition buffer (all pitches and N % 4 == 0)
   int b_mn;               // B operand is MN-major ([K][N] source), see TcGemm
 };
 
+// EPI >= 0: coalesced epilogue specialised at compile time on what leaves the kernel (bit 0: fp32 C, 1: bf16 hi image,
+// 2: bf16 lo image, 3: residual added) — the generic epilogue spent ~800 instructions per 32 x 32 chunk on option
+// predicates and 64-bit address arithmetic (ncu: issue-bound at 44 % of the slots with 2.5 warps per scheduler).
+// EPI < 0: generic row-layout epilogue (ragged N, unaligned pitches, transposed v output).
+template <int EPI>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, TcKernelArgs a) {
@@ -66,7 +72,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 32 * a.epi_warps);
+      mbar_init(&acc_empty[s], 32 * 8);
     }
     fence_barrier_init();
   }
@@ -162,8 +168,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     }
   } else {
     const int q = warp & 3, r = q * 32 + lane, hf = (warp - 2) >> 2;
-    float* bias_s = reinterpret_cast<float*>(smem + G_OFF_BIAS) + (warp - 2) * 128;
-    const int cw = a.epi_warps == 8 ? 64 : 128;  // columns of a tile per epilogue warp
+    float* bias_s = reinterpret_cast<float*>(smem + G_OFF_BIAS) + (warp - 2) * 64;
+    // Coalescing: tcgen05.ld hands every thread one accumulator ROW, so storing from that layout makes each 16-byte store
+    // of a warp touch 32 different 128-byte lines (ncu: 32 L1 tag requests / wavefronts per STG.128, and the LSU data pipe,
+    // not the tensor pipe, bounded the node-track GEMMs).  The finished 32 x 32 chunk is therefore turned through shared
+    // memory (16-byte chunks XOR-swizzled by row: conflict-free both ways) and leaves as rows of 128 contiguous bytes.
+    float* xp = reinterpret_cast<float*>(smem + G_OFF_XP) + (warp - 2) * 1024;
+    constexpr int cw = 64;  // columns of a tile per epilogue warp
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % NT, mt = (tile / NT) % MT, bz = tile / (NT * MT);
@@ -181,14 +192,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         // chunk loop queues behind the previous chunk's scattered stores and its latency is fully exposed (ncu: the
         // dependent FADD was the top long-scoreboard stall of the kernel).
         const int nb0 = nt * 128 + hf * cw + lane;
-        float bv[4];
+        float bv[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bv[u] = (u * 32 < cw && nb0 + u * 32 < a.N) ? __ldg(bias + nb0 + u * 32) : 0.f;
+        for (int u = 0; u < 2; ++u) bv[u] = (nb0 + u * 32 < a.N) ? __ldg(bias + nb0 + u * 32) : 0.f;
         __syncwarp();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bias_s[u * 32 + lane] = bv[u];
+        for (int u = 0; u < 2; ++u) bias_s[u * 32 + lane] = bv[u];
         __syncwarp();
       }
+      // Residual values of a chunk are fetched (in the coalesced layout: lane -> row it*4 + lane/8, columns 4*(lane%8)..+3)
+      // before the accumulator wait / while the previous chunk drains, ahead of any store of this tile: `res` may alias `C`,
+      // so loads placed after a store could not be hoisted by the compiler and each would expose a full L2 round trip.
+      constexpr bool kC = EPI >= 0 && (EPI & 1), kHi = EPI >= 0 && (EPI & 2), kLo = EPI >= 0 && (EPI & 4), kRes = EPI >= 0 && (EPI & 8);
+      const long boff = ib * a.sCb + ih * a.sCh;
+      const int xj = lane & 7;
+      const long row0 = (long)mt * TM + q * 32 + (lane >> 3);  // first of the 8 rows (stride 4) this lane stores
+      float4 rv[8];
+      auto fetch_res = [&](int c0) {
+        const int n = nt * 128 + c0 + xj * 4;
+        const float* rp = a.res + boff + row0 * a.ldres + n;
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8, rp += 4 * a.ldres)
+          rv[i8] = (row0 + 4 * i8 < a.M && n < a.N) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if constexpr (kRes) fetch_res(hf * cw);
       mbar_wait(&acc_full[ab], aph);
       tc_fence_after();
       const uint32_t taddr = tmem + ab * 128 + ((uint32_t)(q * 32) << 16);
@@ -198,11 +225,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         if (n0 >= a.N) break;  // warp-uniform
         float v[32];  // static indexing only below: stays in registers
         tmem_ld32(taddr + c0, v);
-        if (!row_ok) continue;
+        if (EPI < 0 && !row_ok) continue;
         const bool full = n0 + 32 <= a.N;
         const bool vec_ok = full && (a.ldres & 3) == 0;
+        if (pre != 1.f) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] *= pre;
+          for (int e = 0; e < 32; ++e) v[e] *= pre;
+        }
         if (bias) {
           const float* bs = bias_s + (c0 - hf * cw);
 #pragma unroll
@@ -215,8 +244,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
         }
+        if (a.row_post) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] *= post;
+          for (int e = 0; e < 32; ++e) v[e] *= post;
+        }
+        if constexpr (EPI >= 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(xp + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          const int n = n0 + xj * 4;
+          const bool col_ok = n < a.N;  // N % 4 == 0: a group of 4 columns is inside or outside as a whole
+          const float* xr = xp + (lane >> 3) * 32;
+          float* cp = kC ? a.C + boff + row0 * a.ldc + n : nullptr;
+          bf16* hp = kHi ? a.out_hi + boff + row0 * a.ldo + n : nullptr;
+          bf16* lp = kLo ? a.out_lo + boff + row0 * a.ldo + n : nullptr;
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            // row = i8*4 + lane/8, so row & 7 = ((i8 & 1) << 2) | (lane >> 3): the swizzle term is known per lane
+            float4 x = *reinterpret_cast<const float4*>(xr + i8 * 128 + ((xj ^ (((i8 & 1) << 2) | (lane >> 3))) << 2));
+            if constexpr (kRes) { x.x += rv[i8].x; x.y += rv[i8].y; x.z += rv[i8].z; x.w += rv[i8].w; }
+            if (col_ok && row0 + 4 * i8 < a.M) {
+              if constexpr (kC) *reinterpret_cast<float4*>(cp) = x;
+              if constexpr (kHi) *reinterpret_cast<uint2*>(hp) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+              if constexpr (kLo)
+                *reinterpret_cast<uint2*>(lp) = make_uint2(pack_bf16(x.x - bf16_round(x.x), x.y - bf16_round(x.y)),
+                                                          pack_bf16(x.z - bf16_round(x.z), x.w - bf16_round(x.w)));
+            }
+            if constexpr (kC) cp += 4 * a.ldc;
+            if constexpr (kHi) hp += 4 * a.ldo;
+            if constexpr (kLo) lp += 4 * a.ldo;
+          }
+          __syncwarp();
+          if constexpr (kRes) { if (c0 + 32 < hf * cw + cw) fetch_res(c0 + 32); }
+          continue;
+        }
         if (rrow) {
           if (vec_ok) {
 #pragma unroll
@@ -374,9 +436,9 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   k.K2 = g.K2; k.a2_cb = g.a2_cb; k.a2_ch = g.a2_ch; k.a2_rb = g.a2_rb; k.a2_rh = g.a2_rh;
   k.b2_cb = g.b2_cb; k.b2_ch = g.b2_ch; k.b2_rb = g.b2_rb; k.b2_rh = g.b2_rh;
   k.bias_sb = g.bias_sb; k.bias_sh = g.bias_sh;
-  k.epi_warps = 8;
   k.b_mn = g.b_mn;
-  if (const char* e = getenv("S2S_GEMM_EPI")) k.epi_warps = atoi(e) == 4 ? 4 : 8;  // timing experiments only
+  k.coalesced = g.N % 4 == 0 && g.ldc % 4 == 0 && g.ldres % 4 == 0 && g.ldo % 4 == 0 && g.sCb % 4 == 0 && g.sCh % 4 == 0 && !g.out_vt;
+  if (const char* e = getenv("S2S_GEMM_COALESCED")) k.coalesced = k.coalesced && atoi(e) != 0;  // A/B timing only
   k.a_cb = g.a_cb; k.a_ch = g.a_ch; k.a_rb = g.a_rb; k.a_rh = g.a_rh;
   k.b_cb = g.b_cb; k.b_ch = g.b_ch; k.b_rb = g.b_rb; k.b_rh = g.b_rh;
   k.M = g.M; k.N = g.N; k.K = g.K; k.nb = g.nb; k.nh = g.nh; k.passes = g.passes; k.relu = g.relu; k.vt_L = g.vt_L;
@@ -391,15 +453,34 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
     if (d & 4) k.C = nullptr;
     k.dbg = d;
   }
-  static bool configured = false;
-  const int smem = G_SMEM + 1024;
-  if (!configured) {
-    S2S_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  const int smem = G_SMEM;  // the kernel's extern array is declared __align__(1024) and checks it
   const int tiles = g.nb * g.nh * ceil_div(g.M, TM) * ceil_div(g.N, 128);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
   S2S_PROF(g_profile_on ? prof_intern("gemm_tc M" + std::to_string(g.M) + " N" + std::to_string(g.N) +  " K" + std::to_string(g.K + g.K2) + " p" + std::to_string(g.passes) + " b" + std::to_string(g.nb * g.nh)) : "gemm_tc", st);
-  gemm_tc_kernel<<<tiles < sm_count() ? tiles : sm_count(), 64 + 32 * k.epi_warps, smem, st>>>(mAh, mAl, mBh, mBl, k);
+  int epi = -1;
+  if (k.coalesced) {
+    epi = (k.C ? 1 : 0) | (k.out_hi ? 2 : 0) | (k.out_lo ? 4 : 0) | (k.res ? 8 : 0);
+    S2S_CHECK(!(epi & 4) || (epi & 2), "gemm_tc: a lo image needs a hi image");
+  }
+  static bool configured[17] = {};  // per instantiation (index epi + 1): every gemm_tc_kernel<EPI> has the same pointer type
+  auto launch = [&](auto kern) {
+    if (!configured[epi + 1]) {
+      S2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured[epi + 1] = true;
+    }
+    kern<<<grid, G_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, k);
+  };
+  switch (epi) {
+    case 1: launch(gemm_tc_kernel<1>); break;
+    case 2: launch(gemm_tc_kernel<2>); break;
+    case 3: launch(gemm_tc_kernel<3>); break;
+    case 6: launch(gemm_tc_kernel<6>); break;
+    case 7: launch(gemm_tc_kernel<7>); break;
+    case 9: launch(gemm_tc_kernel<9>); break;
+    case 11: launch(gemm_tc_kernel<11>); break;
+    case 15: launch(gemm_tc_kernel<15>); break;
+    default: epi = -1; launch(gemm_tc_kernel<-1>); break;
+  }
   S2S_LAUNCH_CHECK();
 }
 

@@ -93,7 +93,8 @@ struct EdgeEmbedArgs {
   const bf16* wimg = nullptr;  // tcgen05 path: pre-swizzled weight blocks (build_ee_wimg)
 };
 void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st);
-void edge_embed_tc(const EdgeEmbedArgs& a, cudaStream_t st);
+void edge_embed_tc(const EdgeEmbedArgs& a, cudaStream_t st);   // first generation (lock-step stations), pair_kernels = 2
+void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st);  // second generation (pipelined stations), pair_tc4.cu
 
 struct EdgeTransitionArgs {
   int B, L;
