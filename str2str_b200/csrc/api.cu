@@ -125,6 +125,7 @@ struct s2s_ctx {
   EtW et[N_BLK - 1];
   bf16 *ee_W2, *ee_W3, *ee_W2t, *ee_W3t, *ee_wimg;
   float* ee_Wd;
+  float* ee_vec;  // [b2 | b3 | ln_w | ln_b] packed (4 x 128): one copy into the pipelined embedder's constant bank per call
   // workspace
   Slab ws;
   int cap_B = 0, cap_L = 0, d_min = 0, n_off = 0;
@@ -312,6 +313,9 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
     prep_t_f32(W1, 120, 128, 98, N_BINS, c->ee_Wd, st);
     c->ee_wimg = c->wslab.take<bf16>(ee_wimg_elems());
     build_ee_wimg(W2, W3, c->ee_wimg, st);
+    c->ee_vec = c->wslab.take<float>(4 * 128);
+    const char* vn[4] = {"embedder.edge_embed.2.bias", "embedder.edge_embed.4.bias", "embedder.edge_embed.5.weight", "embedder.edge_embed.5.bias"};
+    for (int v = 0; v < 4; ++v) S2S_CUDA(cudaMemcpyAsync(c->ee_vec + v * 128, c->P(vn[v]), 128 * 4, cudaMemcpyDeviceToDevice, st));
   }
   // bf16 hi/lo images of every matrix the tensor-core node track multiplies by
   c->wsplit.clear();
@@ -425,7 +429,7 @@ void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, c
   a.sc_ca = sc_ca; a.ridx = ridx; a.mask = rmask;
   a.W2 = c->ee_W2; a.W3 = c->ee_W3; a.W2t = c->ee_W2t; a.W3t = c->ee_W3t;
   a.b2 = c->P(ee + "2.bias"); a.b3 = c->P(ee + "4.bias"); a.ln_w = c->P(ee + "5.weight"); a.ln_b = c->P(ee + "5.bias");
-  a.z_out = z_out; a.wimg = c->ee_wimg;
+  a.z_out = z_out; a.wimg = c->ee_wimg; a.vec4 = c->ee_vec;
   // the tcgen05 kernels work on 128-row tiles of one (b, i): chain lengths that are not a multiple of 128 take the
   // SIMT kernels (same inputs, same rounding points)
   static const int ee_gen = [] { const char* e = getenv("S2S_EE_GEN"); return e ? atoi(e) : 2; }();  // 1: first-generation kernel (A/B)

@@ -5,14 +5,21 @@
 // kernel sits at ~17 % of either roofline (1.16 ms at B = 64, L = 256: 1.07 GB written, 0.27 TFLOP).  Here the steps are
 // stations of a pipeline, each owned by its own warps and each working on a DIFFERENT tile at any moment:
 //
-//   G  (8 warps)  layer 1 by table lookups for tile t+2  -> A1[stage]  (bf16, K-major SWIZZLE_128B, 2 stages)
+//   G  (7 warps)  layer 1 by table lookups for tile t+2  -> A1[stage]  (bf16, K-major SWIZZLE_128B, 2 stages)
 //   M  (1 warp)   tcgen05.mma  layer 2 of tile t+1 (A1 x W2 -> acc2[stage]), layer 3 of tile t (A2 x W3 -> acc3[stage])
 //   E2 (4 warps)  acc2 -> + b2, ReLU -> A2[stage]                                (2 stages)
 //   E3 (4 warps)  acc3 -> + b3, LayerNorm (two-pass, re-reading tensor memory), mask -> z (bf16) in HBM
 //
 // One persistent CTA per SM (tiles strided by the grid, so the SMs write neighbouring tiles at any moment); the four
 // accumulators fill the 512 columns of tensor memory; W2 / W3 stay resident in shared memory; stations hand tiles over
-// through mbarriers only.  Same arithmetic and rounding points as the first generation (and as pair_simt.cu).
+// through mbarriers only.  Same arithmetic and rounding points as the first generation (and as pair_simt.cu), except
+// that the LayerNorm statistics are taken in one shifted pass (sum and sum of squares of y - y_0).
+//
+// What bounded the first cut of this pipeline (ncu, profiles/r01c_ncu_edge_embed.txt): the LSU data pipe at 76 % of its
+// wavefront rate, not latency.  Row-per-thread 16-byte global stores cost 32 wavefronts each (32 different 128-byte
+// lines), and every warp-uniform shared-memory read of a bias / LayerNorm parameter costs 2.  So the output rows are
+// turned through a swizzled shared-memory buffer and leave as 512-byte contiguous pieces, and b2 / b3 / ln_w / ln_b sit
+// in the constant bank where they are instruction operands rather than loads.
 #include "s2s_internal.cuh"
 #include "tc_common.cuh"
 
@@ -22,16 +29,50 @@ using namespace tc;
 
 namespace {
 
-constexpr int P_G_WARPS = 8;
+constexpr int P_G_WARPS = 7;  // 16 warps in all: 512 threads keep 128 registers per thread (544 threads are capped at 96 and spill)
 constexpr int P_THREADS = 32 * (1 + P_G_WARPS + 4 + 4);
 constexpr int P_WD_PITCH = C_Z + 4;
 constexpr int P_OFF_A1 = 0;                    // 2 stages x 2 K-blocks
-constexpr int P_OFF_A2 = 4 * TILE_BYTES;       // 2 stages x 2 K-blocks
+constexpr int P_OFF_A2 = 4 * TILE_BYTES;       // 1 stage x 2 K-blocks (E2 idles two thirds of the time: no second stage needed)
+constexpr int P_OFF_OUT = 6 * TILE_BYTES;      // E3 output staging: 4 warps x [32 rows x 256 B], 16-byte chunks swizzled by row
 constexpr int P_OFF_W = 8 * TILE_BYTES;        // W2 k0, W2 k1, W3 k0, W3 k1
 constexpr int P_OFF_VEC = 12 * TILE_BYTES;
-constexpr int P_VEC_FLOATS = 4 * C_Z + N_BINS * P_WD_PITCH + 32;  // b2, b3, ln_w, ln_b, Wd, bin edges
+constexpr int P_VEC_FLOATS = N_BINS * P_WD_PITCH + 32;  // Wd, bin edges
 constexpr int P_OFF_BAR = P_OFF_VEC + P_VEC_FLOATS * 4;
 constexpr int P_SMEM = P_OFF_BAR + 20 * 8 + 16;
+
+__constant__ float c_ee[4][C_Z];  // b2, b3, ln_w, ln_b (copied from EdgeEmbedArgs::vec4 in stream order before every launch)
+
+// Waits of the stations that idle by design (E2, E3, M) back off instead of spinning: a spinning warp takes issue slots
+// from the G warps that share its scheduler (ncu: ~2500 try_wait iterations per tile, `not selected` stalls on G).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* b, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(40);
+  }
+}
+
+// pair_distogram_bin (s2s_internal.cuh) without the 22-step scan: the edges are an arithmetic progression, so a guess from
+// the quotient is off by at most one either way; the two comparisons that settle it use the table's own fp32 edges, so the
+// strict inequalities of geo_utils.py:44-56 are decided exactly as in the scan.
+__device__ __forceinline__ int pair_distogram_bin_fast(const float* a, const float* b, const float* lower, float inv_step) {
+  const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  int k = (int)fminf(fmaxf((d - lower[0]) * inv_step, 0.f), (float)(N_BINS - 1));
+  if (!(d > lower[k])) --k;
+  else if (k < N_BINS - 1 && d > lower[k + 1]) ++k;
+  if (k < 0) return -1;
+  const float upper = (k < N_BINS - 1) ? lower[k + 1] : 1e8f;
+  return d < upper ? k : -1;
+}
 
 struct EePipeArgs {
   EdgeEmbedArgs e;
@@ -42,11 +83,7 @@ struct EePipeArgs {
 __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
-  float* b2_s = reinterpret_cast<float*>(smem + P_OFF_VEC);
-  float* b3_s = b2_s + C_Z;
-  float* lnw_s = b3_s + C_Z;
-  float* lnb_s = lnw_s + C_Z;
-  float* wd_s = lnb_s + C_Z;
+  float* wd_s = reinterpret_cast<float*>(smem + P_OFF_VEC);
   float* edge_s = wd_s + N_BINS * P_WD_PITCH;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_OFF_BAR);
   uint64_t* w_full = bars;
@@ -69,20 +106,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
       mbar_init(&a1_empty[s], 1);
       mbar_init(&acc2_full[s], 1);
       mbar_init(&acc2_empty[s], 128);
-      mbar_init(&a2_full[s], 128);
-      mbar_init(&a2_empty[s], 1);
       mbar_init(&acc3_full[s], 1);
       mbar_init(&acc3_empty[s], 128);
     }
+    mbar_init(&a2_full[0], 128);
+    mbar_init(&a2_empty[0], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  for (int c = threadIdx.x; c < C_Z; c += blockDim.x) {
-    b2_s[c] = e.b2[c];
-    b3_s[c] = e.b3[c];
-    lnw_s[c] = e.ln_w[c];
-    lnb_s[c] = e.ln_b[c];
-  }
   for (int c = threadIdx.x; c < N_BINS * C_Z; c += blockDim.x) wd_s[(c / C_Z) * P_WD_PITCH + (c % C_Z)] = e.Wd[c];
   if (threadIdx.x < N_BINS) edge_s[threadIdx.x] = e.bin_lower[threadIdx.x];
   tc_fence_before();
@@ -108,8 +139,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
     for (int k = 0; k <= n_local; ++k) {
       if (k < n_local) {
         const uint32_t s = k & 1, ph = (k >> 1) & 1;
-        mbar_wait(&a1_full[s], ph);
-        mbar_wait(&acc2_empty[s], ph ^ 1);
+        mbar_wait_backoff(&a1_full[s], ph);
+        mbar_wait_backoff(&acc2_empty[s], ph ^ 1);
         tc_fence_after();
         if (elect_one()) {
           kblock_ss(tmem + s * 128, a1 + s * 2 * BLK, wb, IDESC, true);
@@ -122,39 +153,41 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
       if (k >= 1) {
         const int j = k - 1;
         const uint32_t s = j & 1, ph = (j >> 1) & 1;
-        mbar_wait(&a2_full[s], ph);
-        mbar_wait(&acc3_empty[s], ph ^ 1);
+        mbar_wait_backoff(&a2_full[0], j & 1);
+        mbar_wait_backoff(&acc3_empty[s], ph ^ 1);
         tc_fence_after();
         if (elect_one()) {
-          kblock_ss(tmem + 256 + s * 128, a2 + s * 2 * BLK, wb + 2 * BLK, IDESC, true);
-          kblock_ss(tmem + 256 + s * 128, a2 + s * 2 * BLK + BLK, wb + 3 * BLK, IDESC, false);
-          umma_commit(&a2_empty[s]);
+          kblock_ss(tmem + 256 + s * 128, a2, wb + 2 * BLK, IDESC, true);
+          kblock_ss(tmem + 256 + s * 128, a2 + BLK, wb + 3 * BLK, IDESC, false);
+          umma_commit(&a2_empty[0]);
           umma_commit(&acc3_full[s]);
         }
         __syncwarp();
       }
     }
   } else if (warp <= P_G_WARPS) {
-    // ---- G: layer 1 by table lookups.  Warp g owns rows g*16 .. g*16+15 of the tile; lanes first classify those rows
+    // ---- G: layer 1 by table lookups.  Warp g owns 18 consecutive rows of the tile (the last warp 20); lanes first classify those rows
     // (distogram bin, relative-position offset), then the warp walks the rows together so that every table row is one
     // coalesced 512-byte read (lane = 4 channels).
     const int g = warp - 1;
     const int c = lane * 4;
     unsigned char* const dst0 = smem + P_OFF_A1 + (c / KBLK) * TILE_BYTES;
+    const float inv_step = (float)(N_BINS - 1) / (edge_s[N_BINS - 1] - edge_s[0]);
     for (int k = 0; k < n_local; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
       const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
       const int b = bi / e.L;
-      const size_t bj0 = (size_t)b * e.L + j0 + g * 16;
-      const size_t bjl = bj0 + (lane & 15);
-      const int bin_l = pair_distogram_bin(e.sc_ca + (size_t)bi * 3, e.sc_ca + bjl * 3, edge_s);
+      const int r_begin = g * 18, r_cnt = g == P_G_WARPS - 1 ? TM - r_begin : 18;
+      const size_t bj0 = (size_t)b * e.L + j0 + r_begin;
+      const size_t bjl = bj0 + (lane < r_cnt ? lane : 0);
+      const int bin_l = pair_distogram_bin_fast(e.sc_ca + (size_t)bi * 3, e.sc_ca + bjl * 3, edge_s, inv_step);
       const int off_l = (int)(e.ridx[bi] - e.ridx[bjl]) - e.d_min;
       const float4 tiv = __ldg(reinterpret_cast<const float4*>(e.Ti + (size_t)bi * C_Z + c));
       const uint32_t s = k & 1, ph = (k >> 1) & 1;
       mbar_wait(&a1_empty[s], ph ^ 1);
       unsigned char* const dst = dst0 + s * 2 * TILE_BYTES;
-#pragma unroll 8
-      for (int r16 = 0; r16 < 16; ++r16) {
+#pragma unroll 6
+      for (int r16 = 0; r16 < r_cnt; ++r16) {
         const int bin = __shfl_sync(0xffffffffu, bin_l, r16);
         const int off = __shfl_sync(0xffffffffu, off_l, r16);
         const float4 tjv = __ldg(reinterpret_cast<const float4*>(e.Tj + (bj0 + r16) * C_Z + c));
@@ -164,7 +197,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
           const float4 wv = *reinterpret_cast<const float4*>(wd_s + bin * P_WD_PITCH + c);
           h.x += wv.x; h.y += wv.y; h.z += wv.z; h.w += wv.w;
         }
-        *reinterpret_cast<uint2*>(dst + sw128_offset(g * 16 + r16, c % KBLK)) =
+        *reinterpret_cast<uint2*>(dst + sw128_offset(r_begin + r16, c % KBLK)) =
             make_uint2(pack_bf16(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f)), pack_bf16(fmaxf(h.z, 0.f), fmaxf(h.w, 0.f)));
       }
       fence_proxy_async();
@@ -174,68 +207,69 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
     // ---- E2: acc2 -> + b2, ReLU -> A2 (this thread: row r of the tile, all 128 columns in two halves) ----
     const int q = warp & 3, r = q * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    unsigned char* const abuf = smem + P_OFF_A2;
     for (int k = 0; k < n_local; ++k) {
       const uint32_t s = k & 1, ph = (k >> 1) & 1;
-      mbar_wait(&acc2_full[s], ph);
-      mbar_wait(&a2_empty[s], ph ^ 1);
+      mbar_wait_backoff(&acc2_full[s], ph);
       tc_fence_after();
-      unsigned char* const abuf = smem + P_OFF_A2 + s * 2 * TILE_BYTES;
+      float v[64];
+      tmem_ld32_issue(lane_base + s * 128, v);
+      tmem_ld32_issue(lane_base + s * 128 + 32, v + 32);
+      tmem_wait_ld();
+      mbar_wait_backoff(&a2_empty[0], (k & 1) ^ 1);  // layer 3 of the previous tile has read A2
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        float v[64];
-        tmem_ld32_issue(lane_base + s * 128 + hf * 64, v);
-        tmem_ld32_issue(lane_base + s * 128 + hf * 64 + 32, v + 32);
-        tmem_wait_ld();
-        if (hf == 1) {  // both halves are in registers: the accumulator can take the next tile
-          tc_fence_before();
+        if (hf == 1) {
+          tmem_ld32_issue(lane_base + s * 128 + 64, v);
+          tmem_ld32_issue(lane_base + s * 128 + 96, v + 32);
+          tmem_wait_ld();
+          tc_fence_before();  // all of acc2[s] is in registers: it can take the tile after next
           mbar_arrive(&acc2_empty[s]);
         }
 #pragma unroll
         for (int gq = 0; gq < 8; ++gq) {
           float h[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) h[u] = fmaxf(v[gq * 8 + u] + b2_s[hf * 64 + gq * 8 + u], 0.f);
+          for (int u = 0; u < 8; ++u) h[u] = fmaxf(v[gq * 8 + u] + c_ee[0][hf * 64 + gq * 8 + u], 0.f);
           store8_sw128(abuf + hf * TILE_BYTES, r, gq * 8, h);
         }
       }
       fence_proxy_async();
-      mbar_arrive(&a2_full[s]);
+      mbar_arrive(&a2_full[0]);
     }
   } else {
-    // ---- E3: acc3 -> + b3, LayerNorm (exact two-pass; tensor memory is re-read instead of holding 128 values), mask, store
+    // ---- E3: acc3 -> + b3, LayerNorm, mask -> z.  Statistics in one pass over tensor memory (shifted by the row's first
+    // value: sum and sum of squares of y - y_0), the second pass normalises into the staging buffer, then the warp's
+    // 32 rows x 256 B leave as sixteen 512-byte contiguous stores.
     const int q = warp & 3, r = q * 32 + lane;
     const uint32_t lane_base = tmem + 256 + ((uint32_t)(q * 32) << 16);
+    unsigned char* const obuf = smem + P_OFF_OUT + q * (32 * 256);
     for (int k = 0; k < n_local; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
       const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
       const size_t bj = (size_t)(bi / e.L) * e.L + j0 + r;
       const float m = __ldg(e.mask + bi) * __ldg(e.mask + bj);
       const uint32_t s = k & 1, ph = (k >> 1) & 1;
-      mbar_wait(&acc3_full[s], ph);
+      mbar_wait_backoff(&acc3_full[s], ph);
       tc_fence_after();
       const uint32_t acc = lane_base + s * 128;
       float v[32];
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C_Z; c0 += 32) {
-        tmem_ld32(acc + c0, v);
+      float sum = 0.f, sq = 0.f, shift = 0.f;
 #pragma unroll
-        for (int u = 0; u < 32; ++u) sum += v[u] + b3_s[c0 + u];
-      }
-      const float mean = sum * (1.f / C_Z);
-      float sq = 0.f;
-#pragma unroll 1
       for (int c0 = 0; c0 < C_Z; c0 += 32) {
         tmem_ld32(acc + c0, v);
+        if (c0 == 0) shift = v[0] + c_ee[1][0];
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
-          const float d = v[u] + b3_s[c0 + u] - mean;
-          sq += d * d;
+          const float d = v[u] + c_ee[1][c0 + u] - shift;
+          sum += d;
+          sq = fmaf(d, d, sq);
         }
       }
-      const float rstd = rsqrtf(sq * (1.f / C_Z) + 1e-5f);
-      bf16* orow = e.z_out + ((size_t)tile * TM + r) * C_Z;
-#pragma unroll 1
+      const float dm = sum * (1.f / C_Z);                   // mean - shift
+      const float rstd = rsqrtf(fmaxf(sq * (1.f / C_Z) - dm * dm, 0.f) + 1e-5f);
+      const float off = shift + dm;                        // mean
+#pragma unroll
       for (int c0 = 0; c0 < C_Z; c0 += 32) {
         tmem_ld32(acc + c0, v);
         if (c0 == C_Z - 32) {  // last read of this accumulator
@@ -248,12 +282,25 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int cc = c0 + gq * 8 + u;
-            o[u] = ((v[gq * 8 + u] + b3_s[cc] - mean) * rstd * lnw_s[cc] + lnb_s[cc]) * m;
+            o[u] = fmaf((v[gq * 8 + u] + c_ee[1][cc] - off) * c_ee[2][cc], rstd, c_ee[3][cc]) * m;  // no per-tile-invariant subexpression to hoist (128 registers)
           }
-          *reinterpret_cast<uint4*>(orow + c0 + gq * 8) =
+          const int chunk = (c0 >> 3) + gq;                // 16-byte chunk 0..15 of this row
+          *reinterpret_cast<uint4*>(obuf + lane * 256 + ((chunk ^ (lane & 7)) << 4)) =
               make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
         }
       }
+      __syncwarp();
+      {
+        unsigned char* const gbase = reinterpret_cast<unsigned char*>(e.z_out + ((size_t)tile * TM + q * 32) * C_Z);
+        const int rr = lane >> 4, ch = lane & 15;
+#pragma unroll
+        for (int i16 = 0; i16 < 16; ++i16) {
+          const int row = i16 * 2 + rr;
+          const uint4 pk = *reinterpret_cast<const uint4*>(obuf + row * 256 + ((ch ^ (row & 7)) << 4));
+          *reinterpret_cast<uint4*>(gbase + row * 256 + ch * 16) = pk;
+        }
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -273,6 +320,8 @@ void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st) {
     S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
     configured = true;
   }
+  S2S_CHECK(a.vec4, "edge_embed_tc2: packed bias / LayerNorm vector missing");
+  S2S_CUDA(cudaMemcpyToSymbolAsync(c_ee, a.vec4, sizeof(float) * 4 * C_Z, 0, cudaMemcpyDeviceToDevice, st));
   S2S_PROF("edge_embed", st);
   const int cap = sm_count();
   edge_embed_pipe_kernel<<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);

@@ -12,37 +12,53 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         const float* __restrict__ rowscale, float* __restrict__ y,
                                                         int rows, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo) {
-  constexpr int PER = D / 32;
+  // one warp per row; a lane owns groups of 4 consecutive channels (16-byte loads and stores, 8-byte bf16 image stores)
+  constexpr int G4 = D / 4, PER = (G4 + 31) / 32;
   const int row = blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
-  float v[PER];
+  float4 v[PER];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = x[(long)row * D + c];
-    if (res) v[i] += res[(long)row * D + c];
-    s += v[i];
+    const int g = lane + 32 * i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < G4) {
+      v[i] = *reinterpret_cast<const float4*>(x + (long)row * D + g * 4);
+      if (res) {
+        const float4 r4 = *reinterpret_cast<const float4*>(res + (long)row * D + g * 4);
+        v[i].x += r4.x; v[i].y += r4.y; v[i].z += r4.z; v[i].w += r4.w;
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
   }
   const float mean = warp_sum(s) * (1.f / D);
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const float d = v[i] - mean;
-    q += d * d;
+    if (lane + 32 * i < G4) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
   const float sc = rowscale ? rowscale[row] : 1.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const int c = lane + 32 * i;
-    const float o = ((v[i] - mean) * rstd * w[c] + b[c]) * sc;
-    y[(long)row * D + c] = o;
-    if (y_hi) {  // split-bf16 image for a following tensor-core GEMM
-      const bf16 hi = __float2bfloat16_rn(o);
-      y_hi[(long)row * D + c] = hi;
-      y_lo[(long)row * D + c] = __float2bfloat16_rn(o - __bfloat162float(hi));
+    const int g = lane + 32 * i;
+    if (g < G4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + g * 4)), b4 = __ldg(reinterpret_cast<const float4*>(b + g * 4));
+      float4 o;
+      o.x = ((v[i].x - mean) * rstd * w4.x + b4.x) * sc;
+      o.y = ((v[i].y - mean) * rstd * w4.y + b4.y) * sc;
+      o.z = ((v[i].z - mean) * rstd * w4.z + b4.z) * sc;
+      o.w = ((v[i].w - mean) * rstd * w4.w + b4.w) * sc;
+      *reinterpret_cast<float4*>(y + (long)row * D + g * 4) = o;
+      if (y_hi) {  // split-bf16 image for a following tensor-core GEMM
+        *reinterpret_cast<uint2*>(y_hi + (long)row * D + g * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        *reinterpret_cast<uint2*>(y_lo + (long)row * D + g * 4) =
+            make_uint2(pack_bf16(o.x - bf16_round(o.x), o.y - bf16_round(o.y)), pack_bf16(o.z - bf16_round(o.z), o.w - bf16_round(o.w)));
+      }
     }
   }
 }

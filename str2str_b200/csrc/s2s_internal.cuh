@@ -91,6 +91,7 @@ struct EdgeEmbedArgs {
   const float *b2, *b3, *ln_w, *ln_b;
   bf16* z_out;             // [B,L,L,128]
   const bf16* wimg = nullptr;  // tcgen05 path: pre-swizzled weight blocks (build_ee_wimg)
+  const float* vec4 = nullptr; // [b2 | b3 | ln_w | ln_b] packed, device (pipelined kernel: copied into its constant bank)
 };
 void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st);
 void edge_embed_tc(const EdgeEmbedArgs& a, cudaStream_t st);   // first generation (lock-step stations), pair_kernels = 2
