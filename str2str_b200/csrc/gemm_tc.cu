@@ -131,14 +131,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     uint32_t cnt = 0, it = 0;
     const uint32_t ring = desc_lo_sw128(smem_u32(smem));
     constexpr uint32_t BLK = TILE_BYTES >> 4;
-    const uint32_t idesc = a.b_mn ? (IDESC | (1u << 16)) : IDESC;            // bit 16: B is MN-major
+    // dbg bits 64 / 128 (timing experiments only, results are garbage): issue every MMA as N = 256 / N = 64
+    const uint32_t idesc_n = (a.dbg & 64) ? make_idesc(128, 256) : (a.dbg & 128) ? make_idesc(128, 64) : IDESC;
+    const uint32_t idesc = a.b_mn ? (idesc_n | (1u << 16)) : idesc_n;        // bit 16: B is MN-major
     const uint32_t bmn_fix = ((uint32_t)(TILE_BYTES / 2) >> 4 << 16) - (1u << 16);  // LBO field 1 -> 512 (8 KB)
     const uint32_t stage_units = blocks_per_stage * BLK;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ab = it & 1, aph = (it >> 1) & 1;
       mbar_wait(&acc_empty[ab], aph ^ 1);
       tc_fence_after();
-      const uint32_t d = tmem + ab * 128;
+      const uint32_t d = (a.dbg & 64) ? tmem : tmem + ab * 128;
       for (int kb = 0; kb < KBT; ++kb, ++cnt) {
         const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
         mbar_wait(&s_full[s], ph);
@@ -219,6 +221,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
       mbar_wait(&acc_full[ab], aph);
       tc_fence_after();
       const uint32_t taddr = tmem + ab * 128 + ((uint32_t)(q * 32) << 16);
+      if constexpr (EPI >= 16) {
+        // bf16-only outputs (hi image, optionally lo; N % 64 == 0): the warp's 64 columns are packed to bf16 in the row layout
+        // and turned through shared memory as whole 128-byte rows, so every 16-byte store of a warp covers four complete lines
+        // (the 32-column fp32 route moves twice the bytes through shared memory and stores half lines).
+        const int n0 = nt * 128 + hf * cw;
+        if (n0 < a.N && !(a.dbg & 32)) {
+          float v[64];
+          tmem_ld32_issue(taddr + hf * cw, v);
+          tmem_ld32_issue(taddr + hf * cw + 32, v + 32);
+          tmem_wait_ld();
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);  // the accumulator is in registers: the MMA warp may refill it
+          if (pre != 1.f) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] *= pre;
+          }
+          if (bias) {
+#pragma unroll
+            for (int e = 0; e < 64; e += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias_s + e);
+              v[e] += bv.x; v[e + 1] += bv.y; v[e + 2] += bv.z; v[e + 3] += bv.w;
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (a.row_post) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] *= post;
+          }
+          uint32_t* xpu = reinterpret_cast<uint32_t*>(xp);
+          const long ooff = boff + row0 * a.ldo + n0 + xj * 8;
+#pragma unroll
+          for (int img = 0; img < ((EPI & 4) ? 2 : 1); ++img) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float x0 = v[8 * j + 2 * u], x1 = v[8 * j + 2 * u + 1];
+                pk[u] = img == 0 ? pack_bf16(x0, x1) : pack_bf16(x0 - bf16_round(x0), x1 - bf16_round(x1));
+              }
+              *reinterpret_cast<uint4*>(xpu + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            __syncwarp();
+            bf16* op = (img == 0 ? a.out_hi : a.out_lo) + ooff;
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8, op += 4 * a.ldo) {
+              const uint4 x = *reinterpret_cast<const uint4*>(xpu + (lane >> 3) * 32 + i8 * 128 + ((xj ^ (((i8 & 1) << 2) | (lane >> 3))) << 2));
+              if (row0 + 4 * i8 < a.M) *reinterpret_cast<uint4*>(op) = x;
+            }
+            __syncwarp();
+          }
+        } else {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = hf * cw; c0 < hf * cw + cw && !(a.dbg & 32); c0 += 32) {
         const int n0 = nt * 128 + c0;
@@ -390,6 +452,323 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
+// =====================================================================================================================
+// Panel GEMM: A resident in tensor memory (TS-mode MMAs), weights streamed.
+//
+// Why: with both operands in shared memory (SS mode) every tcgen05.mma of the kernel above costs ~210 cycles + 0.42 N
+// (measured, S2S_GEMM_DEBUG 40 / 104 / 168: MMA-only time 87 / 97 / 117 us for N = 64 / 128 / 256 at identical instruction
+// counts), i.e. a 128x128x16 MMA takes ~265 cycles against a 64-cycle tensor floor, and the node-track GEMMs — all
+// K <= 320 with 3 split-bf16 passes — were bound by that per-instruction cost, not by FLOPs, bytes or the epilogue.
+// The fused EdgeTransition kernel, whose A operand lives in tensor memory, issues the same MMAs at ~80 cycles.
+//
+// So for the non-batched GEMMs (C = act(A W^T + b), A [M, K] = activations): one CTA owns a 128-row panel of A, copies it
+// ONCE into tensor memory (TMA -> SW128 shared block -> registers -> tcgen05.st; hi and lo images) and then walks all N
+// output columns in chunks of <= 128, streaming only the weight blocks through the shared-memory ring.  A_hi serves two
+// of the three split-bf16 passes; A is read from L2 once per panel instead of once per 128 output columns.
+// Tensor memory: [A_hi | A_lo] (K/2 columns each) + two accumulator buffers (128 + 128, or 128 + 64 when K = 320 leaves
+// only 192 columns).  Roles: TMA producer warp, MMA warp, 8 epilogue warps of which the first four (one per TMEM lane
+// quarter) also stage A at the start of a panel.  Coalesced compile-time-specialised epilogue as above (EPI >= 0 only).
+struct PanelGeom {
+  int acol_lo;     // first TMEM column of A_lo (A_hi starts at column 0)
+  int acc0, acc1;  // first TMEM column of the two accumulator buffers
+  int w1;          // width of buffer 1 (buffer 0 is 128 wide)
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                  const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, TcKernelArgs a, PanelGeom pg) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
+  uint64_t* s_full = bars;          // [12]
+  uint64_t* s_empty = bars + 12;    // [12]
+  uint64_t* acc_full = bars + 24;   // [2]
+  uint64_t* acc_empty = bars + 26;  // [2]
+  uint64_t* a_ready = bars + 28;    // A of the current panel is in tensor memory
+  uint64_t* a_free = bars + 29;     // every MMA of the panel has completed: A may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int bps = a.passes == 3 ? 2 : 1;  // blocks per ring stage: (hi, lo) or hi
+  const int n_stages = 12 / bps;
+  const uint32_t stage_bytes = bps * TILE_BYTES;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 12; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 32 * 8);
+    }
+    mbar_init(a_ready, 128);
+    mbar_init(a_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int MT = (a.M + TM - 1) / TM, KB = a.K / KBLK;
+  // chunk ci of the whole CTA run uses accumulator buffer ci & 1; its width follows from the buffer and what is left of N
+  auto chunk_width = [&](uint32_t ci, int n_done) { return min((ci & 1) ? pg.w1 : 128, a.N - n_done); };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t cnt = 0, ci = 0;
+      for (int mt = blockIdx.x; mt < MT; mt += gridDim.x) {
+        for (int kb = 0; kb < KB; ++kb, ++cnt) {  // the panel of A (consumed by the staging warps)
+          const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
+          mbar_wait(&s_empty[s], ph ^ 1);
+          mbar_expect_tx(&s_full[s], stage_bytes);
+          unsigned char* st = smem + s * stage_bytes;
+          tma_load_2d(st, &mAh, kb * KBLK, mt * TM, &s_full[s]);
+          if (bps == 2) tma_load_2d(st + TILE_BYTES, &mAl, kb * KBLK, mt * TM, &s_full[s]);
+        }
+        for (int n = 0; n < a.N; ++ci) {  // weight blocks: 128 rows of W from row n (rows past N read as zeros), one K block
+          const int w = chunk_width(ci, n);
+          for (int kb = 0; kb < KB; ++kb, ++cnt) {
+            const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
+            mbar_wait(&s_empty[s], ph ^ 1);
+            mbar_expect_tx(&s_full[s], stage_bytes);
+            unsigned char* st = smem + s * stage_bytes;
+            tma_load_2d(st, &mBh, kb * KBLK, n, &s_full[s]);
+            if (bps == 2) tma_load_2d(st + TILE_BYTES, &mBl, kb * KBLK, n, &s_full[s]);
+          }
+          n += w;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // MMA issuer (whole warp converged, one elected lane issues): D[acc] += A[tmem] * W_blk^T
+    uint32_t cnt = 0, ci = 0, pi = 0;
+    const uint32_t ring = desc_lo_sw128(smem_u32(smem));
+    constexpr uint32_t BLK = TILE_BYTES >> 4;
+    const uint32_t stage_units = bps * BLK;
+    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++pi) {
+      cnt += KB;  // the ring stages that carried A
+      mbar_wait(a_ready, pi & 1);
+      tc_fence_after();
+      for (int n = 0; n < a.N; ++ci) {
+        const int w = chunk_width(ci, n);
+        const uint32_t ab = ci & 1, aph = (ci >> 1) & 1;
+        mbar_wait(&acc_empty[ab], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + (ab ? pg.acc1 : pg.acc0);
+        const uint32_t idesc = make_idesc(128, (w + 15) & ~15);
+        for (int kb = 0; kb < KB; ++kb, ++cnt) {
+          const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
+          mbar_wait(&s_full[s], ph);
+          tc_fence_after();
+          const uint32_t bh = ring + s * stage_units;
+          const uint32_t ah = tmem + kb * 32, al = tmem + pg.acol_lo + kb * 32;
+          if (elect_one()) {
+            if (!(a.dbg & 16)) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (kb | k) umma_ts<true>(d, ah + 8 * k, bh + 2 * k, idesc); else umma_ts<false>(d, ah + 8 * k, bh + 2 * k, idesc);
+                if (bps == 2) {
+                  umma_ts<true>(d, al + 8 * k, bh + 2 * k, idesc);
+                  umma_ts<true>(d, ah + 8 * k, bh + BLK + 2 * k, idesc);
+                }
+              }
+            }
+            umma_commit(&s_empty[s]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(&acc_full[ab]);
+        __syncwarp();
+        n += w;
+      }
+      if (elect_one()) umma_commit(a_free);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane, hf = (warp - 2) >> 2;
+    float* bias_s = reinterpret_cast<float*>(smem + G_OFF_BIAS) + (warp - 2) * 64;
+    float* xp = reinterpret_cast<float*>(smem + G_OFF_XP) + (warp - 2) * 1024;
+    uint32_t* xpu = reinterpret_cast<uint32_t*>(xp);
+    constexpr bool kC = (EPI & 1) != 0, kHi = (EPI & 2) != 0, kLo = (EPI & 4) != 0, kRes = (EPI & 8) != 0, kWide = (EPI & 16) != 0;
+    const int xj = lane & 7;
+    uint32_t cnt = 0, ci = 0, pi = 0;
+    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++pi) {
+      if (hf == 0) {
+        // ---- stage the panel of A into tensor memory: this thread copies row r of every K block (128 bytes = 32 columns)
+        if (pi > 0) mbar_wait(a_free, (pi - 1) & 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb, ++cnt) {
+          const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
+          mbar_wait(&s_full[s], ph);
+          const unsigned char* st = smem + s * stage_bytes;
+          for (int img = 0; img < bps; ++img) {
+            uint32_t pk[32];
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const uint4 x = *reinterpret_cast<const uint4*>(st + img * TILE_BYTES + sw128_offset(r, c8 * 8));
+              pk[4 * c8] = x.x; pk[4 * c8 + 1] = x.y; pk[4 * c8 + 2] = x.z; pk[4 * c8 + 3] = x.w;
+            }
+            tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + (img ? pg.acol_lo : 0) + kb * 32, pk);
+          }
+          named_bar_sync(1, 128);  // all four staging warps have read the blocks
+          if (threadIdx.x == 64) mbar_arrive(&s_empty[s]);
+        }
+        tc_fence_before();
+        mbar_arrive(a_ready);
+      }
+      const int m = mt * TM + r;
+      const bool row_ok = m < a.M;
+      const float pre = (row_ok && a.row_pre) ? a.row_pre[m] * a.alpha : a.alpha;
+      const float post = (row_ok && a.row_post) ? a.row_post[m] : 1.f;
+      const long row0 = (long)mt * TM + q * 32 + (lane >> 3);  // first of the 8 rows (stride 4) this lane stores
+      for (int n = 0; n < a.N; ++ci) {
+        const int w = chunk_width(ci, n);
+        const uint32_t ab = ci & 1, aph = (ci >> 1) & 1;
+        const int nw0 = n + hf * 64;                 // first column of this warp's 64-column share of the chunk
+        const bool has_cols = hf * 64 < w;           // warp-uniform
+        if (has_cols && a.bias) {
+          float bv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) bv[u] = (nw0 + u * 32 + lane < a.N) ? __ldg(a.bias + nw0 + u * 32 + lane) : 0.f;
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) bias_s[u * 32 + lane] = bv[u];
+          __syncwarp();
+        }
+        float4 rv[8];
+        auto fetch_res = [&](int nc) {  // residual of the 32-column sub-chunk starting at column nc, coalesced layout
+          const int nn = nc + xj * 4;
+          const float* rp = a.res + row0 * a.ldres + nn;
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8, rp += 4 * a.ldres)
+            rv[i8] = (row0 + 4 * i8 < a.M && nn < a.N) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if constexpr (kRes) { if (has_cols) fetch_res(nw0); }
+        mbar_wait(&acc_full[ab], aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem + (ab ? pg.acc1 : pg.acc0) + hf * 64 + ((uint32_t)(q * 32) << 16);
+        if (!has_cols || (a.dbg & 32)) {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
+        } else if constexpr (kWide) {
+          float v[64];
+          tmem_ld32_issue(taddr, v);
+          tmem_ld32_issue(taddr + 32, v + 32);
+          tmem_wait_ld();
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
+          if (pre != 1.f) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] *= pre;
+          }
+          if (a.bias) {
+#pragma unroll
+            for (int e = 0; e < 64; e += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias_s + e);
+              v[e] += bv.x; v[e + 1] += bv.y; v[e + 2] += bv.z; v[e + 3] += bv.w;
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (a.row_post) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] *= post;
+          }
+          const long ooff = row0 * a.ldo + nw0 + xj * 8;
+#pragma unroll
+          for (int img = 0; img < (kLo ? 2 : 1); ++img) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float x0 = v[8 * j + 2 * u], x1 = v[8 * j + 2 * u + 1];
+                pk[u] = img == 0 ? pack_bf16(x0, x1) : pack_bf16(x0 - bf16_round(x0), x1 - bf16_round(x1));
+              }
+              *reinterpret_cast<uint4*>(xpu + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            __syncwarp();
+            bf16* op = (img == 0 ? a.out_hi : a.out_lo) + ooff;
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8, op += 4 * a.ldo) {
+              const uint4 x = *reinterpret_cast<const uint4*>(xpu + (lane >> 3) * 32 + i8 * 128 + ((xj ^ (((i8 & 1) << 2) | (lane >> 3))) << 2));
+              if (row0 + 4 * i8 < a.M) *reinterpret_cast<uint4*>(op) = x;
+            }
+            __syncwarp();
+          }
+        } else {
+#pragma unroll 1
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            const int n0 = nw0 + c0;
+            if (hf * 64 + c0 >= w) break;  // warp-uniform
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            if (c0 == 32 || hf * 64 + 32 >= w) {  // last read of this accumulator by this warp
+              tc_fence_before();
+              mbar_arrive(&acc_empty[ab]);
+            }
+            if (pre != 1.f) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] *= pre;
+            }
+            if (a.bias) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + e);
+                v[e] += bv.x; v[e + 1] += bv.y; v[e + 2] += bv.z; v[e + 3] += bv.w;
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            if (a.row_post) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] *= post;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(xp + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int nn = n0 + xj * 4;
+            const bool col_ok = nn < a.N;
+            const float* xr = xp + (lane >> 3) * 32;
+            float* cp = kC ? a.C + row0 * a.ldc + nn : nullptr;
+            bf16* hp = kHi ? a.out_hi + row0 * a.ldo + nn : nullptr;
+            bf16* lp = kLo ? a.out_lo + row0 * a.ldo + nn : nullptr;
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              float4 x = *reinterpret_cast<const float4*>(xr + i8 * 128 + ((xj ^ (((i8 & 1) << 2) | (lane >> 3))) << 2));
+              if constexpr (kRes) { x.x += rv[i8].x; x.y += rv[i8].y; x.z += rv[i8].z; x.w += rv[i8].w; }
+              if (col_ok && row0 + 4 * i8 < a.M) {
+                if constexpr (kC) *reinterpret_cast<float4*>(cp) = x;
+                if constexpr (kHi) *reinterpret_cast<uint2*>(hp) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+                if constexpr (kLo)
+                  *reinterpret_cast<uint2*>(lp) = make_uint2(pack_bf16(x.x - bf16_round(x.x), x.y - bf16_round(x.y)),
+                                                            pack_bf16(x.z - bf16_round(x.z), x.w - bf16_round(x.w)));
+              }
+              if constexpr (kC) cp += 4 * a.ldc;
+              if constexpr (kHi) hp += 4 * a.ldo;
+              if constexpr (kLo) lp += 4 * a.ldo;
+            }
+            __syncwarp();
+            if constexpr (kRes) { if (c0 == 0 && hf * 64 + 32 < w) fetch_res(n0 + 32); }
+          }
+        }
+        n += w;
+        cnt += KB;  // the ring stages that carried this chunk's weight blocks (the staging warps index the ring by cnt)
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 __global__ void split_bf16_kernel(const float* __restrict__ src, long ld, int rows, int cols, bf16* __restrict__ hi,
                                   bf16* __restrict__ lo) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,8 +840,45 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   if (k.coalesced) {
     epi = (k.C ? 1 : 0) | (k.out_hi ? 2 : 0) | (k.out_lo ? 4 : 0) | (k.res ? 8 : 0);
     S2S_CHECK(!(epi & 4) || (epi & 2), "gemm_tc: a lo image needs a hi image");
+    static const int wide = [] { const char* e = getenv("S2S_GEMM_WIDE"); return e ? atoi(e) : 1; }();  // A/B timing only
+    if (wide && (epi == 2 || epi == 6) && g.N % 64 == 0 && g.ldo % 8 == 0 && g.sCb % 8 == 0 && g.sCh % 8 == 0) epi |= 16;
   }
-  static bool configured[17] = {};  // per instantiation (index epi + 1): every gemm_tc_kernel<EPI> has the same pointer type
+  // panel kernel (A resident in tensor memory): non-batched, K a multiple of 64 that fits beside two accumulators
+  static const int use_panel = [] { const char* e = getenv("S2S_GEMM_PANEL"); return e ? atoi(e) : 1; }();  // 0: A/B timing
+  const int a_cols = (g.K / 2) * (g.passes == 3 ? 2 : 1);
+  if (use_panel && epi >= 0 && g.nb * g.nh == 1 && g.K2 == 0 && !g.b_mn && g.K % 64 == 0 && a_cols <= 320 &&
+      g.a_cb == 0 && g.a_ch == 0 && g.a_rb == 0 && g.a_rh == 0 && g.b_cb == 0 && g.b_ch == 0 && g.b_rb == 0 && g.b_rh == 0) {
+    PanelGeom pg;
+    pg.acol_lo = g.K / 2;
+    pg.acc0 = a_cols;
+    pg.acc1 = a_cols + 128;
+    pg.w1 = 512 - a_cols - 128 >= 128 ? 128 : 64;
+    const int pgrid = ceil_div(g.M, TM) < sm_count() ? ceil_div(g.M, TM) : sm_count();
+    static bool pconf[24] = {};
+    auto plaunch = [&](auto kern) {
+      if (!pconf[epi]) {
+        S2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        pconf[epi] = true;
+      }
+      kern<<<pgrid, G_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, k, pg);
+    };
+    switch (epi) {
+      case 1: plaunch(gemm_panel_kernel<1>); break;
+      case 2: plaunch(gemm_panel_kernel<2>); break;
+      case 3: plaunch(gemm_panel_kernel<3>); break;
+      case 6: plaunch(gemm_panel_kernel<6>); break;
+      case 7: plaunch(gemm_panel_kernel<7>); break;
+      case 9: plaunch(gemm_panel_kernel<9>); break;
+      case 11: plaunch(gemm_panel_kernel<11>); break;
+      case 15: plaunch(gemm_panel_kernel<15>); break;
+      case 18: plaunch(gemm_panel_kernel<18>); break;
+      case 22: plaunch(gemm_panel_kernel<22>); break;
+      default: S2S_CHECK(false, "gemm_tc: unexpected epilogue variant");
+    }
+    S2S_LAUNCH_CHECK();
+    return;
+  }
+  static bool configured[24] = {};  // per instantiation (index epi + 1): every gemm_tc_kernel<EPI> has the same pointer type
   auto launch = [&](auto kern) {
     if (!configured[epi + 1]) {
       S2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -479,6 +895,8 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
     case 9: launch(gemm_tc_kernel<9>); break;
     case 11: launch(gemm_tc_kernel<11>); break;
     case 15: launch(gemm_tc_kernel<15>); break;
+    case 18: launch(gemm_tc_kernel<18>); break;
+    case 22: launch(gemm_tc_kernel<22>); break;
     default: epi = -1; launch(gemm_tc_kernel<-1>); break;
   }
   S2S_LAUNCH_CHECK();
