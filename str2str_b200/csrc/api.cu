@@ -334,7 +334,8 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
     if (n.find("transformer") != std::string::npos || (n.find("trunk.linear_") != std::string::npos)) cols = 320;
     if (n.find("linear_out") != std::string::npos) cols = IPA_FEAT;
     if (n.find("trunk.0") != std::string::npos || n.find("trunk.2") != std::string::npos || n.find("final_layer") != std::string::npos) cols = 384;
-    if (n.find("embedder") != std::string::npos || n.find("linear_b.") != std::string::npos || n.find("down_z") != std::string::npos) continue;
+    const bool ne_tc = n.find("node_embed.2.") != std::string::npos || n.find("node_embed.4.") != std::string::npos;  // optional TC3 path
+    if ((n.find("embedder") != std::string::npos && !ne_tc) || n.find("linear_b.") != std::string::npos || n.find("down_z") != std::string::npos) continue;
     reg(c->P(n), ps.numel, cols);
   }
   for (int b = 0; b < N_BLK; ++b) reg(c->ipa[b].proj_w, (size_t)6816 * 256, 256);
@@ -417,8 +418,13 @@ void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, c
   node_features(t, ridx, fixed, c->tfreq, c->pdenom, c->feat65, c->tf33, B, L, st);
   const std::string ne = "embedder.node_embed.", ee = "embedder.edge_embed.";
   linear(c, c->feat65, 65, c->P(ne + "0.weight"), 65, c->P(ne + "0.bias"), c->a256, 256, R, 256, 65, st, 1);
-  linear(c, c->a256, 256, c->P(ne + "2.weight"), 256, c->P(ne + "2.bias"), c->b256, 256, R, 256, 256, st, 1);
-  linear(c, c->b256, 256, c->P(ne + "4.weight"), 256, c->P(ne + "4.bias"), c->a256, 256, R, 256, 256, st);
+  // layers 2 and 3 (K = 256): split-bf16 tensor-core GEMMs (~16 mantissa bits per operand; measured on B200: trajectory error
+  // 1.259e-5 vs 1.245e-5 with exact fp32 at L = 64 x 100 steps, 8.65e-6 vs 8.27e-6 at L = 128 x 50 — profiles/r01c_traj_parity.log).
+  // Single bf16 is NOT enough here (6.7e-4, DESIGN.md precision table).  S2S_NODE_EMBED_TC=0 restores the exact FFMA GEMMs.
+  static const int ne_env = [] { const char* e = getenv("S2S_NODE_EMBED_TC"); return e ? atoi(e) : 1; }();
+  const int ne_prec = (ne_env && c->opt_node == 1) ? (int)TC3 : (int)EXACT;
+  linear(c, c->a256, 256, c->P(ne + "2.weight"), 256, c->P(ne + "2.bias"), c->b256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, ne_prec);
+  linear(c, c->b256, 256, c->P(ne + "4.weight"), 256, c->P(ne + "4.bias"), c->a256, 256, R, 256, 256, st, 0, nullptr, 0, nullptr, nullptr, ne_prec);
   layernorm(c->a256, nullptr, c->P(ne + "5.weight"), c->P(ne + "5.bias"), rmask, node_out, R, 256, st);
   const float* W1 = c->P(ee + "0.weight");
   linear(c, c->tf33, 33, W1, 120, c->P(ee + "0.bias"), c->Ti, 128, R, 128, 33, st);
