@@ -132,14 +132,14 @@ def algorithmic(B, L):
 
 def ncu_traffic(B, L):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-    (profiles/r01b_ncu_full_*.csv, made with tools/ncu_summary.py at cfg2).  None for any other shape."""
+    (profiles/r01c_ncu_full_pair_kernels.csv, made with tools/ncu_summary.py at cfg2).  None for any other shape."""
     if (B, L) != (64, 256):
         return {}
     import csv
 
     out = {}
-    for fn, names in (("r01b_ncu_full_edge_transition.csv", {"edge_transition_tc": "edge_transition"}),
-                      ("r01b_ncu_full_ipa_stage_kernels.csv", {"ipa_pair_tc_kernel": "ipa_pair_attention", "edge_embed_tc_kernel": "edge_embed"})):
+    for fn, names in (("r01c_ncu_full_pair_kernels.csv", {"edge_transition_tc": "edge_transition", "ipa_pair_tc_kernel": "ipa_pair_attention",
+                                                          "edge_embed_pipe_kernel": "edge_embed"}),):
         path = os.path.join(ROOT, "profiles", fn)
         if not os.path.exists(path):
             continue
@@ -274,7 +274,7 @@ def run_ours(a):
         dom = max((k for k in per if k in alg), key=lambda k: per[k][0], default=None)
         if dom:
             roof = {k: extra[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-            roof.update(kernel=dom, traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/r01b_ncu_full_*.csv (dram read + write per launch)",
+            roof.update(kernel=dom, traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/r01c_ncu_full_pair_kernels.csv (dram read + write per launch)",
                         peak_source=src, timing="CUDA events around each launch, one eager step")
 
     cpu = None
