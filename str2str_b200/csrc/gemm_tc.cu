@@ -512,30 +512,52 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int MT = (a.M + TM - 1) / TM, KB = a.K / KBLK;
+  const int KB2 = (a.K2 + KBLK - 1) / KBLK, KBT = KB + KB2;  // second K segment (passes == 1): through the mAl / mBl maps
+  const int NP = a.nb * a.nh * MT;                            // panels: (batch, head, 128-row tile)
+  auto ksteps_of = [&](int kb) { return (min(KBLK, kb < KB ? a.K - kb * KBLK : a.K2 - (kb - KB) * KBLK) + 15) / 16; };
   // chunk ci of the whole CTA run uses accumulator buffer ci & 1; its width follows from the buffer and what is left of N
   auto chunk_width = [&](uint32_t ci, int n_done) { return min((ci & 1) ? pg.w1 : 128, a.N - n_done); };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t cnt = 0, ci = 0;
-      for (int mt = blockIdx.x; mt < MT; mt += gridDim.x) {
-        for (int kb = 0; kb < KB; ++kb, ++cnt) {  // the panel of A (consumed by the staging warps)
+      for (int p = blockIdx.x; p < NP; p += gridDim.x) {
+        const int mt = p % MT, bz = p / MT, ib = bz / a.nh, ih = bz % a.nh;
+        const int arow = ib * a.a_rb + ih * a.a_rh + mt * TM, acol = ib * a.a_cb + ih * a.a_ch;
+        const int brow = ib * a.b_rb + ih * a.b_rh, bcol = ib * a.b_cb + ih * a.b_ch;
+        for (int kb = 0; kb < KBT; ++kb, ++cnt) {  // the panel of A (consumed by the staging warps)
           const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
           mbar_wait(&s_empty[s], ph ^ 1);
           mbar_expect_tx(&s_full[s], stage_bytes);
           unsigned char* st = smem + s * stage_bytes;
-          tma_load_2d(st, &mAh, kb * KBLK, mt * TM, &s_full[s]);
-          if (bps == 2) tma_load_2d(st + TILE_BYTES, &mAl, kb * KBLK, mt * TM, &s_full[s]);
+          if (kb >= KB) {
+            tma_load_2d(st, &mAl, ib * a.a2_cb + ih * a.a2_ch + (kb - KB) * KBLK, ib * a.a2_rb + ih * a.a2_rh + mt * TM, &s_full[s]);
+            continue;
+          }
+          tma_load_2d(st, &mAh, acol + kb * KBLK, arow, &s_full[s]);
+          if (bps == 2) tma_load_2d(st + TILE_BYTES, &mAl, acol + kb * KBLK, arow, &s_full[s]);
         }
-        for (int n = 0; n < a.N; ++ci) {  // weight blocks: 128 rows of W from row n (rows past N read as zeros), one K block
+        for (int n = 0; n < a.N; ++ci) {  // weight blocks: 128 rows of W from row n (rows past the end read as zeros), one K block
           const int w = chunk_width(ci, n);
-          for (int kb = 0; kb < KB; ++kb, ++cnt) {
+          for (int kb = 0; kb < KBT; ++kb, ++cnt) {
             const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
             mbar_wait(&s_empty[s], ph ^ 1);
             mbar_expect_tx(&s_full[s], stage_bytes);
             unsigned char* st = smem + s * stage_bytes;
-            tma_load_2d(st, &mBh, kb * KBLK, n, &s_full[s]);
-            if (bps == 2) tma_load_2d(st + TILE_BYTES, &mBl, kb * KBLK, n, &s_full[s]);
+            if (kb >= KB) {
+              tma_load_2d(st, &mBl, ib * a.b2_cb + ih * a.b2_ch + (kb - KB) * KBLK, ib * a.b2_rb + ih * a.b2_rh + n, &s_full[s]);
+            } else if (a.b_mn) {  // B given as [K rows][N columns]: two [64 k x 64 n] boxes per K block
+              const int r0 = brow + kb * KBLK, c0 = bcol + n;
+              tma_load_2d(st, &mBh, c0, r0, &s_full[s]);
+              tma_load_2d(st + TILE_BYTES / 2, &mBh, c0 + 64, r0, &s_full[s]);
+              if (bps == 2) {
+                tma_load_2d(st + TILE_BYTES, &mBl, c0, r0, &s_full[s]);
+                tma_load_2d(st + TILE_BYTES + TILE_BYTES / 2, &mBl, c0 + 64, r0, &s_full[s]);
+              }
+            } else {
+              tma_load_2d(st, &mBh, bcol + kb * KBLK, brow + n, &s_full[s]);
+              if (bps == 2) tma_load_2d(st + TILE_BYTES, &mBl, bcol + kb * KBLK, brow + n, &s_full[s]);
+            }
           }
           n += w;
         }
@@ -547,8 +569,9 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     const uint32_t ring = desc_lo_sw128(smem_u32(smem));
     constexpr uint32_t BLK = TILE_BYTES >> 4;
     const uint32_t stage_units = bps * BLK;
-    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++pi) {
-      cnt += KB;  // the ring stages that carried A
+    const uint32_t bmn_fix = ((uint32_t)(TILE_BYTES / 2) >> 4 << 16) - (1u << 16);  // MN-major B: LBO field 1 -> 512 (8 KB between halves)
+    for (int p = blockIdx.x; p < NP; p += gridDim.x, ++pi) {
+      cnt += KBT;  // the ring stages that carried A
       mbar_wait(a_ready, pi & 1);
       tc_fence_after();
       for (int n = 0; n < a.N; ++ci) {
@@ -557,21 +580,23 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
         mbar_wait(&acc_empty[ab], aph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + (ab ? pg.acc1 : pg.acc0);
-        const uint32_t idesc = make_idesc(128, (w + 15) & ~15);
-        for (int kb = 0; kb < KB; ++kb, ++cnt) {
+        const uint32_t idesc = make_idesc(128, (w + 15) & ~15) | (a.b_mn ? (1u << 16) : 0u);  // bit 16: B is MN-major
+        for (int kb = 0; kb < KBT; ++kb, ++cnt) {
           const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
           mbar_wait(&s_full[s], ph);
           tc_fence_after();
-          const uint32_t bh = ring + s * stage_units;
+          const uint32_t bh0 = ring + s * stage_units;
           const uint32_t ah = tmem + kb * 32, al = tmem + pg.acol_lo + kb * 32;
+          const int ksteps = ksteps_of(kb);
           if (elect_one()) {
             if (!(a.dbg & 16)) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (kb | k) umma_ts<true>(d, ah + 8 * k, bh + 2 * k, idesc); else umma_ts<false>(d, ah + 8 * k, bh + 2 * k, idesc);
+              for (int k = 0; k < ksteps; ++k) {
+                // K-major B: k-step = +32 B inside the 128-byte rows; MN-major B: k-step = 16 rows = +2 KB
+                const uint32_t bh = a.b_mn ? bh0 + 128 * k + bmn_fix : bh0 + 2 * k;
+                if (kb | k) umma_ts<true>(d, ah + 8 * k, bh, idesc); else umma_ts<false>(d, ah + 8 * k, bh, idesc);
                 if (bps == 2) {
-                  umma_ts<true>(d, al + 8 * k, bh + 2 * k, idesc);
-                  umma_ts<true>(d, ah + 8 * k, bh + BLK + 2 * k, idesc);
+                  umma_ts<true>(d, al + 8 * k, bh, idesc);
+                  umma_ts<true>(d, ah + 8 * k, bh + BLK, idesc);
                 }
               }
             }
@@ -594,12 +619,15 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     constexpr bool kC = (EPI & 1) != 0, kHi = (EPI & 2) != 0, kLo = (EPI & 4) != 0, kRes = (EPI & 8) != 0, kWide = (EPI & 16) != 0;
     const int xj = lane & 7;
     uint32_t cnt = 0, ci = 0, pi = 0;
-    for (int mt = blockIdx.x; mt < MT; mt += gridDim.x, ++pi) {
+    for (int p = blockIdx.x; p < NP; p += gridDim.x, ++pi) {
+      const int mt = p % MT, bz = p / MT, ib = bz / a.nh, ih = bz % a.nh;
+      const long boff = ib * a.sCb + ih * a.sCh;
+      const float* bias = a.bias ? a.bias + ib * a.bias_sb + ih * a.bias_sh : nullptr;
       if (hf == 0) {
         // ---- stage the panel of A into tensor memory: this thread copies row r of every K block (128 bytes = 32 columns)
         if (pi > 0) mbar_wait(a_free, (pi - 1) & 1);
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb, ++cnt) {
+        for (int kb = 0; kb < KBT; ++kb, ++cnt) {
           const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
           mbar_wait(&s_full[s], ph);
           const unsigned char* st = smem + s * stage_bytes;
@@ -628,10 +656,10 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
         const uint32_t ab = ci & 1, aph = (ci >> 1) & 1;
         const int nw0 = n + hf * 64;                 // first column of this warp's 64-column share of the chunk
         const bool has_cols = hf * 64 < w;           // warp-uniform
-        if (has_cols && a.bias) {
+        if (has_cols && bias) {
           float bv[2];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) bv[u] = (nw0 + u * 32 + lane < a.N) ? __ldg(a.bias + nw0 + u * 32 + lane) : 0.f;
+          for (int u = 0; u < 2; ++u) bv[u] = (nw0 + u * 32 + lane < a.N) ? __ldg(bias + nw0 + u * 32 + lane) : 0.f;
           __syncwarp();
 #pragma unroll
           for (int u = 0; u < 2; ++u) bias_s[u * 32 + lane] = bv[u];
@@ -640,7 +668,7 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
         float4 rv[8];
         auto fetch_res = [&](int nc) {  // residual of the 32-column sub-chunk starting at column nc, coalesced layout
           const int nn = nc + xj * 4;
-          const float* rp = a.res + row0 * a.ldres + nn;
+          const float* rp = a.res + boff + row0 * a.ldres + nn;
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8, rp += 4 * a.ldres)
             rv[i8] = (row0 + 4 * i8 < a.M && nn < a.N) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -663,7 +691,7 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
             for (int e = 0; e < 64; ++e) v[e] *= pre;
           }
-          if (a.bias) {
+          if (bias) {
 #pragma unroll
             for (int e = 0; e < 64; e += 4) {
               const float4 bv = *reinterpret_cast<const float4*>(bias_s + e);
@@ -678,7 +706,7 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
             for (int e = 0; e < 64; ++e) v[e] *= post;
           }
-          const long ooff = row0 * a.ldo + nw0 + xj * 8;
+          const long ooff = boff + row0 * a.ldo + nw0 + xj * 8;
 #pragma unroll
           for (int img = 0; img < (kLo ? 2 : 1); ++img) {
 #pragma unroll
@@ -715,7 +743,7 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 32; ++e) v[e] *= pre;
             }
-            if (a.bias) {
+            if (bias) {
 #pragma unroll
               for (int e = 0; e < 32; e += 4) {
                 const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + e);
@@ -737,9 +765,9 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             const int nn = n0 + xj * 4;
             const bool col_ok = nn < a.N;
             const float* xr = xp + (lane >> 3) * 32;
-            float* cp = kC ? a.C + row0 * a.ldc + nn : nullptr;
-            bf16* hp = kHi ? a.out_hi + row0 * a.ldo + nn : nullptr;
-            bf16* lp = kLo ? a.out_lo + row0 * a.ldo + nn : nullptr;
+            float* cp = kC ? a.C + boff + row0 * a.ldc + nn : nullptr;
+            bf16* hp = kHi ? a.out_hi + boff + row0 * a.ldo + nn : nullptr;
+            bf16* lp = kLo ? a.out_lo + boff + row0 * a.ldo + nn : nullptr;
 #pragma unroll
             for (int i8 = 0; i8 < 8; ++i8) {
               float4 x = *reinterpret_cast<const float4*>(xr + i8 * 128 + ((xj ^ (((i8 & 1) << 2) | (lane >> 3))) << 2));
@@ -760,7 +788,7 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
           }
         }
         n += w;
-        cnt += KB;  // the ring stages that carried this chunk's weight blocks (the staging warps index the ring by cnt)
+        cnt += KBT;  // the ring stages that carried this chunk's weight blocks (the staging warps index the ring by cnt)
       }
     }
   }
@@ -845,15 +873,22 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   }
   // panel kernel (A resident in tensor memory): non-batched, K a multiple of 64 that fits beside two accumulators
   static const int use_panel = [] { const char* e = getenv("S2S_GEMM_PANEL"); return e ? atoi(e) : 1; }();  // 0: A/B timing
-  const int a_cols = (g.K / 2) * (g.passes == 3 ? 2 : 1);
-  if (use_panel && epi >= 0 && g.nb * g.nh == 1 && g.K2 == 0 && !g.b_mn && g.K % 64 == 0 && a_cols <= 320 &&
-      g.a_cb == 0 && g.a_ch == 0 && g.a_rb == 0 && g.a_rh == 0 && g.b_cb == 0 && g.b_ch == 0 && g.b_rb == 0 && g.b_rh == 0) {
+  const int kbt = g.K / 64 + ceil_div(g.K2, 64);  // K blocks of the panel (both segments)
+  const int a_cols = kbt * 32 * (g.passes == 3 ? 2 : 1);
+  // Batched (decoy, head) GEMMs, a second K segment and an MN-major B are supported by the panel kernel but measured SLOWER there
+  // (q.k^T+points 75 vs 60 us, P.v 60 vs 48, P.v_pts 48 vs 41 per launch at cfg2): with only two output chunks per panel the A
+  // staging -> MMA -> epilogue chain of a panel is not overlapped with the next panel.  Off by default (S2S_GEMM_PANEL_BATCHED=1: A/B).
+  static const int panel_batched = [] { const char* e = getenv("S2S_GEMM_PANEL_BATCHED"); return e ? atoi(e) : 0; }();
+  const bool plain = g.nb * g.nh == 1 && g.K2 == 0 && !g.b_mn;
+  if (use_panel && epi >= 0 && (plain || panel_batched) && g.K % 64 == 0 && a_cols <= 320 && (g.K2 == 0 || g.passes == 1) &&
+      (!g.b_mn || g.K2 == 0)) {
     PanelGeom pg;
-    pg.acol_lo = g.K / 2;
+    pg.acol_lo = kbt * 32;
     pg.acc0 = a_cols;
     pg.acc1 = a_cols + 128;
     pg.w1 = 512 - a_cols - 128 >= 128 ? 128 : 64;
-    const int pgrid = ceil_div(g.M, TM) < sm_count() ? ceil_div(g.M, TM) : sm_count();
+    const int n_panels = g.nb * g.nh * ceil_div(g.M, TM);
+    const int pgrid = n_panels < sm_count() ? n_panels : sm_count();
     static bool pconf[24] = {};
     auto plaunch = [&](auto kern) {
       if (!pconf[epi]) {
