@@ -154,6 +154,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
               // leading-byte-offset field (bits 16..29) carries the 8 KB distance between the two 64-column halves.
               const uint32_t ah = st + 2 * k;
               const uint32_t bh = a.b_mn ? st + BLK + 128 * k + bmn_fix : st + BLK + 2 * k;
+              if (a.dbg & 256) {  // timing experiment only: consecutive MMAs alternate between the two accumulator buffers
+                umma_ss<true>(tmem + (k & 1) * 128, ah, bh, idesc);
+                continue;
+              }
               if (kb | k) umma_ss<true>(d, ah, bh, idesc); else umma_ss<false>(d, ah, bh, idesc);
               if (a.passes == 3) {
                 umma_ss<true>(d, st + 2 * BLK + 2 * k, bh, idesc);

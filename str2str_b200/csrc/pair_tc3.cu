@@ -53,6 +53,7 @@ struct Args {
   bf16* z_out;
   int L, n_tiles, ncopy;
   int dbg;  // timing experiments only (S2S_ET_DEBUG): 1 no weight TMA, 2 no MMA, 4 no epilogue math
+  int interleave;  // layer-1 chunks 0 and 1 issued interleaved (two independent accumulator chains)
 };
 
 // MC = true: the kernel runs as clusters of two CTAs that share the weight stream: each 16 KB weight block is fetched from
@@ -198,7 +199,40 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
         ph_a0 ^= 1;
         tc_fence_after();
         // ---- layer 1: three 128-column chunks in R0+R1, R2, R0+R1; A = [z | n'_j] from shared memory ----
-        for (int nc = 0; nc < 3; ++nc) {
+        // SS-mode MMAs that accumulate into the SAME tensor-memory columns run as a dependent chain (~260 cycles each in the
+        // GEMM experiments, ~190 when consecutive MMAs alternate between two accumulators: profiles/r01c_gemm_and_embedder_
+        // experiments.log), so chunks 0 (E) and 1 (R2) are issued interleaved k-step by k-step: block (chunk 0, kb) and block
+        // (chunk 1, kb) = ring positions cnt + kb and cnt + 4 + kb are both held, and released together.
+        int nc_first = 0;
+        if (a.interleave) {
+          wait_prev(emptyE, nE);
+          wait_prev(empty2, n2);
+          tc_fence_after();
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint32_t c0 = cnt + kb, c1 = cnt + 4 + kb;
+            mbar_wait(&w_full[c0 % NSTAGE], (c0 / NSTAGE) & 1);
+            mbar_wait(&w_full[c1 % NSTAGE], (c1 / NSTAGE) & 1);
+            tc_fence_after();
+            const uint32_t w0 = wr + (c0 % NSTAGE) * BLK, w1 = wr + (c1 % NSTAGE) * BLK, ab = a0 + kb * BLK;
+            if (elect_one()) {
+              if (do_mma) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (kb | k) { umma_ss<true>(tmem, ab + 2 * k, w0 + 2 * k, IDESC128); umma_ss<true>(tmem + 128, ab + 2 * k, w1 + 2 * k, IDESC128); }
+                  else { umma_ss<false>(tmem, ab + 2 * k, w0 + 2 * k, IDESC128); umma_ss<false>(tmem + 128, ab + 2 * k, w1 + 2 * k, IDESC128); }
+                }
+              }
+              if constexpr (MC) { umma_commit_mc(&w_empty[c0 % NSTAGE], (uint16_t)3); umma_commit_mc(&w_empty[c1 % NSTAGE], (uint16_t)3); }
+              else { umma_commit(&w_empty[c0 % NSTAGE]); umma_commit(&w_empty[c1 % NSTAGE]); }
+            }
+            __syncwarp();
+          }
+          cnt += 8;
+          if (elect_one()) { umma_commit(fullE); umma_commit(full2); }
+          __syncwarp();
+          nc_first = 2;
+        }
+        for (int nc = nc_first; nc < 3; ++nc) {
           uint32_t d;
           if (nc == 1) { wait_prev(empty2, n2); d = tmem + 128; }
           else { wait_prev(emptyE, nE); d = tmem; }
@@ -444,6 +478,8 @@ void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st) {
   {
     const char* e = getenv("S2S_ET_DEBUG");
     k.dbg = e ? atoi(e) : 0;
+    static const int il = [] { const char* v = getenv("S2S_ET_INTERLEAVE"); return v ? atoi(v) : 0; }();
+    k.interleave = il;
   }
   static bool configured = false;
   const int smem = SMEM_BYTES + 1024;
