@@ -112,6 +112,15 @@ int s2s_backbone_atoms(s2s_ctx* ctx, int rows, const float* rigids, const float*
 int s2s_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
                    void* stream);
 
+/* Tensor-core linear layer of the node track (reference nn.Linear call sites: src/models/net/ipa.py:131-158,262,306-318;
+ * layers.py:138-145,199-213):  Y = act(A W^T + bias) [+ res]  with A [M,K], W [N,K] (row-major fp32, device).  passes = 3: split-bf16
+ * (hi/lo) operands, three tcgen05 MMA passes, fp32 accumulate (~16 mantissa bits per operand); passes = 1: single bf16.  Outputs
+ * (any subset, at least one): C [M,N] fp32, out_hi / out_lo [M,N] bf16 images of the result (out_lo needs out_hi).  Routed to the
+ * panel kernel (A resident in tensor memory) when K % 64 == 0 and the panel fits, else to the tile kernel.  K % 16 == 0, N % 4 == 0.
+ * `res` may alias `C`.  Temporaries (operand images) are allocated and freed on `stream`. */
+int s2s_linear_tc(const float* A, const float* W, const float* bias, const float* res, float* C, void* out_hi, void* out_lo,
+                  int M, int N, int K, int passes, int relu, void* stream);
+
 /* Per-kernel device timing for the benchmark's roofline line: when enabled, CUDA events bracket the launches of
  * the named kernels ("edge_transition", "edge_embed", "ipa_pair_attention", "gemm") on their stream.  Must be
  * off during CUDA-graph capture.  s2s_profile_read returns 1 if no launch of `name` was recorded. */

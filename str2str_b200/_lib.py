@@ -34,6 +34,7 @@ SIGNATURES = {
     "s2s_se3_perturb": (_i, [_i, _i] + [_vp] * 11),
     "s2s_backbone_atoms": (_i, [_vp, _i] + [_vp] * 6),
     "s2s_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "s2s_linear_tc": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
     "s2s_launch_count": (_i64, []),
     "s2s_profile_enable": (None, [_i]),
     "s2s_profile_reset": (None, []),

@@ -886,6 +886,30 @@ int s2s_backbone_atoms(s2s_ctx* c, int rows, const float* rigids, const float* p
   });
 }
 
+int s2s_linear_tc(const float* A, const float* W, const float* bias, const float* res, float* C, void* out_hi, void* out_lo,
+                  int M, int N, int K, int passes, int relu, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(A && W && (C || out_hi), "s2s_linear_tc: null argument");
+    S2S_CHECK(!out_lo || out_hi, "s2s_linear_tc: out_lo needs out_hi");
+    S2S_CHECK(M > 0 && N > 0 && K > 0 && K % 16 == 0 && N % 4 == 0, "s2s_linear_tc: needs K % 16 == 0 and N % 4 == 0");
+    S2S_CHECK(passes == 1 || passes == 3, "s2s_linear_tc: passes must be 1 or 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    bf16 *a_hi, *a_lo, *w_hi, *w_lo;
+    S2S_CUDA(cudaMallocAsync(&a_hi, (size_t)M * K * 2, st)); S2S_CUDA(cudaMallocAsync(&a_lo, (size_t)M * K * 2, st));
+    S2S_CUDA(cudaMallocAsync(&w_hi, (size_t)N * K * 2, st)); S2S_CUDA(cudaMallocAsync(&w_lo, (size_t)N * K * 2, st));
+    split_bf16(A, K, M, K, a_hi, a_lo, st);
+    split_bf16(W, K, N, K, w_hi, w_lo, st);
+    TcGemm g;
+    g.A_hi = a_hi; g.A_lo = a_lo; g.a_rows = M; g.a_cols = K; g.a_pitch = K;
+    g.B_hi = w_hi; g.B_lo = w_lo; g.b_rows = N; g.b_cols = K; g.b_pitch = K;
+    g.M = M; g.N = N; g.K = K; g.passes = passes; g.relu = relu; g.bias = bias; g.res = res; g.ldres = N;
+    g.C = C; g.ldc = N; g.out_hi = (bf16*)out_hi; g.out_lo = (bf16*)out_lo; g.ldo = N;
+    gemm_tc(g, st);
+    S2S_CUDA(cudaFreeAsync(a_hi, st)); S2S_CUDA(cudaFreeAsync(a_lo, st));
+    S2S_CUDA(cudaFreeAsync(w_hi, st)); S2S_CUDA(cudaFreeAsync(w_lo, st));
+  });
+}
+
 int s2s_linear_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu, void* stream) {
   return guarded([&] {
     S2S_CHECK(A && W && C, "s2s_linear_f32: null argument");

@@ -396,3 +396,57 @@ def test_predict_step_delta_sweep_layout(params, tmp_path):
         assert all(len(ln) == 80 for ln in txt.split("\n")[:-1])
     merged = open(os.path.join(out, "toy.pdb")).read()
     assert merged.count("MODEL") == 6 and merged.count("ENDMDL") == 6 and merged.endswith("END".ljust(80) + "\n")
+
+
+GEMM_CASES = [
+    # M,   N,    K,    passes, relu, res,   outs          kernel / epilogue variant exercised
+    (640, 320, 320, 3, 0, True, "c"),       # panel, K = 320 geometry (128 + 64 accumulators), residual
+    (384, 672, 256, 3, 0, False, "c"),      # panel, ragged last chunk (32 columns)
+    (200, 64, 128, 3, 1, False, "chl"),     # panel, M not a multiple of 128, ReLU, fp32 + both bf16 images
+    (256, 768, 256, 1, 0, False, "h"),      # panel, single bf16 pass, bf16-only output (wide epilogue)
+    (256, 960, 320, 3, 0, False, "hl"),     # panel, hi + lo images only (wide epilogue, alternating 128 / 64 chunks)
+    (256, 256, 2688, 3, 0, True, "chl"),    # tile kernel (panel does not fit), residual + images
+    (130, 36, 48, 3, 0, False, "c"),        # tile kernel, K % 64 != 0, N = 36
+    (300, 256, 256, 3, 1, True, "c_inplace"),  # residual aliasing the output
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=[f"M{c[0]}_N{c[1]}_K{c[2]}_p{c[3]}_{c[6]}" for c in GEMM_CASES])
+def test_linear_tc_vs_fp64(case):
+    """The tensor-core linear layer (panel kernel / tile kernel, every epilogue variant) through the C ABI against fp64:
+    3-pass split-bf16 within 3e-5 relative L2 (the dropped lo*lo term is ~2^-16), single bf16 pass within 1e-2; the bf16 images
+    are the rounded result (hi) and its remainder (hi + lo within 2^-15 of the fp32 output)."""
+    from str2str_b200 import _lib
+
+    M, N, K, passes, relu, use_res, outs = case
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g) if use_res else None
+    ref = A.double() @ W.double().T + b.double()
+    if relu:
+        ref = torch.relu(ref)
+    if use_res:
+        ref = ref + R.double()
+    Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
+    inplace = outs == "c_inplace"
+    kinds = outs.split("_")[0]
+    Cd = R.cuda().clone() if inplace else (torch.full((M, N), float("nan"), device="cuda") if "c" in kinds else None)
+    Rd = Cd if inplace else (R.cuda() if use_res else None)
+    Hd = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if "h" in kinds else None
+    Ld = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if "l" in kinds else None
+    p = lambda t: _lib.ptr(t) if t is not None else None
+    _lib.check(lib.s2s_linear_tc(p(Ad), p(Wd), p(bd), p(Rd), p(Cd), p(Hd), p(Ld), M, N, K, passes, relu, _lib.stream()))
+    torch.cuda.synchronize()
+    tol = 3e-5 if passes == 3 else 1e-2
+    if Cd is not None:
+        assert torch.isfinite(Cd).all()
+        assert rel(Cd, ref) < tol, rel(Cd, ref)
+    if Hd is not None:
+        assert rel(Hd.float(), ref) < max(tol, 4e-3)            # bf16 rounding of the output
+        if Cd is not None:
+            assert torch.equal(Hd, Cd.bfloat16())
+    if Ld is not None:
+        assert rel(Hd.float() + Ld.float(), ref) < max(tol, 4e-5)
