@@ -120,14 +120,24 @@ def gt_frames_4x4(q, x):
 
 
 def algorithmic(B, L):
-    """Per-launch algorithmic work of the candidate dominant kernels (DESIGN.md 'Kernels')."""
+    """Per-launch ALGORITHMIC work of the candidate dominant kernels = SURVEY.md §8(d)'s per-unit figures x the units one launch
+    processes (DESIGN.md §6 states them): name -> (bound, algorithmic FLOPs or bytes, algorithmic bytes, extra fields).
+      EdgeTransition: F_ET = 2 (2 * 384^2 + 384 * 128) = 688 128 FLOP per pair row — the reference's three 384-wide layers.  The kernel
+        executes 655 360 per row (n'_i terms folded into per-residue vectors); `executed_flops` carries that count.
+      IPA pair kernel: bytes_IPA = B [L^2 c_z s_z + 2 L c_s 4 + L 7 4 + L 4] + parameters once, with s_z = 2 (bf16 pair tensor).  The
+        kernel as built also reads the logits and writes the attention weights (2 B H L^2 4 bytes: the q.k^T and P.v GEMMs are separate
+        launches); `moved_bytes` is that larger, actually necessary traffic of this kernel.
+      edge embedder: 2 * 2 * 128^2 FLOP per pair row (layer 1 table-ised, as SURVEY §8d allows); writes the pair tensor once."""
     rows = B * L * L
-    et_flops = rows * 2 * (128 * 384 + 384 * 384 + 384 * 128 + 128 * 128)   # fused EdgeTransition, factored form
+    et_flops = rows * 2 * (2 * 384 * 384 + 384 * 128) + 2 * B * L * 256 * 128
+    et_exec = rows * 2 * (256 * 384 + 384 * 384 + 640 * 128)
     et_bytes = rows * 128 * 2 * 2                                           # z read + z' write, bf16
-    ipa_bytes = rows * 128 * 2 + 2 * B * 8 * L * L * 4 + B * L * 256 * 4    # z (bf16) + logits in / weights out + o_pair
+    ipa_alg = B * (L * L * 128 * 2 + 2 * L * 256 * 4 + L * 7 * 4 + L * 4) + 2445264 * 4
+    ipa_moved = rows * 128 * 2 + 2 * B * 8 * L * L * 4 + B * L * 256 * 4     # z (bf16) + logits in / weights out + o_pair
     ee_flops = rows * 2 * 2 * 128 * 128
-    return dict(edge_transition=("tensor", et_flops, et_bytes), ipa_pair_attention=("hbm", ipa_bytes, ipa_bytes),
-                edge_embed=("tensor", ee_flops, rows * 128 * 2))
+    return dict(edge_transition=("tensor", et_flops, et_bytes, {"executed_flops": et_exec}),
+                ipa_pair_attention=("hbm", ipa_alg, ipa_alg, {"moved_bytes": ipa_moved}),
+                edge_embed=("tensor", ee_flops, rows * 128 * 2, {}))
 
 
 def ncu_traffic(B, L):
@@ -260,21 +270,26 @@ def run_ours(a):
             avg = tot / cnt
             rec = {"launches": cnt, "avg_ms": round(avg, 4), "share_of_profiled": round(tot / total_prof, 3)}
             if name in alg:
-                bound, work, byts = alg[name]
+                bound, work, byts, more = alg[name]
                 if bound == "tensor":
                     ach = work / (avg * 1e-3) / 1e12
                     rec.update(bound="tensor", achieved=round(ach, 1), peak=tf, unit="TFLOP/s", frac=round(ach / tf, 3))
+                    if "executed_flops" in more:
+                        rec["executed_tflops"] = round(more["executed_flops"] / (avg * 1e-3) / 1e12, 1)
                 else:
                     ach = work / (avg * 1e-3) / 1e9
                     rec.update(bound="hbm", achieved=round(ach, 1), peak=hbm, unit="GB/s", frac=round(ach / hbm, 3))
-            if name in alg:
-                rec["algorithmic_bytes"] = alg[name][2]
+                    if "moved_bytes" in more:
+                        rec["moved_gbs"] = round(more["moved_bytes"] / (avg * 1e-3) / 1e9, 1)
+                        rec["moved_frac"] = round(more["moved_bytes"] / (avg * 1e-3) / 1e9 / hbm, 3)
+                rec["algorithmic_bytes"] = byts
                 rec["traffic"] = traffic.get(name)
             extra[name] = rec
         dom = max((k for k in per if k in alg), key=lambda k: per[k][0], default=None)
         if dom:
             roof = {k: extra[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-            roof.update(kernel=dom, traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/r01c_ncu_full_pair_kernels.csv (dram read + write per launch)",
+            roof.update({k: extra[dom][k] for k in ("executed_tflops", "moved_gbs", "moved_frac") if k in extra[dom]})
+            roof.update(kernel=dom, algorithmic="SURVEY.md 8(d) per-unit figure x units per launch (bench.py: algorithmic())", traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/r01c_ncu_full_pair_kernels.csv (dram read + write per launch)",
                         peak_source=src, timing="CUDA events around each launch, one eager step")
 
     cpu = None
