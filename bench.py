@@ -166,6 +166,42 @@ def ncu_traffic(B, L):
     return out
 
 
+def roofline_records(per, B, L):
+    """per = {kernel name: (total device ms, launches)} of one eager step -> (roofline object of the dominant kernel, per-kernel records)."""
+    hbm, tf, src = peaks()
+    alg = algorithmic(B, L)
+    traffic = ncu_traffic(B, L)
+    extra, roof = {}, None
+    total_prof = sum(v[0] for v in per.values())
+    for name, (tot, cnt) in per.items():
+        avg = tot / cnt
+        rec = {"launches": cnt, "avg_ms": round(avg, 4), "share_of_profiled": round(tot / total_prof, 3)}
+        if name in alg:
+            bound, work, byts, more = alg[name]
+            if bound == "tensor":
+                ach = work / (avg * 1e-3) / 1e12
+                rec.update(bound="tensor", achieved=round(ach, 1), peak=tf, unit="TFLOP/s", frac=round(ach / tf, 3))
+                if "executed_flops" in more:
+                    rec["executed_tflops"] = round(more["executed_flops"] / (avg * 1e-3) / 1e12, 1)
+            else:
+                ach = work / (avg * 1e-3) / 1e9
+                rec.update(bound="hbm", achieved=round(ach, 1), peak=hbm, unit="GB/s", frac=round(ach / hbm, 3))
+                if "moved_bytes" in more:
+                    rec["moved_gbs"] = round(more["moved_bytes"] / (avg * 1e-3) / 1e9, 1)
+                    rec["moved_frac"] = round(more["moved_bytes"] / (avg * 1e-3) / 1e9 / hbm, 3)
+            rec["algorithmic_bytes"] = byts
+            rec["traffic"] = traffic.get(name)
+        extra[name] = rec
+    dom = max((k for k in per if k in alg), key=lambda k: per[k][0], default=None)
+    if dom:
+        roof = {k: extra[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+        roof.update({k: extra[dom][k] for k in ("executed_tflops", "moved_gbs", "moved_frac") if k in extra[dom]})
+        roof.update(kernel=dom, algorithmic="SURVEY.md 8(d) per-unit figure x units per launch (bench.py: algorithmic())",
+                    traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/r01c_ncu_full_pair_kernels.csv (dram read + write per launch)",
+                    peak_source=src, timing="CUDA events around each launch, one eager step")
+    return roof, extra
+
+
 def run_ours(a):
     import torch.distributed as dist
 
@@ -257,40 +293,12 @@ def run_ours(a):
         eager.forward_backward(dev_batch, r0, 0.5, return_numpy=False)
         torch.cuda.synchronize(dev)
         lib.s2s_profile_enable(0)
-        hbm, tf, src = peaks()
-        alg = algorithmic(B, L)
-        traffic = ncu_traffic(B, L)
         per = {}
         for name in ("edge_transition", "ipa_pair_attention", "edge_embed", "gemm", "gemm_tc"):
             tot, cnt = C.c_double(0), C.c_int64(0)
             if lib.s2s_profile_read(name.encode(), C.byref(tot), C.byref(cnt)) == 0 and cnt.value:
                 per[name] = (tot.value, cnt.value)
-        total_prof = sum(v[0] for v in per.values())
-        for name, (tot, cnt) in per.items():
-            avg = tot / cnt
-            rec = {"launches": cnt, "avg_ms": round(avg, 4), "share_of_profiled": round(tot / total_prof, 3)}
-            if name in alg:
-                bound, work, byts, more = alg[name]
-                if bound == "tensor":
-                    ach = work / (avg * 1e-3) / 1e12
-                    rec.update(bound="tensor", achieved=round(ach, 1), peak=tf, unit="TFLOP/s", frac=round(ach / tf, 3))
-                    if "executed_flops" in more:
-                        rec["executed_tflops"] = round(more["executed_flops"] / (avg * 1e-3) / 1e12, 1)
-                else:
-                    ach = work / (avg * 1e-3) / 1e9
-                    rec.update(bound="hbm", achieved=round(ach, 1), peak=hbm, unit="GB/s", frac=round(ach / hbm, 3))
-                    if "moved_bytes" in more:
-                        rec["moved_gbs"] = round(more["moved_bytes"] / (avg * 1e-3) / 1e9, 1)
-                        rec["moved_frac"] = round(more["moved_bytes"] / (avg * 1e-3) / 1e9 / hbm, 3)
-                rec["algorithmic_bytes"] = byts
-                rec["traffic"] = traffic.get(name)
-            extra[name] = rec
-        dom = max((k for k in per if k in alg), key=lambda k: per[k][0], default=None)
-        if dom:
-            roof = {k: extra[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-            roof.update({k: extra[dom][k] for k in ("executed_tflops", "moved_gbs", "moved_frac") if k in extra[dom]})
-            roof.update(kernel=dom, algorithmic="SURVEY.md 8(d) per-unit figure x units per launch (bench.py: algorithmic())", traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/r01c_ncu_full_pair_kernels.csv (dram read + write per launch)",
-                        peak_source=src, timing="CUDA events around each launch, one eager step")
+        roof, extra = roofline_records(per, B, L)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:  # reported at N=1 only (the host cores are shared by the ranks otherwise)

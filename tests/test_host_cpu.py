@@ -164,3 +164,29 @@ def test_trajectory_scheduler_plan_and_phases():
     assert ref == sum(2 * (n + 1) for n in {int(1000 * d / 100) for d in range(25, 75, 5)})
     total_rows = sum(n + 1 for n in steps)
     assert -(-total_rows // 64) <= cont < ref and cont < 0.82 * ref             # 7766 vs 9520 iterations (lower bound 7438): 18 % fewer
+
+
+def test_bench_roofline_records():
+    """bench.py's roofline arithmetic on recorded timings (no GPU): algorithmic work per SURVEY 8(d), executed / moved figures
+    alongside, dominant kernel = largest device time."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    alg = bench.algorithmic(64, 256)
+    rows = 64 * 256 * 256
+    assert alg["edge_transition"][1] == rows * 688128 + 2 * 64 * 256 * 256 * 128
+    assert alg["edge_transition"][3]["executed_flops"] == rows * 655360
+    assert alg["ipa_pair_attention"][1] == 64 * (256 * 256 * 128 * 2 + 2 * 256 * 256 * 4 + 256 * 7 * 4 + 256 * 4) + 2445264 * 4
+    per = {"edge_transition": (15 * 2.5276, 15), "ipa_pair_attention": (20 * 0.2678, 20), "edge_embed": (5 * 1.1463, 5), "gemm_tc": (3.0, 100)}
+    roof, extra = bench.roofline_records(per, 64, 256)
+    assert roof["kernel"] == "edge_transition" and roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s"
+    assert abs(roof["achieved"] - 1142.3) < 0.2 and abs(roof["executed_tflops"] - 1087.5) < 0.2
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-3
+    ipa = extra["ipa_pair_attention"]
+    assert ipa["bound"] == "hbm" and abs(ipa["achieved"] - 4173.3) < 0.5 and abs(ipa["moved_gbs"] - 5074.5) < 0.5
+    assert "bound" not in extra["gemm_tc"] and abs(sum(r["share_of_profiled"] for r in extra.values()) - 1.0) < 2e-3
+    if roof["traffic"] is not None:      # committed ncu capture: DRAM traffic of the dominant kernel matches its algorithmic bytes
+        assert abs(roof["traffic"] / extra["edge_transition"]["algorithmic_bytes"] - 1.0) < 0.05
