@@ -14,8 +14,9 @@ are kept: frames are built in fp64 from the parsed coordinates, ROUNDED TO fp32 
 rigid_utils.py:327-331,902), and the torsion frames are inverted in fp32 before they meet the fp64 fourth atom.
 One-off per protein, host side, torch CPU; pinned to the unmodified reference by tests/golden/featurize_*.npz.
 
-Not produced (training-loss inputs that `predict_step` never reads): chi_angles_sin_cos / chi_mask (they are views of
-torsion_angles_sin_cos[3:]), pseudo_beta, atom14_* tables.
+All 34 tensors of the reference transform are produced (the sampling path reads seven of them; the chi / pseudo-beta / atom14
+features are the training losses' inputs: data_transforms.py:370-402 `make_pseudo_beta`, :575-646 `make_atom14_masks`, :656-757
+`make_atom14_positions`, :1103-1110 `get_chi_angles`).
 """
 from __future__ import annotations
 
@@ -72,6 +73,42 @@ def _tables():
 
 
 CHI_ATOM_IDX, CHI_MASK, CHI_PI_PERIODIC, GROUP_BASE_ATOMS, GROUP_MASK, GROUP_AMBIGUOUS = _tables()
+
+# heavy atoms of each residue type in atom14 order (residue_constants.py:504-527) and the pairs whose names are interchangeable (:369-374)
+_ATOM14 = {
+    "ALA": "N CA C O CB", "ARG": "N CA C O CB CG CD NE CZ NH1 NH2", "ASN": "N CA C O CB CG OD1 ND2", "ASP": "N CA C O CB CG OD1 OD2",
+    "CYS": "N CA C O CB SG", "GLN": "N CA C O CB CG CD OE1 NE2", "GLU": "N CA C O CB CG CD OE1 OE2", "GLY": "N CA C O",
+    "HIS": "N CA C O CB CG ND1 CD2 CE1 NE2", "ILE": "N CA C O CB CG1 CG2 CD1", "LEU": "N CA C O CB CG CD1 CD2",
+    "LYS": "N CA C O CB CG CD CE NZ", "MET": "N CA C O CB CG SD CE", "PHE": "N CA C O CB CG CD1 CD2 CE1 CE2 CZ", "PRO": "N CA C O CB CG CD",
+    "SER": "N CA C O CB OG", "THR": "N CA C O CB OG1 CG2", "TRP": "N CA C O CB CG CD1 CD2 NE1 CE2 CE3 CZ2 CZ3 CH2",
+    "TYR": "N CA C O CB CG CD1 CD2 CE1 CE2 CZ OH", "VAL": "N CA C O CB CG1 CG2",
+}
+_SWAPS = {"ASP": {"OD1": "OD2"}, "GLU": {"OE1": "OE2"}, "PHE": {"CD1": "CD2", "CE1": "CE2"}, "TYR": {"CD1": "CD2", "CE1": "CE2"}}
+
+
+def _atom14_tables():
+    a14_to_37 = np.zeros((21, 14), np.int64)
+    a37_to_14 = np.zeros((21, 37), np.int64)
+    a14_mask = np.zeros((21, 14), np.float32)
+    a37_mask = np.zeros((21, 37), np.float32)
+    rename = np.tile(np.eye(14), (21, 1, 1))
+    ambiguous = np.zeros((21, 14), np.float64)
+    for r, name in enumerate(RESNAMES):
+        names = _ATOM14[name].split()
+        for i, a in enumerate(names):
+            a14_to_37[r, i] = ATOM_ORDER[a]
+            a37_to_14[r, ATOM_ORDER[a]] = i
+            a14_mask[r, i] = 1.0
+            a37_mask[r, ATOM_ORDER[a]] = 1.0
+        for a, b in _SWAPS.get(name, {}).items():
+            i, j = names.index(a), names.index(b)
+            rename[r, i, i] = rename[r, j, j] = 0.0
+            rename[r, i, j] = rename[r, j, i] = 1.0
+            ambiguous[r, i] = ambiguous[r, j] = 1.0
+    return a14_to_37, a37_to_14, a14_mask, a37_mask, rename, ambiguous
+
+
+ATOM14_TO_37, ATOM37_TO_14, ATOM14_MASK, ATOM37_MASK, ATOM14_RENAME, ATOM14_AMBIGUOUS = _atom14_tables()
 
 
 # --- PDB text -> atom37 arrays ---------------------------------------------------------------------------------------
@@ -236,6 +273,28 @@ def atom37_to_torsion_angles(aatype: torch.Tensor, pos: torch.Tensor, mask: torc
     return {"torsion_angles_sin_cos": sc, "alt_torsion_angles_sin_cos": sc * mirror[..., None], "torsion_angles_mask": tmask}
 
 
+def pseudo_beta_and_atom14(aatype: torch.Tensor, pos: torch.Tensor, mask: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Pseudo-beta (CB, CA for glycine; data_transforms.py:370-387) and the dense 14-atom view of the atom37 arrays with its
+    renamed alternative for the residues whose atom names are interchangeable (:575-757)."""
+    L = aatype.shape[0]
+    is_gly = aatype == RESNAME_TO_IDX["GLY"]
+    ca, cb = ATOM_ORDER["CA"], ATOM_ORDER["CB"]
+    out = {"pseudo_beta": torch.where(is_gly[:, None], pos[:, ca], pos[:, cb]), "pseudo_beta_mask": torch.where(is_gly, mask[:, ca], mask[:, cb])}
+    a14_to_37 = torch.as_tensor(ATOM14_TO_37)[aatype]
+    exists14 = torch.as_tensor(ATOM14_MASK)[aatype]
+    ar = torch.arange(L)[:, None]
+    gt_exists = exists14 * mask[ar, a14_to_37]
+    gt_pos = gt_exists[..., None] * pos[ar, a14_to_37]
+    rename = torch.as_tensor(ATOM14_RENAME, dtype=mask.dtype)[aatype]
+    out.update({
+        "atom14_atom_exists": exists14, "residx_atom14_to_atom37": a14_to_37, "residx_atom37_to_atom14": torch.as_tensor(ATOM37_TO_14)[aatype],
+        "atom37_atom_exists": torch.as_tensor(ATOM37_MASK)[aatype], "atom14_gt_exists": gt_exists, "atom14_gt_positions": gt_pos,
+        "atom14_alt_gt_positions": torch.einsum("rac,rab->rbc", gt_pos, rename), "atom14_alt_gt_exists": torch.einsum("ra,rab->rb", gt_exists, rename),
+        "atom14_atom_is_ambiguous": torch.as_tensor(ATOM14_AMBIGUOUS, dtype=mask.dtype)[aatype],
+    })
+    return out
+
+
 class ProteinFeatureTransform:
     """Same constructor keys as the reference's class (configs/data/sampling.yaml:8-13; dataset.py:26-47) and the same
     order of operations in `__call__` (:49-68)."""
@@ -277,6 +336,9 @@ class ProteinFeatureTransform:
         t.update(atom37_to_torsion_angles(t["aatype"], t["atom_positions"], t["atom_mask"]))
         t["backbone_rigid_tensor"] = t["rigidgroups_gt_frames"][..., 0, :, :]
         t["backbone_rigid_mask"] = t["rigidgroups_gt_exists"][..., 0]
+        t["chi_angles_sin_cos"] = t["torsion_angles_sin_cos"][..., 3:, :].to(t["atom_mask"].dtype)
+        t["chi_mask"] = t["torsion_angles_mask"][..., 3:].to(t["atom_mask"].dtype)
+        t.update(pseudo_beta_and_atom14(t["aatype"].clamp(max=20), t["atom_positions"], t["atom_mask"]))
         return t
 
 

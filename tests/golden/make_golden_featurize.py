@@ -40,7 +40,9 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 KEYS = ["aatype", "residue_index", "residue_idx", "chain_index", "atom_positions", "atom_mask", "seq_mask", "residue_mask", "fixed_mask",
         "sc_ca_t", "rigidgroups_gt_frames", "rigidgroups_gt_exists", "rigidgroups_group_exists", "rigidgroups_group_is_ambiguous",
         "rigidgroups_alt_gt_frames", "torsion_angles_sin_cos", "alt_torsion_angles_sin_cos", "torsion_angles_mask",
-        "backbone_rigid_tensor", "backbone_rigid_mask"]
+        "backbone_rigid_tensor", "backbone_rigid_mask", "b_factors", "chi_angles_sin_cos", "chi_mask", "pseudo_beta", "pseudo_beta_mask",
+        "atom14_atom_exists", "residx_atom14_to_atom37", "residx_atom37_to_atom14", "atom37_atom_exists", "atom14_gt_exists",
+        "atom14_gt_positions", "atom14_alt_gt_positions", "atom14_alt_gt_exists", "atom14_atom_is_ambiguous"]
 
 
 def check_tables():
@@ -91,6 +93,7 @@ def synthetic_protein(L, seed, unk_ends=0, missing=True, two_chains=False):
 
 def run_ref(raw, **kw):
     out = RefTransform(**kw)({k: np.array(v) for k, v in raw.items()})
+    assert sorted(out.keys()) == sorted(KEYS), sorted(set(out.keys()) ^ set(KEYS))   # every tensor of the reference transform is pinned
     return {k: out[k].numpy() for k in KEYS}
 
 

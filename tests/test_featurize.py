@@ -36,7 +36,7 @@ def test_transform_matches_reference(path):
     kw = ast.literal_eval(str(g["transform_kwargs"]))
     out = F.ProteinFeatureTransform(**kw)(F.parse_pdb_string(str(g["pdb_text"])))
     keys = [k[4:] for k in g.files if k.startswith("out_")]
-    assert len(keys) == 20
+    assert len(keys) == 34   # every tensor of the reference transform
     for k in keys:
         ref, got = g[f"out_{k}"], out[k].numpy()
         assert got.shape == ref.shape and got.dtype == ref.dtype, (k, got.shape, ref.shape, got.dtype, ref.dtype)
