@@ -15,7 +15,7 @@
 // through mbarriers only.  Same arithmetic and rounding points as the first generation (and as pair_simt.cu), except
 // that the LayerNorm statistics are taken in one shifted pass (sum and sum of squares of y - y_0).
 //
-// What bounded the first cut of this pipeline (ncu, profiles/r01c_ncu_edge_embed.txt): the LSU data pipe at 76 % of its
+// What bounded the first cut of this pipeline (ncu, profiles/r01c_gemm_and_embedder_experiments.log): the LSU data pipe at 76 % of its
 // wavefront rate, not latency.  Row-per-thread 16-byte global stores cost 32 wavefronts each (32 different 128-byte
 // lines), and every warp-uniform shared-memory read of a bias / LayerNorm parameter costs 2.  So the output rows are
 // turned through a swizzled shared-memory buffer and leave as 512-byte contiguous pieces, and b2 / b3 / ln_w / ln_b sit
