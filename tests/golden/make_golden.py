@@ -107,8 +107,26 @@ def npz(name, **arrs):
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def trajectory(net, diffuser, name, B, L, n, n_pad, n_fixed, seed):
+    """Full forward-backward trajectory of the unmodified reference from a perturbation drawn at fixed seeds."""
+    feats = synthetic.make_features(B, L, seed=seed, n_pad=n_pad, n_fixed=n_fixed, random_aatype=True)
+    q, x = synthetic.make_backbone(L, seed=seed)
+    r0 = rigid_from_quat_trans(q[None].repeat(B, 1, 1), x[None].repeat(B, 1, 1))
+    torch.manual_seed(123)
+    np.random.seed(123)
+    rigids_t = diffuser.forward_marginal(rigids_0=r0, t=0.5 * torch.ones(B), diffuse_mask=feats["residue_mask"],
+                                         as_tensor_7=True)["rigids_t"]
+    fin, psi, atom37, sig = reference_forward_backward(net, diffuser, feats, rigids_t, 0.5, 2 * n)
+    npz(name, rigids_t=rigids_t, final_rigids=fin, final_psi=psi, final_atom37=atom37[..., :5, :], sigma_idx=sig,
+        meta=np.array([B, L, n, n_pad, n_fixed, seed]))
+
+
 def main():
     net, diffuser = build_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "traj128":
+        # a chain length the tcgen05 pair kernels take (L % 128 == 0), two decoys, padded tail: 20 denoising steps
+        trajectory(net, diffuser, "traj_L128_n20.npz", 2, 128, 20, 4, 0, 9)
+        return
 
     # --- A. one network forward, small, with padding / fixed residues / chain break / mixed aatype --------
     B, L = 2, 12
@@ -172,20 +190,9 @@ def main():
         sigma_idx_grid=sig, cdf_row_500=diffuser.rot_diffuser._cdf[500].numpy())
 
     # --- C. cfg 1 of BASELINE.json: L=64, B=1, 10 denoise steps, full trajectory --------------------------
-    def trajectory(name, B, L, n, n_pad, n_fixed, seed):
-        feats = synthetic.make_features(B, L, seed=seed, n_pad=n_pad, n_fixed=n_fixed, random_aatype=True)
-        q, x = synthetic.make_backbone(L, seed=seed)
-        r0 = rigid_from_quat_trans(q[None].repeat(B, 1, 1), x[None].repeat(B, 1, 1))
-        torch.manual_seed(123)
-        np.random.seed(123)
-        rigids_t = diffuser.forward_marginal(rigids_0=r0, t=0.5 * torch.ones(B), diffuse_mask=feats["residue_mask"],
-                                             as_tensor_7=True)["rigids_t"]
-        fin, psi, atom37, sig = reference_forward_backward(net, diffuser, feats, rigids_t, 0.5, 2 * n)
-        npz(name, rigids_t=rigids_t, final_rigids=fin, final_psi=psi, final_atom37=atom37[..., :5, :], sigma_idx=sig,
-            meta=np.array([B, L, n, n_pad, n_fixed, seed]))
-
-    trajectory("traj_cfg1_L64_n10.npz", 1, 64, 10, 0, 0, 7)
-    trajectory("traj_masked_L24_n6.npz", 2, 24, 6, 3, 2, 5)
+    trajectory(net, diffuser, "traj_cfg1_L64_n10.npz", 1, 64, 10, 0, 0, 7)
+    trajectory(net, diffuser, "traj_masked_L24_n6.npz", 2, 24, 6, 3, 2, 5)
+    trajectory(net, diffuser, "traj_L128_n20.npz", 2, 128, 20, 4, 0, 9)
 
 
 if __name__ == "__main__":

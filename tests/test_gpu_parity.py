@@ -198,6 +198,13 @@ def test_trajectory_masked_vs_reference_golden(golden_dir, params):
     _run_traj(golden_dir, params, "traj_masked_L24_n6.npz", (1, 1), True)
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_trajectory_L128_vs_reference_golden(golden_dir, params, graph):
+    """128 residues x 20 denoise steps, 2 decoys with a padded tail: the tcgen05 pair kernels (L % 128 == 0), the panel GEMMs and
+    the fused IPA kernel against a trajectory of the UNMODIFIED reference — final C-alpha within 1e-4 relative."""
+    _run_traj(golden_dir, params, "traj_L128_n20.npz", (1, 1), graph)
+
+
 @pytest.mark.parametrize("L", [128, 256, 384])
 def test_pair_kernels_tc_vs_simt(params, L):
     """tcgen05 pair kernels against the SIMT restatement with identical rounding points, full forward."""
