@@ -43,16 +43,20 @@ int s2s_set_param(s2s_ctx* ctx, const char* name, const float* data, int64_t num
 /* Check that all 274 tensors are present with the right sizes and build the derived device tensors
  * (bf16 / split / transposed weight images, concatenated projections, softplus head weights). */
 int s2s_finalize(s2s_ctx* ctx, void* stream);
-/* Options: "pair_kernels" 0 = SIMT cross-check kernels, 1 = tcgen05 kernels (default), 2 = tcgen05 with the
- *                         first-generation EdgeTransition kernel (serial MMA/epilogue; kept for A/B timing);
- *          "node_gemm"    0 = exact fp32 FFMA everywhere, 1 = tensor-core GEMMs where the parity budget allows;
- *          "ipa_kernels"  1 = second-generation IPA path (default; needs node_gemm = 1, L <= 256, L % 16 == 0, other shapes
- *                         fall back automatically): point-attention term folded into the logits GEMM, persistent TMA +
- *                         tcgen05 pair kernel, split-bf16 attention weights; 0 = first-generation kernels (A/B, tests). */
+/* Options: "pair_kernels" 1 = tcgen05 pair kernels (default), 0 = SIMT cross-check kernels (tests);
+ *          "node_gemm"    1 = tensor-core GEMMs where the parity budget allows (default), 0 = exact fp32 FFMA everywhere (tests);
+ *          "ipa_kernels"  1 = second-generation IPA path (default; needs node_gemm = 1 and L <= 512, longer chains fall back
+ *                         automatically): point-attention term folded into the logits GEMM, persistent TMA + tcgen05 pair kernel,
+ *                         split-bf16 attention weights; 0 = first-generation kernels (A/B, tests). */
 int s2s_set_option(s2s_ctx* ctx, const char* key, int value);
 /* Size the workspace for (B, L) and build the relative-position table for residue-index offsets in
- * [d_min, d_max] (= min/max of residue_idx[i] - residue_idx[j]).  Must be called before s2s_net_forward and
- * outside CUDA-graph capture; calling it again with a larger shape re-allocates. */
+ * [d_min, d_max] (= min/max of residue_idx[i] - residue_idx[j]); d_max < d_min keeps the table already planned
+ * (shape-only call).  Must be called before the forward entry points and outside CUDA-graph capture; the
+ * allocation only ever grows (a larger B, L or offset range re-allocates; smaller shapes reuse it).
+ * ANY chain length L >= 1 is accepted by every entry point: the tensor-core kernels tile chains in units of 32
+ * residues, other lengths are padded inside the library with residues that take part in no reduction (mask 0
+ * for IPA / pair rows, removed from the sequence transformer's keys), so results equal the un-padded computation
+ * of the reference; offsets outside the planned range are clamped to the table (never read out of bounds). */
 int s2s_reserve(s2s_ctx* ctx, int B, int L, int d_min, int d_max, void* stream);
 
 /* ---- score network ------------------------------------------------------------------------------------------
@@ -83,6 +87,13 @@ int s2s_ipa(s2s_ctx* ctx, int blk, int B, int L, const float* node, const void* 
 int s2s_edge_transition(s2s_ctx* ctx, int blk, int B, int L, const float* node, const void* z_in,
                         const float* residue_mask, void* z_out, void* stream);
 
+/* Module-level pieces of the trunk on `rows` residue rows [rows,256] (rows <= reserved B * L), for drop-in use of the
+ * reference's sub-modules: NodeTransition.forward (layers.py:138-145) -> out [rows,256]; TorsionAngleHead.forward
+ * (layers.py:199-213) -> out [rows,2]; BackboneUpdate.forward (layers.py:232-241) -> out [rows,6]. */
+int s2s_node_transition(s2s_ctx* ctx, int blk, int64_t rows, const float* s, float* out, void* stream);
+int s2s_torsion_head(s2s_ctx* ctx, int64_t rows, const float* s, float* out, void* stream);
+int s2s_backbone_update(s2s_ctx* ctx, int blk, int64_t rows, const float* s, float* out, void* stream);
+
 /* ---- SE(3) diffusion step ------------------------------------------------------------------------------------
  * FrameDiffuser.score + FrameDiffuser.reverse (reference src/models/score/frame.py:109-210).
  * Per-decoy schedule scalars are computed by the host exactly as the reference computes them (same torch ops,
@@ -103,6 +114,12 @@ int s2s_se3_step(int B, int L, const float* rigids_t, const float* rigids_0, con
 int s2s_se3_perturb(int B, int L, const float* rot0, const float* trans0, const float* diffuse_mask,
                     const float* sched_f, const double* cdf, const float* omega_grid, const float* axis_noise,
                     const float* u_noise, const float* trans_noise, float* rigids_out, void* stream);
+/* Random draws keyed by GLOBAL decoy id (replaces the torch.randn / torch.rand calls of so3.py:259-262, r3.py:66,109):
+ * out [B][n_per_decoy] fp32; decoy b of the call is decoy first_decoy + b of the job and reads Philox4x32-10 subsequence
+ * (first_decoy + b) of `seed`, block `stream_id` (0 axis, 1 angle quantile, 2 translation of the perturbation; 16 + 2k / 17 + 2k
+ * rotation / translation noise of SDE iteration k).  uniform = 0: N(0,1); 1: U[0,1).  A decoy's draws therefore do not depend
+ * on the batch, rank or world size it is sampled in. */
+int s2s_rng_fill(float* out, int B, int64_t n_per_decoy, uint64_t seed, int64_t first_decoy, int stream_id, int uniform, void* stream);
 /* compute_backbone (reference src/common/all_atom.py:141-173): atom37 [B,L,37,3], atom14 [B,L,14,3] (nullable).
  * aatype may be NULL (all alanine, as the reference does for aatype=None). */
 int s2s_backbone_atoms(s2s_ctx* ctx, int rows, const float* rigids, const float* psi, const int64_t* aatype,

@@ -30,8 +30,12 @@ SIGNATURES = {
     "s2s_embed": (_i, [_vp, _i, _i] + [_vp] * 8),
     "s2s_ipa": (_i, [_vp, _i, _i, _i] + [_vp] * 7),
     "s2s_edge_transition": (_i, [_vp, _i, _i, _i] + [_vp] * 5),
+    "s2s_node_transition": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "s2s_torsion_head": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "s2s_backbone_update": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "s2s_se3_step": (_i, [_i, _i] + [_vp] * 8 + [_f, _i, _i] + [_vp] * 4),
     "s2s_se3_perturb": (_i, [_i, _i] + [_vp] * 11),
+    "s2s_rng_fill": (_i, [_vp, _i, _i64, C.c_uint64, _i64, _i, _i, _vp]),
     "s2s_backbone_atoms": (_i, [_vp, _i] + [_vp] * 6),
     "s2s_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "s2s_linear_tc": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
@@ -72,19 +76,35 @@ def check(rc: int) -> None:
         raise RuntimeError("str2str_b200: " + load().s2s_last_error().decode())
 
 
-def ptr(t):
-    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+def ptr(t, dtype=torch.float32):
+    """Device pointer of a contiguous CUDA tensor of the dtype the kernel reads (None -> NULL).  The kernels reinterpret the
+    bytes, so a tensor of another dtype is an error here rather than garbage there."""
     if t is None:
         return None
     if not t.is_cuda:
         raise ValueError("str2str_b200 kernels take CUDA tensors; got a CPU tensor (no CPU fallback exists)")
     if not t.is_contiguous():
         raise ValueError("tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"kernel argument must be {dtype}, got {t.dtype}: cast at the call site")
     return C.c_void_p(t.data_ptr())
 
 
-def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def ptr_i64(t):
+    return ptr(t, torch.int64)
+
+
+def ptr_bf16(t):
+    return ptr(t, torch.bfloat16)
+
+
+def ptr_f64(t):
+    return ptr(t, torch.float64)
+
+
+def stream(device=None):
+    """Current torch stream of `device` (default: the current device)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def f32(t, device=None):

@@ -104,7 +104,7 @@ struct IpaW {
 };
 struct EtW {
   bf16 *W1z, *W2, *Wfh, *Wfz, *W1zt, *W2t, *Wft, *Wfzt;
-  bf16 *wimg, *wimg2, *wimg3;  // tcgen05 weight images (first / second / third generation kernel)
+  bf16* wimg3;  // tcgen05 weight image (pre-swizzled blocks in consumption order), wimg_copies replicas
 };
 
 }  // namespace
@@ -115,7 +115,7 @@ using namespace s2s;
 struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
-  int opt_pair = 1, opt_node = 0, opt_ipa = 1;
+  int opt_pair = 1, opt_node = 1, opt_ipa = 1;
   int tfm_passes = 1;  // sequence-transformer in_proj + attention GEMMs: 1 = single bf16 (default; trajectory error unchanged, tools/traj_parity.py), 3 = split-bf16 (S2S_TFM_PASSES=3)
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
@@ -128,7 +128,11 @@ struct s2s_ctx {
   float* ee_vec;  // [b2 | b3 | ln_w | ln_b] packed (4 x 128): one copy into the pipelined embedder's constant bank per call
   // workspace
   Slab ws;
-  int cap_B = 0, cap_L = 0, d_min = 0, n_off = 0;
+  int cap_B = 0, cap_L = 0, d_min = 0, n_off = 0, cap_off = 0;  // cap_L is a padded length (pad_len)
+  // internal chain-length padding: padded copies [B][Lp] of the per-residue inputs / outputs; `hard` marks real rows
+  float *pd_rig, *pd_sc, *pd_rmask, *pd_fixed, *pd_psi, *pd_hard, *pd_orig, *pd_opsi;
+  long long* pd_ridx;
+  const float* hard = nullptr;  // non-null while a padded call is running
   float *feat65, *tf33, *node, *init_node, *a256, *b256, *proj, *feats, *q_pts, *k_pts, *v_pts, *S, *opt;
   float *skip64, *x320, *t320, *y320, *qkv, *nprime, *u384, *v384, *p128, *q128, *Ti, *Tj, *Tpos, *relfeat;
   float *quat, *trans, *upd6, *psi_u, *diffuse, *keybias;
@@ -153,6 +157,19 @@ struct s2s_ctx {
 namespace {
 
 enum Prec { EXACT = 0, TC3 = 3, TC1 = 1 };
+// RAII marker of a padded call: c->hard is non-null exactly while the padded stages run (also on error paths)
+struct HardScope {
+  s2s_ctx* c;
+  HardScope(s2s_ctx* ctx, const float* hard) : c(ctx) { c->hard = hard; }
+  ~HardScope() { c->hard = nullptr; }
+};
+
+struct PrecScope {
+  s2s_ctx* c;
+  PrecScope(s2s_ctx* ctx, int p) : c(ctx) { c->cur_prec = p; }
+  ~PrecScope() { c->cur_prec = EXACT; }
+};
+
 struct Split { bf16* hi = nullptr; bf16* lo = nullptr; };  // split-bf16 image of an fp32 activation (dense, pitch = width)
 
 // bf16 (hi, lo) image of a weight (or of a sub-block of one) registered at finalize
@@ -289,17 +306,10 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
       prep_split(W2, 384, 384, 0, 384, x.W2, nullptr, st);   prep_t_bf16(W2, 384, 384, 0, 384, x.W2t, st);
       prep_split(Wf, 384, 128, 0, 384, x.Wfh, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 384, x.Wft, st);
       prep_split(Wf, 384, 128, 0, 128, x.Wfz, nullptr, st);  prep_t_bf16(Wf, 384, 128, 0, 128, x.Wfzt, st);
-      x.wimg = c->wslab.take<bf16>(et_wimg_elems() * c->wimg_copies);
-      build_et_wimg(W1, W2, Wf, x.wimg, st);
-      x.wimg2 = c->wslab.take<bf16>(et2_wimg_elems() * c->wimg_copies);
-      build_et2_wimg(W1, W2, Wf, x.wimg2, st);
       x.wimg3 = c->wslab.take<bf16>(et3_wimg_elems() * c->wimg_copies);
       build_et3_wimg(W1, W2, Wf, x.wimg3, st);
-      for (int k = 1; k < c->wimg_copies; ++k) {
+      for (int k = 1; k < c->wimg_copies; ++k)
         S2S_CUDA(cudaMemcpyAsync(x.wimg3 + k * et3_wimg_elems(), x.wimg3, et3_wimg_elems() * 2, cudaMemcpyDeviceToDevice, st));
-        S2S_CUDA(cudaMemcpyAsync(x.wimg + k * et_wimg_elems(), x.wimg, et_wimg_elems() * 2, cudaMemcpyDeviceToDevice, st));
-        S2S_CUDA(cudaMemcpyAsync(x.wimg2 + k * et2_wimg_elems(), x.wimg2, et2_wimg_elems() * 2, cudaMemcpyDeviceToDevice, st));
-      }
     }
   }
   {
@@ -344,31 +354,46 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
   c->finalized = true;
 }
 
-void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st) {
+// Chain lengths run on the tensor-core tiling: the pair kernels tile the flattened pair tensor in 32-row segments that must
+// not straddle an i row, the batched attention GEMMs need K = L % 16 == 0.  Other lengths are padded INSIDE the library
+// (pad_inputs / repitch_* in rows.cu) and come back un-padded; results equal the un-padded computation because appended
+// residues are excluded from every reduction over residues (see rows.cu: masks_kernel, pad_inputs_kernel).
+int pad_len(int L) { return (L + 31) & ~31; }
+
+void do_reserve(s2s_ctx* c, int B, int L_user, int d_min, int d_max, cudaStream_t st) {
   S2S_CHECK(c->finalized, "s2s_finalize must run before s2s_reserve");
-  S2S_CHECK(B > 0 && L > 0 && d_max >= d_min, "reserve: bad shape");
+  S2S_CHECK(B > 0 && L_user > 0, "reserve: bad shape");
+  const int L = pad_len(L_user);
+  const bool keep_table = d_max < d_min;  // shape only: the relative-position table stays as planned (or the 1-row default)
+  if (keep_table) {
+    d_min = c->ws.base ? c->d_min : 0;
+    d_max = c->ws.base ? c->d_min + c->n_off - 1 : 0;
+  }
   const int n_off = d_max - d_min + 1;
-  if (!(B <= c->cap_B && L <= c->cap_L && c->d_min == d_min && c->n_off == n_off && c->ws.base)) {
+  if (!(B <= c->cap_B && L <= c->cap_L && n_off <= c->cap_off && c->ws.base)) {
     if (c->ws.base) S2S_CUDA(cudaDeviceSynchronize());
     c->ws.release();
-    const size_t R = (size_t)B * L;
+    B = std::max(B, c->cap_B);  // never shrink: an engine alternating between shapes settles on one allocation
+    const int Lc = std::max(L, c->cap_L), cap_off = std::max(n_off, c->cap_off);
+    const size_t R = (size_t)B * Lc;
     size_t bytes = 0;
     auto add = [&](size_t n, size_t sz) { bytes += ((n * sz + 255) & ~size_t(255)) + 256; };
     add(R * 65, 4); add(R * 33, 4); for (int k = 0; k < 4; ++k) add(R * 256, 4);
     add(R * 6816, 4); add(R * IPA_FEAT, 4); add(R * 192, 4); add(R * 192, 4); add(R * 288, 4);
-    add((size_t)B * N_H * L * L, 4); add(R * 288, 4);
+    add((size_t)B * N_H * Lc * Lc, 4); add(R * 288, 4);
     add(R * 64, 4); for (int k = 0; k < 3; ++k) add(R * 320, 4); add(R * 960, 4);
     add(R * 128, 4); add(R * 384, 4); add(R * 384, 4); add(R * 128, 4); add(R * 128, 4); add(R * 128, 4); add(R * 128, 4);
-    add((size_t)n_off * 128, 4); add((size_t)n_off * 32, 4);
+    add((size_t)cap_off * 128, 4); add((size_t)cap_off * 32, 4);
     add(R * 4, 4); add(R * 3, 4); add(R * 6, 4); add(R * 2, 4); add(R, 4); add(R, 4);
-    add(R * L * C_Z, 2); add(R * 128, 2);
-    add(R * IPA_FEAT, 2); add(R * IPA_FEAT, 2); add(R * 6144, 2); add(R * 2048, 2); add((size_t)B * N_H * L * L, 2);
-    add(R * 960, 2); add(R * 960, 2); add(R * 320, 2); add(R * 320, 2); add((size_t)B * TFM_H * L * L, 2);
+    add(R * Lc * C_Z, 2); add(R * 128, 2);
+    add(R * IPA_FEAT, 2); add(R * IPA_FEAT, 2); add(R * 6144, 2); add(R * 2048, 2); add((size_t)B * N_H * Lc * Lc, 2);
+    add(R * 960, 2); add(R * 960, 2); add(R * 320, 2); add(R * 320, 2); add((size_t)B * TFM_H * Lc * Lc, 2);
     for (int k = 0; k < 8; ++k) add(R * 256, 2);
     for (int k = 0; k < 6; ++k) add(R * 320, 2);
     add(R * 128, 2);
     add(R * N_H * PT_K, 2); add(R * N_H * PT_K, 2); add(R * N_H * VP_PITCH, 2); add(R * N_H * VP_PITCH, 2);
-    add((size_t)B * N_H * L * L, 2); add(R * N_H, 4);
+    add((size_t)B * N_H * Lc * Lc, 2); add(R * N_H, 4);
+    add(R * 7, 4); add(R * 3, 4); add(R, 4); add(R, 4); add(R * 2, 4); add(R, 4); add(R * 7, 4); add(R * 2, 4); add(R, 8);
     c->ws.cap = bytes + 4096;
     S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
     Slab& w = c->ws;
@@ -376,20 +401,20 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->node = w.take<float>(R * 256); c->init_node = w.take<float>(R * 256); c->a256 = w.take<float>(R * 256); c->b256 = w.take<float>(R * 256);
     c->proj = w.take<float>(R * 6816); c->feats = w.take<float>(R * IPA_FEAT);
     c->q_pts = w.take<float>(R * 192); c->k_pts = w.take<float>(R * 192); c->v_pts = w.take<float>(R * 288);
-    c->S = w.take<float>((size_t)B * N_H * L * L); c->opt = w.take<float>(R * 288);
+    c->S = w.take<float>((size_t)B * N_H * Lc * Lc); c->opt = w.take<float>(R * 288);
     c->skip64 = w.take<float>(R * 64); c->x320 = w.take<float>(R * 320); c->t320 = w.take<float>(R * 320); c->y320 = w.take<float>(R * 320);
     c->qkv = w.take<float>(R * 960);
     c->nprime = w.take<float>(R * 128); c->u384 = w.take<float>(R * 384); c->v384 = w.take<float>(R * 384);
     c->p128 = w.take<float>(R * 128); c->q128 = w.take<float>(R * 128); c->Ti = w.take<float>(R * 128); c->Tj = w.take<float>(R * 128);
-    c->Tpos = w.take<float>((size_t)n_off * 128); c->relfeat = w.take<float>((size_t)n_off * 32);
+    c->Tpos = w.take<float>((size_t)cap_off * 128); c->relfeat = w.take<float>((size_t)cap_off * 32);
     c->quat = w.take<float>(R * 4); c->trans = w.take<float>(R * 3); c->upd6 = w.take<float>(R * 6); c->psi_u = w.take<float>(R * 2);
     c->diffuse = w.take<float>(R); c->keybias = w.take<float>(R);
-    c->z = w.take<bf16>(R * L * C_Z);
+    c->z = w.take<bf16>(R * Lc * C_Z);
     c->nprime_bf16 = w.take<bf16>(R * 128);
     c->sa_hi = w.take<bf16>(R * IPA_FEAT); c->sa_lo = w.take<bf16>(R * IPA_FEAT);
-    c->qkv_bf16 = w.take<bf16>(R * 6144); c->P_bf16 = w.take<bf16>((size_t)B * N_H * L * L);
+    c->qkv_bf16 = w.take<bf16>(R * 6144); c->P_bf16 = w.take<bf16>((size_t)B * N_H * Lc * Lc);
     c->tq_hi = w.take<bf16>(R * 960); c->tq_lo = w.take<bf16>(R * 960);
-    c->tP_lo = w.take<bf16>((size_t)B * TFM_H * L * L);
+    c->tP_lo = w.take<bf16>((size_t)B * TFM_H * Lc * Lc);
     c->node_hi = w.take<bf16>(R * 256); c->node_lo = w.take<bf16>(R * 256); c->init_hi = w.take<bf16>(R * 256); c->init_lo = w.take<bf16>(R * 256);
     c->a256_hi = w.take<bf16>(R * 256); c->a256_lo = w.take<bf16>(R * 256); c->b256_hi = w.take<bf16>(R * 256); c->b256_lo = w.take<bf16>(R * 256);
     c->x320_hi = w.take<bf16>(R * 320); c->x320_lo = w.take<bf16>(R * 320); c->t320_hi = w.take<bf16>(R * 320); c->t320_lo = w.take<bf16>(R * 320);
@@ -397,17 +422,23 @@ void do_reserve(s2s_ctx* c, int B, int L, int d_min, int d_max, cudaStream_t st)
     c->nprime_hi = c->nprime_bf16; c->nprime_lo = w.take<bf16>(R * 128);
     c->qp_aug = w.take<bf16>(R * N_H * PT_K); c->kp_aug = w.take<bf16>(R * N_H * PT_K);
     c->vp_hi = w.take<bf16>(R * N_H * VP_PITCH); c->vp_lo = w.take<bf16>(R * N_H * VP_PITCH);
-    c->P_lo = w.take<bf16>((size_t)B * N_H * L * L); c->colbias = w.take<float>(R * N_H);
-    c->cap_B = B; c->cap_L = L; c->d_min = d_min; c->n_off = n_off;
+    c->P_lo = w.take<bf16>((size_t)B * N_H * Lc * Lc); c->colbias = w.take<float>(R * N_H);
+    c->pd_rig = w.take<float>(R * 7); c->pd_sc = w.take<float>(R * 3); c->pd_rmask = w.take<float>(R); c->pd_fixed = w.take<float>(R);
+    c->pd_psi = w.take<float>(R * 2); c->pd_hard = w.take<float>(R); c->pd_orig = w.take<float>(R * 7); c->pd_opsi = w.take<float>(R * 2);
+    c->pd_ridx = w.take<long long>(R);
+    c->cap_B = B; c->cap_L = Lc; c->cap_off = cap_off;
+    c->n_off = 0;  // the table memory is new: rebuild it below
   }
+  if (keep_table && c->n_off == n_off && c->d_min == d_min) return;
   // relative-position table: Tpos[r] = W1[:,66:98] pos(d_min + r)   (denoising_ipa.py:144-149)
+  c->d_min = d_min; c->n_off = n_off;
   relpos_features(c->pdenom, c->relfeat, d_min, n_off, st);
   linear(c, c->relfeat, 32, c->P("embedder.edge_embed.0.weight") + 66, 120, nullptr, c->Tpos, 128, n_off, 128, 32, st);
 }
 
 void check_shape(const s2s_ctx* c, int B, int L) {
   S2S_CHECK(c->finalized, "context not finalized");
-  S2S_CHECK(c->ws.base && B <= c->cap_B && L <= c->cap_L && B > 0 && L > 0,
+  S2S_CHECK(c->ws.base && B <= c->cap_B && pad_len(L) <= c->cap_L && B > 0 && L > 0,
             "workspace too small: call s2s_reserve(B, L, ...) first");
 }
 
@@ -430,17 +461,17 @@ void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, c
   linear(c, c->tf33, 33, W1, 120, c->P(ee + "0.bias"), c->Ti, 128, R, 128, 33, st);
   linear(c, c->tf33, 33, W1 + 33, 120, nullptr, c->Tj, 128, R, 128, 33, st);
   EdgeEmbedArgs a;
-  a.B = B; a.L = L; a.d_min = c->d_min;
+  a.B = B; a.L = L; a.d_min = c->d_min; a.n_off = c->n_off;
   a.Ti = c->Ti; a.Tj = c->Tj; a.Tpos = c->Tpos; a.Wd = c->ee_Wd; a.bin_lower = c->bin_lower;
   a.sc_ca = sc_ca; a.ridx = ridx; a.mask = rmask;
   a.W2 = c->ee_W2; a.W3 = c->ee_W3; a.W2t = c->ee_W2t; a.W3t = c->ee_W3t;
   a.b2 = c->P(ee + "2.bias"); a.b3 = c->P(ee + "4.bias"); a.ln_w = c->P(ee + "5.weight"); a.ln_b = c->P(ee + "5.bias");
   a.z_out = z_out; a.wimg = c->ee_wimg; a.vec4 = c->ee_vec;
-  // the tcgen05 kernels work on 128-row tiles of one (b, i): chain lengths that are not a multiple of 128 take the
-  // SIMT kernels (same inputs, same rounding points)
-  static const int ee_gen = [] { const char* e = getenv("S2S_EE_GEN"); return e ? atoi(e) : 2; }();  // 1: first-generation kernel (A/B)
-  if (c->opt_pair >= 1 && L % 128 == 0) {
-    if (c->opt_pair == 2 || ee_gen == 1) edge_embed_tc(a, st); else edge_embed_tc2(a, st);
+  // pair_kernels = 0 selects the SIMT cross-check kernels (same inputs, same rounding points); the tcgen05 kernel takes every
+  // chain length the public entry points hand down (they pad to a multiple of 32)
+  if (c->opt_pair >= 1) {
+    S2S_CHECK(L % 32 == 0, "internal: the tcgen05 edge embedder was handed an un-padded chain length");
+    edge_embed_tc2(a, st);
   } else edge_embed_simt(a, st);
 }
 
@@ -562,7 +593,8 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   const Split np = tcn ? Split{c->nprime_hi, c->nprime_lo} : Split();
   linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st, 0,
          nullptr, 0, nullptr, nullptr, -1, node_sp, np);
-  const bool tc = c->opt_pair >= 1 && L % 128 == 0;
+  const bool tc = c->opt_pair >= 1;
+  S2S_CHECK(!tc || L % 32 == 0, "internal: the tcgen05 EdgeTransition was handed an un-padded chain length");
   linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
   linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
   if (tc) {  // the n'_j terms ride along as extra K columns of the MMAs: they need n' in bf16 (= the hi image)
@@ -577,13 +609,8 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   a.W1z = w.W1z; a.W2 = w.W2; a.Wfh = w.Wfh; a.Wfz = w.Wfz;
   a.W1zt = w.W1zt; a.W2t = w.W2t; a.Wft = w.Wft; a.Wfzt = w.Wfzt;
   a.b2 = c->P(e + "trunk.2.bias"); a.ln_w = c->P(e + "layer_norm.weight"); a.ln_b = c->P(e + "layer_norm.bias");
-  a.z_out = z_out; a.wimg = w.wimg; a.wimg2 = w.wimg2; a.wimg3 = w.wimg3; a.wimg_copies = c->wimg_copies; a.nprime_bf16 = c->nprime_bf16;
-  if (!tc) edge_transition_simt(a, st);
-  else if (c->opt_pair == 2) edge_transition_tc(a, st);  // first-generation kernel (serial MMA / epilogue), kept for A/B
-  else {
-    static const int gen = [] { const char* e = getenv("S2S_ET_GEN"); return e ? atoi(e) : 3; }();  // 2: previous kernel (A/B)
-    if (gen == 2) edge_transition_tc2(a, st); else edge_transition_tc3(a, st);
-  }
+  a.z_out = z_out; a.wimg3 = w.wimg3; a.wimg_copies = c->wimg_copies; a.nprime_bf16 = c->nprime_bf16;
+  if (tc) edge_transition_tc3(a, st); else edge_transition_simt(a, st);
 }
 
 void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {
@@ -653,8 +680,8 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
               const float* gt_psi, float* out_rigids, float* out_psi, cudaStream_t st) {
   const int R = B * L;
   const std::string tk = "translator.trunk.";
-  make_masks(rmask, fixed, c->diffuse, c->keybias, R, st);
-  c->cur_prec = TC3;  // residual-stream layers: split-bf16 tensor-core GEMMs (exact fp32 when node_gemm = 0)
+  make_masks(rmask, fixed, c->hard, c->diffuse, c->keybias, R, st);
+  PrecScope prec_scope(c, TC3);  // residual-stream layers: split-bf16 tensor-core GEMMs (exact fp32 when node_gemm = 0)
   // Split-bf16 images of the activations are written by whichever kernel produces them (LayerNorm, GEMM epilogue,
   // concat), so the tensor-core GEMMs that consume them need no separate conversion pass.
   const bool img = c->opt_node == 1 && L % 16 == 0;
@@ -699,12 +726,39 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
   join_rigids(c->quat, c->trans, out_rigids, R, st);
 }
 
+// padded copies of the per-residue inputs (any of them may be null) into the context's pd_* buffers
+void pad_residue_inputs(s2s_ctx* c, int B, int L, int Lp, const float* rig, const float* sc, const long long* ridx, const float* rmask,
+                        const float* fixed, const float* psi, cudaStream_t st) {
+  PadInputs p;
+  p.B = B; p.L = L; p.Lp = Lp;
+  p.rig = rig; p.sc = sc; p.ridx = ridx; p.rmask = rmask; p.fixed = fixed; p.psi = psi;
+  p.o_rig = c->pd_rig; p.o_sc = c->pd_sc; p.o_ridx = c->pd_ridx; p.o_rmask = c->pd_rmask; p.o_fixed = c->pd_fixed; p.o_psi = c->pd_psi;
+  p.o_hard = c->pd_hard;
+  pad_inputs(p, st);
+}
+
 void do_forward(s2s_ctx* c, int B, int L, const float* rigids_t, const float* sc_ca, const float* t,
                 const long long* ridx, const float* rmask, const float* fixed, const float* gt_psi, float* out_rigids,
                 float* out_psi, cudaStream_t st) {
   check_shape(c, B, L);
-  do_embed(c, B, L, t, ridx, fixed, sc_ca, rmask, c->node, c->z, st);
-  do_trunk(c, B, L, rigids_t, rmask, fixed, gt_psi, out_rigids, out_psi, st);
+  const int Lp = pad_len(L);
+  if (Lp == L) {
+    do_embed(c, B, L, t, ridx, fixed, sc_ca, rmask, c->node, c->z, st);
+    do_trunk(c, B, L, rigids_t, rmask, fixed, gt_psi, out_rigids, out_psi, st);
+    return;
+  }
+  pad_residue_inputs(c, B, L, Lp, rigids_t, sc_ca, ridx, rmask, fixed, gt_psi, st);
+  HardScope hs(c, c->pd_hard);
+  do_embed(c, B, Lp, t, c->pd_ridx, c->pd_fixed, c->pd_sc, c->pd_rmask, c->node, c->z, st);
+  do_trunk(c, B, Lp, c->pd_rig, c->pd_rmask, c->pd_fixed, c->pd_psi, c->pd_orig, c->pd_opsi, st);
+  repitch_rows(c->pd_orig, out_rigids, B, Lp, L, 7, st);
+  repitch_rows(c->pd_opsi, out_psi, B, Lp, L, 2, st);
+}
+
+// ---- module-level pieces of the trunk (reference layers.py:138-145,199-213,232-241) on `rows` residue rows ----
+void check_rows(const s2s_ctx* c, long rows) {
+  S2S_CHECK(c->finalized, "context not finalized");
+  S2S_CHECK(rows > 0 && c->ws.base && rows <= (long)c->cap_B * c->cap_L, "workspace too small: call s2s_reserve first");
 }
 
 template <typename F>
@@ -786,7 +840,7 @@ int s2s_set_option(s2s_ctx* c, const char* key, int value) {
   return guarded([&] {
     S2S_CHECK(c && key, "null argument");
     const std::string k = key;
-    if (k == "pair_kernels") { S2S_CHECK(value >= 0 && value <= 2, "pair_kernels: 0|1|2"); c->opt_pair = value; }
+    if (k == "pair_kernels") { S2S_CHECK(value == 0 || value == 1, "pair_kernels: 0|1"); c->opt_pair = value; }
     else if (k == "node_gemm") { S2S_CHECK(value == 0 || value == 1, "node_gemm: 0|1"); c->opt_node = value; }
     else if (k == "ipa_kernels") { S2S_CHECK(value == 0 || value == 1, "ipa_kernels: 0|1"); c->opt_ipa = value; }
     else S2S_CHECK(false, "unknown option " + k);
@@ -814,9 +868,21 @@ int s2s_trunk(s2s_ctx* c, int B, int L, const float* node_embed, const void* z, 
     check_shape(c, B, L);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t R = (size_t)B * L;
-    if (node_embed != c->node) S2S_CUDA(cudaMemcpyAsync(c->node, node_embed, R * 256 * 4, cudaMemcpyDeviceToDevice, st));
-    if (z != (const void*)c->z) S2S_CUDA(cudaMemcpyAsync(c->z, z, R * L * C_Z * 2, cudaMemcpyDeviceToDevice, st));
-    do_trunk(c, B, L, rigids_t, residue_mask, fixed_mask, gt_psi, out_rigids, out_psi, st);
+    const int Lp = pad_len(L);
+    if (Lp == L) {
+      if (node_embed != c->node) S2S_CUDA(cudaMemcpyAsync(c->node, node_embed, R * 256 * 4, cudaMemcpyDeviceToDevice, st));
+      if (z != (const void*)c->z) S2S_CUDA(cudaMemcpyAsync(c->z, z, R * L * C_Z * 2, cudaMemcpyDeviceToDevice, st));
+      do_trunk(c, B, L, rigids_t, residue_mask, fixed_mask, gt_psi, out_rigids, out_psi, st);
+      return;
+    }
+    S2S_CHECK(node_embed != c->node && z != (const void*)c->z, "s2s_trunk: padded chain lengths need caller-owned embeddings");
+    repitch_rows(node_embed, c->node, B, L, Lp, 256, st);
+    repitch_pair((const bf16*)z, c->z, B, L, Lp, st);
+    pad_residue_inputs(c, B, L, Lp, rigids_t, nullptr, nullptr, residue_mask, fixed_mask, gt_psi, st);
+    HardScope hs(c, c->pd_hard);
+    do_trunk(c, B, Lp, c->pd_rig, c->pd_rmask, c->pd_fixed, gt_psi ? c->pd_psi : nullptr, c->pd_orig, c->pd_opsi, st);
+    repitch_rows(c->pd_orig, out_rigids, B, Lp, L, 7, st);
+    repitch_rows(c->pd_opsi, out_psi, B, Lp, L, 2, st);
   });
 }
 
@@ -825,7 +891,17 @@ int s2s_embed(s2s_ctx* c, int B, int L, const float* t, const int64_t* residue_i
   return guarded([&] {
     S2S_CHECK(c && t && residue_idx && fixed_mask && sc_ca && residue_mask && node_out && z_out, "s2s_embed: null argument");
     check_shape(c, B, L);
-    do_embed(c, B, L, t, (const long long*)residue_idx, fixed_mask, sc_ca, residue_mask, node_out, (bf16*)z_out, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Lp = pad_len(L);
+    if (Lp == L) {
+      do_embed(c, B, L, t, (const long long*)residue_idx, fixed_mask, sc_ca, residue_mask, node_out, (bf16*)z_out, st);
+      return;
+    }
+    pad_residue_inputs(c, B, L, Lp, nullptr, sc_ca, (const long long*)residue_idx, residue_mask, fixed_mask, nullptr, st);
+    HardScope hs(c, c->pd_hard);
+    do_embed(c, B, Lp, t, c->pd_ridx, c->pd_fixed, c->pd_sc, c->pd_rmask, c->node, c->z, st);
+    repitch_rows(c->node, node_out, B, Lp, L, 256, st);
+    repitch_pair(c->z, (bf16*)z_out, B, Lp, L, st);
   });
 }
 
@@ -834,7 +910,20 @@ int s2s_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const void* z,
   return guarded([&] {
     S2S_CHECK(c && node && z && quat && trans_nm && residue_mask && out && blk >= 0 && blk < N_BLK, "s2s_ipa: bad argument");
     check_shape(c, B, L);
-    do_ipa(c, blk, B, L, node, (const bf16*)z, quat, trans_nm, residue_mask, out, nullptr, nullptr, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Lp = pad_len(L);
+    if (Lp == L) {
+      do_ipa(c, blk, B, L, node, (const bf16*)z, quat, trans_nm, residue_mask, out, nullptr, nullptr, st);
+      return;
+    }
+    repitch_rows(node, c->node, B, L, Lp, 256, st);
+    repitch_pair((const bf16*)z, c->z, B, L, Lp, st);
+    repitch_rows(quat, c->quat, B, L, Lp, 4, st);      // appended rows: zero quaternion / translation (finite, masked out)
+    repitch_rows(trans_nm, c->trans, B, L, Lp, 3, st);
+    pad_residue_inputs(c, B, L, Lp, nullptr, nullptr, nullptr, residue_mask, nullptr, nullptr, st);
+    HardScope hs(c, c->pd_hard);
+    do_ipa(c, blk, B, Lp, c->node, c->z, c->quat, c->trans, c->pd_rmask, c->a256, nullptr, nullptr, st);
+    repitch_rows(c->a256, out, B, Lp, L, 256, st);
   });
 }
 
@@ -843,7 +932,61 @@ int s2s_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   return guarded([&] {
     S2S_CHECK(c && node && z_in && residue_mask && z_out && blk >= 0 && blk < N_BLK - 1, "s2s_edge_transition: bad argument");
     check_shape(c, B, L);
-    do_edge_transition(c, blk, B, L, node, (const bf16*)z_in, residue_mask, (bf16*)z_out, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Lp = pad_len(L);
+    PrecScope ps(c, TC3);  // n' and the per-residue terms: split-bf16 tensor-core GEMMs as inside the trunk (exact when node_gemm = 0)
+    if (Lp == L) {
+      do_edge_transition(c, blk, B, L, node, (const bf16*)z_in, residue_mask, (bf16*)z_out, st);
+      return;
+    }
+    repitch_rows(node, c->node, B, L, Lp, 256, st);
+    repitch_pair((const bf16*)z_in, c->z, B, L, Lp, st);
+    pad_residue_inputs(c, B, L, Lp, nullptr, nullptr, nullptr, residue_mask, nullptr, nullptr, st);
+    HardScope hs(c, c->pd_hard);
+    do_edge_transition(c, blk, B, Lp, c->node, c->z, c->pd_rmask, c->z, st);
+    repitch_pair(c->z, (bf16*)z_out, B, Lp, L, st);
+  });
+}
+
+// NodeTransition.forward of block blk (layers.py:138-145): out = LN(s + linear_3(relu(linear_2(relu(linear_1(s))))))
+int s2s_node_transition(s2s_ctx* c, int blk, int64_t rows, const float* s_in, float* out, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && s_in && out && blk >= 0 && blk < N_BLK, "s2s_node_transition: bad argument");
+    check_rows(c, rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = (int)rows;
+    const std::string nt = "translator.trunk.node_transition_" + std::to_string(blk) + ".";
+    PrecScope ps(c, TC3);
+    linear(c, s_in, 256, c->P(nt + "linear_1.weight"), 256, c->P(nt + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1);
+    linear(c, c->a256, 256, c->P(nt + "linear_2.weight"), 256, c->P(nt + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 1);
+    linear(c, c->b256, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), c->a256, 256, R, 256, 256, st, 0, s_in, 256);
+    layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), nullptr, out, R, 256, st);
+  });
+}
+
+// TorsionAngleHead.forward (layers.py:199-213; linear_3 is registered but unused): out [rows][2], unit norm (clamp 1e-8)
+int s2s_torsion_head(s2s_ctx* c, int64_t rows, const float* s_in, float* out, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && s_in && out, "s2s_torsion_head: bad argument");
+    check_rows(c, rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = (int)rows;
+    const std::string tp = "translator.torsion_pred.";
+    PrecScope ps(c, TC3);
+    linear(c, s_in, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1);
+    linear(c, c->a256, 256, c->P(tp + "linear_2.weight"), 256, c->P(tp + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 0, s_in, 256);
+    linear(c, c->b256, 256, c->P(tp + "linear_final.weight"), 256, c->P(tp + "linear_final.bias"), c->psi_u, 2, R, 2, 256, st, 0, nullptr, 0, nullptr, nullptr, EXACT);
+    psi_finalize(c->psi_u, nullptr, nullptr, out, R, st);
+  });
+}
+
+// BackboneUpdate.forward of block blk (layers.py:232-241): out [rows][6] = linear(s), exact fp32
+int s2s_backbone_update(s2s_ctx* c, int blk, int64_t rows, const float* s_in, float* out, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(c && s_in && out && blk >= 0 && blk < N_BLK, "s2s_backbone_update: bad argument");
+    S2S_CHECK(c->finalized && rows > 0, "s2s_backbone_update: context not finalized");
+    const std::string bb = "translator.trunk.bb_update_" + std::to_string(blk) + ".linear.";
+    linear(c, s_in, 256, c->P(bb + "weight"), 256, c->P(bb + "bias"), out, 6, (int)rows, 6, 256, (cudaStream_t)stream, 0, nullptr, 0, nullptr, nullptr, EXACT);
   });
 }
 
@@ -875,6 +1018,13 @@ int s2s_se3_perturb(int B, int L, const float* rot0, const float* trans0, const 
     a.B = B; a.L = L; a.rot0 = rot0; a.trans0 = trans0; a.diffuse = diffuse_mask; a.sched_f = sched_f; a.cdf = cdf;
     a.omega_grid = omega_grid; a.axis_noise = axis_noise; a.u_noise = u_noise; a.trans_noise = trans_noise; a.rig_out = rigids_out;
     se3_perturb(a, (cudaStream_t)stream);
+  });
+}
+
+int s2s_rng_fill(float* out, int B, int64_t n_per_decoy, uint64_t seed, int64_t first_decoy, int stream_id, int uniform, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(out && B > 0 && n_per_decoy > 0 && first_decoy >= 0 && stream_id >= 0, "s2s_rng_fill: bad argument");
+    philox_fill(out, B, (long)n_per_decoy, seed, first_decoy, (unsigned long long)stream_id, uniform, (cudaStream_t)stream);
   });
 }
 

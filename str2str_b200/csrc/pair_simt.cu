@@ -1,8 +1,8 @@
 // SIMT restatement of the two pair-track MLP kernels (edge embedder, EdgeTransition).
 //
-// Same inputs, outputs and bf16 rounding points as the tcgen05 kernels in pair_tc.cu, but with plain FFMA
-// loops: it is the on-device cross-check for the tensor-core path (tests/test_pair_kernels.py) and the
-// path taken for row counts that are not a multiple of the 128-row MMA tile.  Not a CPU fallback.
+// Same inputs, outputs and bf16 rounding points as the tcgen05 kernels (pair_tc3.cu, pair_tc4.cu), but with plain FFMA
+// loops: the on-device cross-check for the tensor-core path (pair_kernels = 0; tests/test_gpu_parity.py).  The product
+// path never takes it: chain lengths are padded to the tensor-core tiling inside the library (api.cu).  Not a CPU fallback.
 #include "s2s_internal.cuh"
 
 namespace s2s {
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) edge_embed_simt_kernel(EdgeEmbedArgs a) {
       row_to_bij(row, a.L, b, i, j);
       const long bi = (long)b * a.L + i, bj = (long)b * a.L + j;
       const int bin = pair_distogram_bin(a.sc_ca + bi * 3, a.sc_ca + bj * 3, a.bin_lower);
-      const int off = (int)(a.ridx[bi] - a.ridx[bj]) - a.d_min;
+      const int off = min(max((int)(a.ridx[bi] - a.ridx[bj]) - a.d_min, 0), a.n_off - 1);
       h = a.Ti[bi * C_Z + n] + a.Tj[bj * C_Z + n] + a.Tpos[(long)off * C_Z + n];
       if (bin >= 0) h += a.Wd[bin * C_Z + n];
       h = bf16_round(fmaxf(h, 0.f));
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(D_ET) edge_transition_simt_kernel(EdgeTransiti
 void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st) {
   const long rows = (long)a.B * a.L * a.L;
   const size_t smem = 2 * C_Z * RT * sizeof(float);
-  S2S_PROF("edge_embed", st);
+  S2S_PROF("edge_embed_simt", st);
   edge_embed_simt_kernel<<<ceil_div(rows, RT), 128, smem, st>>>(a);
   S2S_LAUNCH_CHECK();
 }
@@ -193,7 +193,7 @@ void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st) {
     S2S_CUDA(cudaFuncSetAttribute(edge_transition_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  S2S_PROF("edge_transition", st);
+  S2S_PROF("edge_transition_simt", st);
   edge_transition_simt_kernel<<<ceil_div(rows, RT), D_ET, smem, st>>>(a);
   S2S_LAUNCH_CHECK();
 }

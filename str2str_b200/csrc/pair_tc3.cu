@@ -16,6 +16,12 @@
 // layer's reads of h2 precede the next tile's layer-1 writes into E / R2, and its accumulation into the h1 region
 // follows the last layer-2 MMA's reads of h1; epilogue threads of one row quarter synchronise before an in-place store
 // (other column parts of the same rows are read by other warps) and once per tile before h1 is rewritten.
+//
+// Row tiles are 128 consecutive rows of the FLATTENED pair tensor [B*L*L][128].  With L % 128 == 0 a tile lies inside one
+// (decoy, i) row (FLAT = false: one u_i / p_i vector and one 128-row n'_j box per tile).  For any other L % 32 == 0
+// (FLAT = true; the library pads chain lengths to a multiple of 32, api.cu) a tile is four 32-row segments, each inside one
+// (decoy, i): the n'_j rows arrive as four 32-row TMA boxes, and every TMEM lane quarter (= one segment) adds its own
+// u_i / p_i vector, so L = 64 fills its tiles with two i rows and L = 96 / 160 / 320 ... run at the same per-row rate.
 #include <cstdlib>
 
 #include "s2s_internal.cuh"
@@ -36,7 +42,8 @@ constexpr int NEW = 16;                     // epilogue warps: NEW/4 per TMEM la
 constexpr int NPART = NEW / 4;
 constexpr int CW = 128 / NPART;             // accumulator columns per thread per 128-column chunk
 constexpr int ET3_THREADS = 64 + 32 * NEW;
-constexpr int VEC_FLOATS = D_ET + C_Z + D_ET + C_Z + C_Z + 2 * NPART * 128;  // u_i, p_i, b2, ln_w, ln_b, LayerNorm partial sums
+constexpr int NSEG = 4;                     // 32-row segments of a tile (FLAT: each has its own (decoy, i))
+constexpr int VEC_FLOATS = NSEG * (D_ET + C_Z) + D_ET + C_Z + C_Z + 2 * NPART * 128;  // u_i, p_i per segment, b2, ln_w, ln_b, LayerNorm partial sums
 constexpr int OFF_BAR = OFF_VEC + VEC_FLOATS * 4;
 constexpr int N_BARS = 2 * NSTAGE + 18;
 constexpr int SMEM_BYTES = OFF_BAR + N_BARS * 8 + 16;
@@ -80,14 +87,14 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
-template <bool MC>
+template <bool MC, bool FLAT>
 __global__ void __launch_bounds__(ET3_THREADS, 1)
 edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_n, Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B operand blocks need 1024-byte alignment
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
-  float* u_s = reinterpret_cast<float*>(smem + OFF_VEC);
-  float* p_s = u_s + D_ET;
-  float* b2_s = p_s + C_Z;
+  float* u_s = reinterpret_cast<float*>(smem + OFF_VEC);  // [NSEG][D_ET]
+  float* p_s = u_s + NSEG * D_ET;                         // [NSEG][C_Z]
+  float* b2_s = p_s + NSEG * C_Z;
   float* lnw_s = b2_s + D_ET;
   float* lnb_s = lnw_s + C_Z;
   float* red_s = lnb_s + C_Z;  // [2 stats][NPART column parts][128 rows]
@@ -136,7 +143,7 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   if constexpr (MC) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int tiles_per_i = a.L / TM;
+  const int tiles_per_i = FLAT ? 1 : a.L / TM;  // FLAT tiles are addressed by flattened row, not by (decoy, i)
   constexpr uint32_t IDESC128 = make_idesc(128, 128), IDESC64 = make_idesc(128, 64);
   const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
@@ -146,15 +153,26 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
       uint32_t cnt = 0, ph_a0 = 0;
       const bf16* wimg = a.wimg + (size_t)(blockIdx.x % a.ncopy) * ((size_t)WTILES * TILE_BYTES / 2);
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
+        const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;  // (unused when FLAT)
         const int b = bi / a.L;
         mbar_wait(a0_empty, ph_a0 ^ 1);
         ph_a0 ^= 1;
         mbar_expect_tx(a0_full, 4 * TILE_BYTES);
         tma_load_2d(smem + OFF_A0, &tmap_z, 0, tile * TM, a0_full);
         tma_load_2d(smem + OFF_A0 + TILE_BYTES, &tmap_z, KBLK, tile * TM, a0_full);
-        tma_load_2d(smem + OFF_A0 + 2 * TILE_BYTES, &tmap_n, 0, b * a.L + j0, a0_full);
-        tma_load_2d(smem + OFF_A0 + 3 * TILE_BYTES, &tmap_n, KBLK, b * a.L + j0, a0_full);
+        if constexpr (FLAT) {  // tmap_n has 32-row boxes: segment sg holds keys j_sg .. j_sg + 31 of its own decoy
+#pragma unroll
+          for (int sg = 0; sg < NSEG; ++sg) {
+            const long f = (long)tile * TM + sg * 32;
+            const int bi_s = (int)(f / a.L), j_s = (int)(f - (long)bi_s * a.L);
+            const int nrow = (bi_s / a.L) * a.L + j_s;
+            tma_load_2d(smem + OFF_A0 + 2 * TILE_BYTES + sg * 4096, &tmap_n, 0, nrow, a0_full);
+            tma_load_2d(smem + OFF_A0 + 3 * TILE_BYTES + sg * 4096, &tmap_n, KBLK, nrow, a0_full);
+          }
+        } else {
+          tma_load_2d(smem + OFF_A0 + 2 * TILE_BYTES, &tmap_n, 0, b * a.L + j0, a0_full);
+          tma_load_2d(smem + OFF_A0 + 3 * TILE_BYTES, &tmap_n, KBLK, b * a.L + j0, a0_full);
+        }
         for (int wt = 0; wt < WTILES; ++wt, ++cnt) {
           const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
           mbar_wait(&w_empty[s], ph ^ 1);
@@ -311,13 +329,34 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
     const bool do_epi = !(a.dbg & 4);
     uint32_t fE = 0, f2 = 0, fF = 0;  // completed uses seen per "full" barrier
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
+      int bi, jr;  // this thread's row: (decoy, i) index and key j
+      if constexpr (FLAT) {
+        const long f = (long)tile * TM + r;
+        bi = (int)(f / a.L);
+        jr = (int)(f - (long)bi * a.L);
+      } else {
+        bi = tile / tiles_per_i;
+        jr = (tile % tiles_per_i) * TM + r;
+      }
       const int b = bi / a.L;
       named_bar_sync(1, 32 * NEW);
-      for (int c = et; c < D_ET; c += 32 * NEW) u_s[c] = a.u[(size_t)bi * D_ET + c];
-      if (et < C_Z) p_s[et] = a.p[(size_t)bi * C_Z + et];
+      if constexpr (FLAT) {  // segment sg's vectors: bi of row sg * 32 (uniform over the segment because L % 32 == 0)
+        for (int c = et; c < NSEG * D_ET; c += 32 * NEW) {
+          const int sg = c / D_ET;
+          u_s[c] = a.u[(size_t)(((long)tile * TM + sg * 32) / a.L) * D_ET + (c - sg * D_ET)];
+        }
+        {
+          const int sg = et / C_Z;  // 512 epilogue threads = NSEG * C_Z
+          p_s[et] = a.p[(size_t)(((long)tile * TM + sg * 32) / a.L) * C_Z + (et - sg * C_Z)];
+        }
+      } else {
+        for (int c = et; c < D_ET; c += 32 * NEW) u_s[c] = a.u[(size_t)bi * D_ET + c];
+        if (et < C_Z) p_s[et] = a.p[(size_t)bi * C_Z + et];
+      }
       named_bar_sync(1, 32 * NEW);
-      const float m = a.mask[bi] * a.mask[(size_t)b * a.L + j0 + r];
+      const float* u_q = FLAT ? u_s + q * D_ET : u_s;  // this lane quarter's segment
+      const float* p_q = FLAT ? p_s + q * C_Z : p_s;
+      const float m = a.mask[bi] * a.mask[(size_t)b * a.L + jr];
       float y[CW];
       auto wait_full = [&](uint64_t* bar, uint32_t& n) {
         mbar_wait(bar, n & 1);
@@ -360,7 +399,7 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
         if (nc == 1) wait_full(full2, f2); else wait_full(fullE, fE);
         if (do_epi) {
           load_cols(base + part * CW, CW);
-          add_vec(u_s + nc * 128 + part * CW, CW);
+          add_vec(u_q + nc * 128 + part * CW, CW);
           store_packed(COL_H1 + nc * 64 + part * (CW / 2), CW);
         }
         tc_fence_before();
@@ -394,7 +433,7 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
         if (do_epi) load_cols(COL_FIN + part * CW, CW);
         tc_fence_before();
         if (!do_epi) continue;
-        add_vec(p_s + part * CW, CW);
+        add_vec(p_q + part * CW, CW);
         float sum = 0.f;
 #pragma unroll
         for (int e = 0; e < CW; ++e) sum += y[e];
@@ -466,12 +505,14 @@ void build_et3_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst
 }
 
 void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st) {
-  S2S_CHECK(a.L % TM == 0, "edge_transition_tc3 needs L % 128 == 0");
+  S2S_CHECK(a.L % 32 == 0, "edge_transition_tc3 needs L % 32 == 0 (api.cu pads chain lengths)");
   static_assert(NEW == 16 && CW == 32, "the in-place h2 stores assume 4 column parts of 32");
+  static_assert(32 * NEW == NSEG * C_Z, "p_i staging assumes one element per epilogue thread");
+  const bool flat = a.L % TM != 0;
   S2S_CHECK(a.wimg3 && a.nprime_bf16, "edge_transition_tc3: weight image / bf16 node embedding missing");
   const size_t rows = (size_t)a.B * a.L * a.L;
   const CUtensorMap mz = make_bf16_2d_map(a.z_in, rows, C_Z, C_Z);
-  const CUtensorMap mn = make_bf16_2d_map(a.nprime_bf16, (size_t)a.B * a.L, C_Z, C_Z);
+  const CUtensorMap mn = make_bf16_2d_map(a.nprime_bf16, (size_t)a.B * a.L, C_Z, C_Z, flat ? 32 : 128);
   Args k;
   k.wimg = a.wimg3; k.u = a.u; k.p = a.p; k.b2 = a.b2; k.ln_w = a.ln_w; k.ln_b = a.ln_b; k.mask = a.mask;
   k.z_out = a.z_out; k.L = a.L; k.n_tiles = (int)(rows / TM); k.ncopy = a.wimg_copies;
@@ -484,8 +525,10 @@ void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st) {
   static bool configured = false;
   const int smem = SMEM_BYTES + 1024;
   if (!configured) {
-    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   S2S_PROF("edge_transition", st);
@@ -503,14 +546,17 @@ void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st) {
     // persistent kernel: never launch more clusters than can be co-resident (GPCs with an odd SM count strand one SM)
     static int max_clusters = 0;
     if (!max_clusters) {
-      S2S_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, edge_transition_tc3_kernel<true>, &cfg));
+      S2S_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, edge_transition_tc3_kernel<true, false>, &cfg));
       S2S_CHECK(max_clusters > 0, "edge_transition_tc3: no 2-CTA cluster fits");
     }
     if (grid > 2 * max_clusters) grid = 2 * max_clusters;
     cfg.gridDim = dim3(grid);
-    S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_tc3_kernel<true>, mz, mn, k));
+    if (flat) S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_tc3_kernel<true, true>, mz, mn, k));
+    else S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_tc3_kernel<true, false>, mz, mn, k));
+  } else if (flat) {
+    edge_transition_tc3_kernel<false, true><<<grid, ET3_THREADS, smem, st>>>(mz, mn, k);
   } else {
-    edge_transition_tc3_kernel<false><<<grid, ET3_THREADS, smem, st>>>(mz, mn, k);
+    edge_transition_tc3_kernel<false, false><<<grid, ET3_THREADS, smem, st>>>(mz, mn, k);
   }
   S2S_LAUNCH_CHECK();
 }

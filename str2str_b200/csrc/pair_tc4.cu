@@ -1,9 +1,9 @@
-// Second-generation fused edge embedder (reference src/models/net/denoising_ipa.py:126-158, geo_utils.py:44-56).
+// Fused edge embedder (reference src/models/net/denoising_ipa.py:126-158, geo_utils.py:44-56).
 //
-// The first-generation kernel (pair_tc.cu: edge_embed_tc_kernel) walks every 128-row tile through its five steps in
-// lock-step (table gather -> MMA -> bias/ReLU restage -> MMA -> LayerNorm/store), so each step's latency is exposed and the
-// kernel sits at ~17 % of either roofline (1.16 ms at B = 64, L = 256: 1.07 GB written, 0.27 TFLOP).  Here the steps are
-// stations of a pipeline, each owned by its own warps and each working on a DIFFERENT tile at any moment:
+// A kernel that walks every 128-row tile through its five steps in lock-step (table gather -> MMA -> bias/ReLU restage ->
+// MMA -> LayerNorm/store) exposes each step's latency (the round-1 first cut: ~17 % of either roofline, 1.16 ms at B = 64,
+// L = 256: 1.07 GB written, 0.27 TFLOP).  Here the steps are stations of a pipeline, each owned by its own warps and each
+// working on a DIFFERENT tile at any moment:
 //
 //   G  (7 warps)  layer 1 by table lookups for tile t+2  -> A1[stage]  (bf16, K-major SWIZZLE_128B, 2 stages)
 //   M  (1 warp)   tcgen05.mma  layer 2 of tile t+1 (A1 x W2 -> acc2[stage]), layer 3 of tile t (A2 x W3 -> acc3[stage])
@@ -12,8 +12,12 @@
 //
 // One persistent CTA per SM (tiles strided by the grid, so the SMs write neighbouring tiles at any moment); the four
 // accumulators fill the 512 columns of tensor memory; W2 / W3 stay resident in shared memory; stations hand tiles over
-// through mbarriers only.  Same arithmetic and rounding points as the first generation (and as pair_simt.cu), except
-// that the LayerNorm statistics are taken in one shifted pass (sum and sum of squares of y - y_0).
+// through mbarriers only.  Same arithmetic and rounding points as pair_simt.cu, except that the LayerNorm statistics are
+// taken in one shifted pass (sum and sum of squares of y - y_0).
+//
+// Tiles are 128 consecutive rows of the flattened pair tensor [B*L*L][128].  FLAT = false (L % 128 == 0): a tile lies in one
+// (decoy, i) row.  FLAT = true (any other L with B*L*L % 128 == 0; api.cu pads chains to a multiple of 32): every row
+// carries its own (decoy, i, j), so short chains fill their tiles with several i rows.
 //
 // What bounded the first cut of this pipeline (ncu, profiles/r01c_gemm_and_embedder_experiments.log): the LSU data pipe at 76 % of its
 // wavefront rate, not latency.  Row-per-thread 16-byte global stores cost 32 wavefronts each (32 different 128-byte
@@ -80,6 +84,7 @@ struct EePipeArgs {
   int n_tiles;
 };
 
+template <bool FLAT>
 __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int tiles_per_i = e.L / TM;
+  const int tiles_per_i = FLAT ? 1 : e.L / TM;
   const int n_local = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   constexpr uint32_t IDESC = make_idesc(128, 128);
 
@@ -175,30 +180,62 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
     const float inv_step = (float)(N_BINS - 1) / (edge_s[N_BINS - 1] - edge_s[0]);
     for (int k = 0; k < n_local; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
-      const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
-      const int b = bi / e.L;
       const int r_begin = g * 18, r_cnt = g == P_G_WARPS - 1 ? TM - r_begin : 18;
-      const size_t bj0 = (size_t)b * e.L + j0 + r_begin;
-      const size_t bjl = bj0 + (lane < r_cnt ? lane : 0);
-      const int bin_l = pair_distogram_bin_fast(e.sc_ca + (size_t)bi * 3, e.sc_ca + bjl * 3, edge_s, inv_step);
-      const int off_l = (int)(e.ridx[bi] - e.ridx[bjl]) - e.d_min;
-      const float4 tiv = __ldg(reinterpret_cast<const float4*>(e.Ti + (size_t)bi * C_Z + c));
       const uint32_t s = k & 1, ph = (k >> 1) & 1;
-      mbar_wait(&a1_empty[s], ph ^ 1);
       unsigned char* const dst = dst0 + s * 2 * TILE_BYTES;
+      if constexpr (FLAT) {
+        // lane l classifies flattened row tile*128 + r_begin + l: its (decoy, i) row bi, its key row bj, bin and offset
+        const long f = (long)tile * TM + r_begin + (lane < r_cnt ? lane : 0);
+        const int bi_l = (int)(f / e.L);
+        const int bj_l = (bi_l / e.L) * e.L + (int)(f - (long)bi_l * e.L);
+        const int bin_l = pair_distogram_bin_fast(e.sc_ca + (size_t)bi_l * 3, e.sc_ca + (size_t)bj_l * 3, edge_s, inv_step);
+        const int off_l = min(max((int)(e.ridx[bi_l] - e.ridx[bj_l]) - e.d_min, 0), e.n_off - 1);
+        int bi_cur = __shfl_sync(0xffffffffu, bi_l, 0);
+        float4 tiv = __ldg(reinterpret_cast<const float4*>(e.Ti + (size_t)bi_cur * C_Z + c));
+        mbar_wait(&a1_empty[s], ph ^ 1);
 #pragma unroll 6
-      for (int r16 = 0; r16 < r_cnt; ++r16) {
-        const int bin = __shfl_sync(0xffffffffu, bin_l, r16);
-        const int off = __shfl_sync(0xffffffffu, off_l, r16);
-        const float4 tjv = __ldg(reinterpret_cast<const float4*>(e.Tj + (bj0 + r16) * C_Z + c));
-        const float4 tpv = __ldg(reinterpret_cast<const float4*>(e.Tpos + (size_t)off * C_Z + c));
-        float4 h = make_float4(tiv.x + tjv.x + tpv.x, tiv.y + tjv.y + tpv.y, tiv.z + tjv.z + tpv.z, tiv.w + tjv.w + tpv.w);
-        if (bin >= 0) {
-          const float4 wv = *reinterpret_cast<const float4*>(wd_s + bin * P_WD_PITCH + c);
-          h.x += wv.x; h.y += wv.y; h.z += wv.z; h.w += wv.w;
+        for (int r16 = 0; r16 < r_cnt; ++r16) {
+          const int bin = __shfl_sync(0xffffffffu, bin_l, r16);
+          const int off = __shfl_sync(0xffffffffu, off_l, r16);
+          const int bi = __shfl_sync(0xffffffffu, bi_l, r16);
+          const int bj = __shfl_sync(0xffffffffu, bj_l, r16);
+          if (bi != bi_cur) {  // warp-uniform: the tile moved on to the next i row
+            bi_cur = bi;
+            tiv = __ldg(reinterpret_cast<const float4*>(e.Ti + (size_t)bi_cur * C_Z + c));
+          }
+          const float4 tjv = __ldg(reinterpret_cast<const float4*>(e.Tj + (size_t)bj * C_Z + c));
+          const float4 tpv = __ldg(reinterpret_cast<const float4*>(e.Tpos + (size_t)off * C_Z + c));
+          float4 h = make_float4(tiv.x + tjv.x + tpv.x, tiv.y + tjv.y + tpv.y, tiv.z + tjv.z + tpv.z, tiv.w + tjv.w + tpv.w);
+          if (bin >= 0) {
+            const float4 wv = *reinterpret_cast<const float4*>(wd_s + bin * P_WD_PITCH + c);
+            h.x += wv.x; h.y += wv.y; h.z += wv.z; h.w += wv.w;
+          }
+          *reinterpret_cast<uint2*>(dst + sw128_offset(r_begin + r16, c % KBLK)) =
+              make_uint2(pack_bf16(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f)), pack_bf16(fmaxf(h.z, 0.f), fmaxf(h.w, 0.f)));
         }
-        *reinterpret_cast<uint2*>(dst + sw128_offset(r_begin + r16, c % KBLK)) =
-            make_uint2(pack_bf16(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f)), pack_bf16(fmaxf(h.z, 0.f), fmaxf(h.w, 0.f)));
+      } else {
+        const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
+        const int b = bi / e.L;
+        const size_t bj0 = (size_t)b * e.L + j0 + r_begin;
+        const size_t bjl = bj0 + (lane < r_cnt ? lane : 0);
+        const int bin_l = pair_distogram_bin_fast(e.sc_ca + (size_t)bi * 3, e.sc_ca + bjl * 3, edge_s, inv_step);
+        const int off_l = min(max((int)(e.ridx[bi] - e.ridx[bjl]) - e.d_min, 0), e.n_off - 1);
+        const float4 tiv = __ldg(reinterpret_cast<const float4*>(e.Ti + (size_t)bi * C_Z + c));
+        mbar_wait(&a1_empty[s], ph ^ 1);
+#pragma unroll 6
+        for (int r16 = 0; r16 < r_cnt; ++r16) {
+          const int bin = __shfl_sync(0xffffffffu, bin_l, r16);
+          const int off = __shfl_sync(0xffffffffu, off_l, r16);
+          const float4 tjv = __ldg(reinterpret_cast<const float4*>(e.Tj + (bj0 + r16) * C_Z + c));
+          const float4 tpv = __ldg(reinterpret_cast<const float4*>(e.Tpos + (size_t)off * C_Z + c));
+          float4 h = make_float4(tiv.x + tjv.x + tpv.x, tiv.y + tjv.y + tpv.y, tiv.z + tjv.z + tpv.z, tiv.w + tjv.w + tpv.w);
+          if (bin >= 0) {
+            const float4 wv = *reinterpret_cast<const float4*>(wd_s + bin * P_WD_PITCH + c);
+            h.x += wv.x; h.y += wv.y; h.z += wv.z; h.w += wv.w;
+          }
+          *reinterpret_cast<uint2*>(dst + sw128_offset(r_begin + r16, c % KBLK)) =
+              make_uint2(pack_bf16(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f)), pack_bf16(fmaxf(h.z, 0.f), fmaxf(h.w, 0.f)));
+        }
       }
       fence_proxy_async();
       mbar_arrive(&a1_full[s]);
@@ -246,8 +283,16 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
     unsigned char* const obuf = smem + P_OFF_OUT + q * (32 * 256);
     for (int k = 0; k < n_local; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
-      const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;
-      const size_t bj = (size_t)(bi / e.L) * e.L + j0 + r;
+      int bi, jr;
+      if constexpr (FLAT) {
+        const long f = (long)tile * TM + r;
+        bi = (int)(f / e.L);
+        jr = (int)(f - (long)bi * e.L);
+      } else {
+        bi = tile / tiles_per_i;
+        jr = (tile % tiles_per_i) * TM + r;
+      }
+      const size_t bj = (size_t)(bi / e.L) * e.L + jr;
       const float m = __ldg(e.mask + bi) * __ldg(e.mask + bj);
       const uint32_t s = k & 1, ph = (k >> 1) & 1;
       mbar_wait_backoff(&acc3_full[s], ph);
@@ -311,20 +356,23 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
 }  // namespace
 
 void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st) {
-  S2S_CHECK(a.L % TM == 0, "edge_embed_tc2 needs L % 128 == 0");
+  S2S_CHECK(((size_t)a.B * a.L * a.L) % TM == 0, "edge_embed_tc2 needs B*L*L % 128 == 0 (api.cu pads chain lengths to a multiple of 32)");
+  const bool flat = a.L % TM != 0;
   S2S_CHECK(a.wimg, "edge_embed_tc2: weight image missing");
   EePipeArgs k;
   k.e = a; k.wimg = a.wimg; k.n_tiles = (int)((size_t)a.B * a.L * a.L / TM);
   static bool configured = false;
   if (!configured) {
-    S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
     configured = true;
   }
   S2S_CHECK(a.vec4, "edge_embed_tc2: packed bias / LayerNorm vector missing");
   S2S_CUDA(cudaMemcpyToSymbolAsync(c_ee, a.vec4, sizeof(float) * 4 * C_Z, 0, cudaMemcpyDeviceToDevice, st));
   S2S_PROF("edge_embed", st);
   const int cap = sm_count();
-  edge_embed_pipe_kernel<<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
+  if (flat) edge_embed_pipe_kernel<true><<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
+  else edge_embed_pipe_kernel<false><<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
   S2S_LAUNCH_CHECK();
 }
 

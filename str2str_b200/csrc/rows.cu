@@ -211,12 +211,70 @@ __global__ void concat_skip_kernel(const float* __restrict__ node, const float* 
   }
 }
 
-__global__ void masks_kernel(const float* __restrict__ rmask, const float* __restrict__ fixed,
+__global__ void masks_kernel(const float* __restrict__ rmask, const float* __restrict__ fixed, const float* __restrict__ hard,
                              float* __restrict__ diffuse, float* __restrict__ keybias, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   diffuse[i] = (1.f - fixed[i]) * rmask[i];
-  keybias[i] = 1.f - rmask[i];  // float src_key_padding_mask is ADDED to the logits (ipa.py:357)
+  // float src_key_padding_mask is ADDED to the logits (ipa.py:357): a masked key of the caller's batch still takes part,
+  // with +1.  Rows the library itself appended to reach a tile multiple are not keys at all: exp() of them is exactly 0.
+  keybias[i] = (hard && hard[i] == 0.f) ? -1e30f : 1.f - rmask[i];
+}
+
+// ---- internal chain-length padding (api.cu: pad_len) ----------------------------------------------------------------
+// The tensor-core kernels tile chains in units of 32 residues.  Other lengths run on padded copies [B][Lp] of the
+// per-residue inputs: appended rows get mask 0 (IPA keys drop out through the -1e5 mask term, pair rows are zeroed by the
+// edge mask), the residue index of the decoy's first residue (offsets stay inside the relative-position table), an identity
+// frame, and hard = 0 (dropped from the sequence transformer's keys, see masks_kernel).  Real rows get hard = 1.
+__global__ void pad_inputs_kernel(int B, int L, int Lp, const float* __restrict__ rig, const float* __restrict__ sc,
+                                  const long long* __restrict__ ridx, const float* __restrict__ rmask,
+                                  const float* __restrict__ fixed, const float* __restrict__ psi, float* __restrict__ o_rig,
+                                  float* __restrict__ o_sc, long long* __restrict__ o_ridx, float* __restrict__ o_rmask,
+                                  float* __restrict__ o_fixed, float* __restrict__ o_psi, float* __restrict__ o_hard) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Lp) return;
+  const int b = idx / Lp, j = idx - b * Lp;
+  const bool real = j < L;
+  const long src = (long)b * L + j;
+  if (rig) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) o_rig[(long)idx * 7 + k] = real ? rig[src * 7 + k] : (k == 0 ? 1.f : 0.f);
+  }
+  if (sc) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o_sc[(long)idx * 3 + k] = real ? sc[src * 3 + k] : 0.f;
+  }
+  if (ridx) o_ridx[idx] = ridx[real ? src : (long)b * L];
+  if (rmask) o_rmask[idx] = real ? rmask[src] : 0.f;
+  if (fixed) o_fixed[idx] = real ? fixed[src] : 0.f;
+  if (psi) {
+    o_psi[(long)idx * 2] = real ? psi[src * 2] : 0.f;
+    o_psi[(long)idx * 2 + 1] = real ? psi[src * 2 + 1] : 0.f;
+  }
+  o_hard[idx] = real ? 1.f : 0.f;
+}
+
+// dst [B][Ld][W] <- src [B][Ls][W]: rows j < min(Ls, Ld) are copied, rows beyond Ls are filled with zeros
+template <typename T>
+__global__ void repitch_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int Ls, int Ld, int W) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * Ld * W) return;
+  const int w = (int)(idx % W);
+  const long bj = idx / W;
+  const int b = (int)(bj / Ld), j = (int)(bj - (long)b * Ld);
+  dst[idx] = j < Ls ? src[((long)b * Ls + j) * W + w] : T(0);
+}
+
+// pair tensor dst [B][Ld][Ld][128] <- src [B][Ls][Ls][128] (bf16, 16-byte pieces), zero outside the source square
+__global__ void repitch_pair_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int Ls, int Ld) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte piece: 16 per pair row
+  if (idx >= (long)B * Ld * Ld * 16) return;
+  const int piece = (int)(idx & 15);
+  const long row = idx >> 4;
+  const int j = (int)(row % Ld);
+  const long bi = row / Ld;
+  const int i = (int)(bi % Ld), b = (int)(bi / Ld);
+  dst[idx] = (i < Ls && j < Ls) ? src[((((long)b * Ls + i) * Ls + j) << 4) + piece] : make_uint4(0u, 0u, 0u, 0u);
 }
 
 }  // namespace
@@ -265,8 +323,22 @@ void concat_skip(const float* node, const float* skip, float* out, long rows, cu
   S2S_LAUNCH_CHECK();
 }
 
-void make_masks(const float* rmask, const float* fixed, float* diffuse, float* keybias, int n, cudaStream_t st) {
-  masks_kernel<<<ceil_div(n, 256), 256, 0, st>>>(rmask, fixed, diffuse, keybias, n);
+void make_masks(const float* rmask, const float* fixed, const float* hard, float* diffuse, float* keybias, int n, cudaStream_t st) {
+  masks_kernel<<<ceil_div(n, 256), 256, 0, st>>>(rmask, fixed, hard, diffuse, keybias, n);
+  S2S_LAUNCH_CHECK();
+}
+
+void pad_inputs(const PadInputs& a, cudaStream_t st) {
+  pad_inputs_kernel<<<ceil_div((long)a.B * a.Lp, 128), 128, 0, st>>>(a.B, a.L, a.Lp, a.rig, a.sc, a.ridx, a.rmask, a.fixed, a.psi, a.o_rig,
+                                                                     a.o_sc, a.o_ridx, a.o_rmask, a.o_fixed, a.o_psi, a.o_hard);
+  S2S_LAUNCH_CHECK();
+}
+void repitch_rows(const float* src, float* dst, int B, int Ls, int Ld, int W, cudaStream_t st) {
+  repitch_rows_kernel<float><<<ceil_div((long)B * Ld * W, 256), 256, 0, st>>>(src, dst, B, Ls, Ld, W);
+  S2S_LAUNCH_CHECK();
+}
+void repitch_pair(const bf16* src, bf16* dst, int B, int Ls, int Ld, cudaStream_t st) {
+  repitch_pair_kernel<<<ceil_div((long)B * Ld * Ld * 16, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), B, Ls, Ld);
   S2S_LAUNCH_CHECK();
 }
 

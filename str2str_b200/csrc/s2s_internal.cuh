@@ -59,7 +59,18 @@ void relpos_features(const float* pdenom, float* out, int d_min, int n, cudaStre
 void psi_finalize(const float* u, const float* gt_psi, const float* fixed, float* psi, int rows, cudaStream_t st);
 void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st, bf16* out_hi = nullptr,
                  bf16* out_lo = nullptr);
-void make_masks(const float* rmask, const float* fixed, float* diffuse, float* keybias, int n, cudaStream_t st);
+void make_masks(const float* rmask, const float* fixed, const float* hard, float* diffuse, float* keybias, int n, cudaStream_t st);
+// internal chain-length padding (rows.cu): per-residue inputs [B][L] -> [B][Lp]; any source may be null (skipped)
+struct PadInputs {
+  int B, L, Lp;
+  const float *rig = nullptr, *sc = nullptr, *rmask = nullptr, *fixed = nullptr, *psi = nullptr;
+  const long long* ridx = nullptr;
+  float *o_rig = nullptr, *o_sc = nullptr, *o_rmask = nullptr, *o_fixed = nullptr, *o_psi = nullptr, *o_hard = nullptr;
+  long long* o_ridx = nullptr;
+};
+void pad_inputs(const PadInputs& a, cudaStream_t st);
+void repitch_rows(const float* src, float* dst, int B, int Ls, int Ld, int W, cudaStream_t st);  // [B][Ls][W] -> [B][Ld][W]
+void repitch_pair(const bf16* src, bf16* dst, int B, int Ls, int Ld, cudaStream_t st);           // [B][Ls][Ls][128] -> [B][Ld][Ld][128]
 
 // ---- pair kernels -------------------------------------------------------------------------------------
 // distogram bin of |a-b| with the reference's strict inequalities (geo_utils.py:44-56); -1 = no bin
@@ -78,6 +89,7 @@ __device__ __forceinline__ int pair_distogram_bin(const float* a, const float* b
 
 struct EdgeEmbedArgs {
   int B, L, d_min;
+  int n_off = 1;           // rows of Tpos: offsets outside [d_min, d_min + n_off) are clamped (never read out of bounds)
   const float* Ti;    // [B*L][128]  W1[:, 0:33] tf_i + b1
   const float* Tj;    // [B*L][128]  W1[:,33:66] tf_j
   const float* Tpos;  // [n_off][128] W1[:,66:98] pos(d_min + r)
@@ -94,8 +106,7 @@ struct EdgeEmbedArgs {
   const float* vec4 = nullptr; // [b2 | b3 | ln_w | ln_b] packed, device (pipelined kernel: copied into its constant bank)
 };
 void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st);
-void edge_embed_tc(const EdgeEmbedArgs& a, cudaStream_t st);   // first generation (lock-step stations), pair_kernels = 2
-void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st);  // second generation (pipelined stations), pair_tc4.cu
+void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st);  // pipelined tcgen05 kernel, pair_tc4.cu
 
 struct EdgeTransitionArgs {
   int B, L;
@@ -109,23 +120,15 @@ struct EdgeTransitionArgs {
   const bf16 *W1zt, *W2t, *Wft, *Wfzt;   // transposed copies [in][out]
   const float *b2, *ln_w, *ln_b;
   bf16* z_out;        // may alias z_in
-  const bf16* wimg = nullptr;         // tcgen05 path: pre-swizzled weight blocks (build_et_wimg)
   const bf16* nprime_bf16 = nullptr;  // tcgen05 path: n' [B*L][128] in bf16 (the n'_j operand rows)
-  const bf16* wimg2 = nullptr;        // second-generation kernel: 8 KB weight blocks (build_et2_wimg)
-  const bf16* wimg3 = nullptr;        // third-generation kernel (build_et3_wimg)
+  const bf16* wimg3 = nullptr;        // tcgen05 path: pre-swizzled weight blocks in consumption order (build_et3_wimg)
   int wimg_copies = 1;                // number of identical images laid out back to back (L2 hot-spot relief)
 };
 void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st);
-void edge_transition_tc(const EdgeTransitionArgs& a, cudaStream_t st);
-void edge_transition_tc2(const EdgeTransitionArgs& a, cudaStream_t st);
 void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st);
 size_t et3_wimg_elems();
 void build_et3_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);
-size_t et2_wimg_elems();
-void build_et2_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);
-size_t et_wimg_elems();
 size_t ee_wimg_elems();
-void build_et_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);
 void build_ee_wimg(const float* W2, const float* W3, bf16* dst, cudaStream_t st);
 void f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t st);
 
@@ -215,5 +218,9 @@ struct Se3PerturbArgs {
 void se3_perturb(const Se3PerturbArgs& a, cudaStream_t st);
 void backbone_atoms(const float* rig7, const float* psi, const long long* aatype, const float* table,
                     float* atom37, float* atom14, int rows, cudaStream_t st);
+
+// ---- rng.cu -------------------------------------------------------------------------------------------
+void philox_fill(float* out, int B, long n_per_decoy, unsigned long long seed, long long first_decoy, unsigned long long stream_id,
+                 int uniform, cudaStream_t st);
 
 }  // namespace s2s

@@ -1,5 +1,5 @@
 // tcgen05 / TMEM / TMA / mbarrier PTX wrappers and the K-major SWIZZLE_128B operand conventions shared by the
-// tensor-core kernels (pair_tc.cu, gemm_tc.cu).  sm_100a only.
+// tensor-core kernels (pair_tc3.cu, pair_tc4.cu, ipa_tc.cu, tfm_attn.cu, gemm_tc.cu).  sm_100a only.
 #pragma once
 #include <cuda.h>
 
@@ -212,7 +212,7 @@ __device__ __forceinline__ void kblock_ts(uint32_t d, uint32_t a_col, uint32_t b
 
 }  // namespace tc
 
-// host helpers (pair_tc.cu)
+// host helpers (tc_host.cu)
 CUtensorMap make_bf16_2d_map(const void* base, size_t rows, size_t cols, size_t row_pitch_elems, int box_rows = 128);
 int sm_count();
 

@@ -165,6 +165,12 @@ def parse_pdb_string(pdb_str: str, chain_id: Optional[str] = None) -> Dict[str, 
         prev = res["atoms"].get(name)
         if prev is None or occ > prev[1]:
             res["atoms"][name] = (xyz, occ, bf)
+    # Biopython walks `for chain in model: for res in chain`: residues are grouped by chain in first-seen chain order (a
+    # chain's HETATM / water records that appear after another chain's atoms still follow that chain's own residues)
+    chain_rank: Dict[str, int] = {}
+    for key in order:
+        chain_rank.setdefault(key[0], len(chain_rank))
+    order.sort(key=lambda k: chain_rank[k[0]])  # stable: first-appearance order inside a chain is kept
     pos, mask, aatype, resid, chains, bfs = [], [], [], [], [], []
     for key in order:
         res = residues[key]

@@ -53,7 +53,7 @@ class InvariantPointAttention(nn.Module):
         net = _engine_of(self)
         eng = net.native(s.device)
         B, L = mask.shape
-        eng.reserve(B, L, torch.zeros(1, dtype=torch.long))
+        eng.reserve(B, L)  # shape only: the relative-position table of the embedder is not this module's to re-plan
         f32 = lambda x: x.to(torch.float32).contiguous()
         return eng.ipa(self._s2s_block, f32(s), z.to(torch.bfloat16).contiguous(), f32(r.get_rots().get_quats()),
                        f32(r.get_trans()), f32(mask))
@@ -84,6 +84,9 @@ class TranslationIPA(nn.Module):
             self.trunk[f"bb_update_{b}"] = BackboneUpdate(c_s)
             if b < no_ipa_blocks - 1:
                 self.trunk[f"edge_transition_{b}"] = EdgeTransition(node_embed_size=c_s, edge_embed_in=c_z, edge_embed_out=c_z)
+                self.trunk[f"edge_transition_{b}"]._s2s_block = b
+            self.trunk[f"node_transition_{b}"]._s2s_block = b
+            self.trunk[f"bb_update_{b}"]._s2s_block = b
         self.torsion_pred = TorsionAngleHead(c_s, 1)
 
     def forward(self, node_embed, edge_embed, batch):
@@ -92,7 +95,7 @@ class TranslationIPA(nn.Module):
         f32 = lambda x: x.to(torch.float32).contiguous()
         node_mask, fixed = f32(batch["residue_mask"]), f32(batch["fixed_mask"])
         B, L = node_mask.shape
-        eng.reserve(B, L, batch["residue_idx"] if "residue_idx" in batch else torch.zeros(1, dtype=torch.long))
+        eng.reserve(B, L)  # shape only (the trunk reads no residue indices)
         init = f32(batch["rigids_t"])
         out7, psi = eng.trunk(f32(node_embed), edge_embed.to(torch.bfloat16).contiguous(), init, node_mask, fixed, None)
         return {"in_rigids": Rigid.from_tensor_7(init), "out_rigids": Rigid.from_tensor_7(out7), "psi": psi}

@@ -65,11 +65,17 @@ class ForwardBackwardSampler:
         return s
 
     def forward_backward(self, batch: Dict[str, torch.Tensor], rigids_0: Rigid, t_delta: float, rigids_t: torch.Tensor = None,
-                         noises=None, return_numpy: bool = True, return_rigids: bool = False):
+                         noises=None, return_numpy: bool = True, return_rigids: bool = False, seed: Optional[int] = None,
+                         first_decoy: int = 0):
         """Sample `rigids_0.shape[0]` conformations.  `rigids_t` (tensor_7) optionally replaces the internal
         perturbation (parity tests feed the reference's perturbed state); `noises[k] = (rot, trans)` injects the
-        SDE noise of iteration k."""
+        SDE noise of iteration k.  With `seed`, every random draw of decoy b (perturbation and SDE noise) is keyed by the
+        job-wide decoy id `first_decoy + b` (FrameDiffuser.decoy_noise), so a decoy's trajectory does not depend on how the job
+        is batched or sharded; without it the draws come from torch's device generator like the reference's.
+        `t_delta <= 0` (or `cfg.backward_only`) starts from the prior at T = 1 (diffusion_module.py:262-263,280-285)."""
         cfg = self.cfg
+        if cfg.backward_only:
+            t_delta = 0.0
         T = t_delta if t_delta > 0 else 1.0
         B, L = rigids_0.shape
         dev = rigids_0.device
@@ -84,9 +90,9 @@ class ForwardBackwardSampler:
         if rigids_t is None:
             if t_delta > 0:
                 rigids_t = self.diffuser.forward_marginal(rigids_0, t_delta * torch.ones(B), diffuse_mask=s["rmask64"],
-                                                          as_tensor_7=True)["rigids_t"]
+                                                          as_tensor_7=True, seed=seed, first_decoy=first_decoy)["rigids_t"]
             else:
-                rigids_t = self.diffuser.sample_prior(rigids_0.shape, dev, as_tensor_7=True)["rigids_t"]
+                rigids_t = self.diffuser.sample_prior(rigids_0.shape, dev, as_tensor_7=True, seed=seed, first_decoy=first_decoy)["rigids_t"]
         state = rigids_t.to(dev, torch.float32).contiguous().clone()
 
         # device tables for all iterations (t identical across decoys, as in the reference)
@@ -99,15 +105,16 @@ class ForwardBackwardSampler:
         sde = not cfg.probability_flow
         # Static buffers + the captured iteration are cached per (shape, mode) and reused by later calls: a call then
         # costs n graph replays and no warm-up iteration / re-capture.  The cache entry dies with the engine workspace
-        # it points into (eng.generation changes whenever s2s_reserve re-allocates).
+        # it points into (eng.token = (engine uid, generation) changes whenever s2s_reserve re-allocates or the net rebuilds
+        # its engine, e.g. after load_state_dict).
         key = (B, L, str(dev), sde, bool(cfg.self_conditioning), float(cfg.noise_scale), bool(self.use_cuda_graph))
         ctx = self._graphs.get(key)
-        if ctx is not None and ctx["generation"] != eng.generation:
-            ctx = None
+        if ctx is not None and ctx["token"] != eng.token:
+            ctx = None  # captured under another engine / workspace allocation: its pointers are dead
         fresh = ctx is None
         if fresh:
             f32 = dict(device=dev, dtype=torch.float32)
-            ctx = dict(generation=eng.generation, graph=None, per_replay=0,
+            ctx = dict(token=eng.token, graph=None, per_replay=0,
                        state=torch.empty(B, L, 7, **f32), sc=torch.zeros(B, L, 3, **f32), out7=torch.empty(B, L, 7, **f32),
                        psi=torch.empty(B, L, 2, **f32), t_cur=torch.empty(B, **f32), sched_cur=torch.empty(B, 8, **f32),
                        sched_d=torch.empty(B, 2, device=dev, dtype=torch.float64),
@@ -167,6 +174,9 @@ class ForwardBackwardSampler:
                 if sde:
                     if noises is not None:
                         rot_n.copy_(noises[k][0]); tr_n.copy_(noises[k][1])
+                    elif seed is not None:
+                        rot_n.copy_(self.diffuser.decoy_noise((B, L, 3), dev, seed, first_decoy, 16 + 2 * k))
+                        tr_n.copy_(self.diffuser.decoy_noise((B, L, 3), dev, seed, first_decoy, 17 + 2 * k))
                     else:
                         rot_n.normal_(); tr_n.normal_()
                 if graph is not None:
@@ -184,8 +194,10 @@ class ForwardBackwardSampler:
         return result
 
     # ------------------------------------------------------------------------------------------------
-    def sample(self, batch: Dict[str, torch.Tensor], t_delta: float, n_replica: Optional[int] = None):
-        """All replicas of one protein at one delta, chunked by replica_per_batch (:339-352). -> [N,L,37,3] numpy."""
+    def sample(self, batch: Dict[str, torch.Tensor], t_delta: float, n_replica: Optional[int] = None, seed: Optional[int] = None,
+               first_decoy: int = 0):
+        """All replicas of one protein at one delta, chunked by replica_per_batch (:339-352). -> [N,L,37,3] numpy.
+        `seed` / `first_decoy`: see forward_backward (replica r is job-wide decoy first_decoy + r)."""
         cfg = self.cfg
         n_replica = cfg.n_replica if n_replica is None else n_replica
         assert batch["aatype"].shape[0] == 1, "Batch size must be 1 for correct inference."
@@ -194,7 +206,7 @@ class ForwardBackwardSampler:
         while done < n_replica:
             bs = min(cfg.replica_per_batch, n_replica - done)
             r0 = Rigid.from_tensor_4x4(gt.repeat(bs, *(1,) * (gt.ndim - 1)))
-            outs.append(self.forward_backward(batch, r0, t_delta))
+            outs.append(self.forward_backward(batch, r0, t_delta, seed=seed, first_decoy=first_decoy + done))
             done += bs
         return np.concatenate(outs, axis=0)
 
@@ -208,15 +220,17 @@ class ForwardBackwardSampler:
         extra = {k: batch[k][0].detach().cpu().numpy() for k in ("aatype", "chain_index", "residue_index") if k in batch}
         return atom37_to_pdb(save_to=save_to, atom_positions=atom37, overwrite=True, **extra)
 
-    def sample_sharded(self, batch: Dict[str, torch.Tensor], t_delta: float, n_replica: int):
+    def sample_sharded(self, batch: Dict[str, torch.Tensor], t_delta: float, n_replica: int, seed: Optional[int] = None):
         """Decoy-sharded sampling under torch.distributed: rank r samples its contiguous share, then ONE
-        all_gather of the final atom coordinates.  Works with any backend (nccl on GPUs)."""
+        all_gather of the final atom coordinates.  Works with any backend (nccl on GPUs).
+        With `seed`, decoy d draws Philox subsequence d whatever the world size, so the gathered ensemble is the same
+        on 1, 2, 4 or 8 ranks (up to the fp32 reordering noise of different batch compositions)."""
         import torch.distributed as dist
 
         world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
         share = shard_bounds(n_replica, world)
         lo, hi = share[rank], share[rank + 1]
-        local = self.sample(batch, t_delta, hi - lo) if hi > lo else np.zeros((0,) + tuple(batch["aatype"].shape[1:]) + (37, 3), np.float32)
+        local = self.sample(batch, t_delta, hi - lo, seed=seed, first_decoy=lo) if hi > lo else np.zeros((0,) + tuple(batch["aatype"].shape[1:]) + (37, 3), np.float32)
         if world == 1:
             return local
         return all_gather_decoys(torch.as_tensor(local), share).numpy()

@@ -59,9 +59,9 @@ class FrameDiffuser:
         m = torch.ones(B, L, device=dev) if mask is None else mask.to(dev, torch.float32).contiguous()
         rs = torch.empty(B, L, 3, device=dev, dtype=torch.float64)
         ts = torch.empty(B, L, 3, device=dev, dtype=torch.float64)
-        p = _lib.ptr
-        _lib.check(_lib.load().s2s_se3_step(B, L, p(rt), p(r0), p(m), None, p(sf), p(sd), None, None, C.c_float(1.0), 1, 1,
-                                            p(rs), p(ts), None, _lib.stream()))
+        p, pd = _lib.ptr, _lib.ptr_f64
+        _lib.check(_lib.load().s2s_se3_step(B, L, p(rt), p(r0), p(m), None, p(sf), pd(sd), None, None, C.c_float(1.0), 1, 1,
+                                            pd(rs), pd(ts), None, _lib.stream(dev)))
         if mask is None or mask.dtype != torch.float64:
             rs, ts = rs.float(), ts.float()  # without fp64 masks the reference's scores stay fp32
         return {"trans_score": ts, "rot_score": rs}
@@ -85,9 +85,9 @@ class FrameDiffuser:
             trans_noise = torch.randn(B, L, 3, device=dev) if trans_noise is None else trans_noise.to(dev, torch.float32).contiguous()
         ones = torch.ones(B, L, device=dev)
         out = torch.empty(B, L, 7, device=dev, dtype=torch.float32)
-        p = _lib.ptr
-        _lib.check(_lib.load().s2s_se3_step(B, L, p(rt), None, p(ones), p(dm), p(sf), p(sd), p(rot_noise), p(trans_noise),
-                                            C.c_float(noise_scale), int(probability_flow), 2, p(rs), p(ts), p(out), _lib.stream()))
+        p, pd = _lib.ptr, _lib.ptr_f64
+        _lib.check(_lib.load().s2s_se3_step(B, L, p(rt), None, p(ones), p(dm), p(sf), pd(sd), p(rot_noise), p(trans_noise),
+                                            C.c_float(noise_scale), int(probability_flow), 2, pd(rs), pd(ts), p(out), _lib.stream(dev)))
         return Rigid.from_tensor_7(out)
 
     def score_and_reverse(self, rigids_0_7, rigids_t_7, residue_mask, diffuse_mask, sched_f, sched_d, out,
@@ -96,15 +96,26 @@ class FrameDiffuser:
         B, L = rigids_t_7.shape[:2]
         p = _lib.ptr
         _lib.check(_lib.load().s2s_se3_step(B, L, p(rigids_t_7), p(rigids_0_7), p(residue_mask), p(diffuse_mask), p(sched_f),
-                                            p(sched_d), p(rot_noise), p(trans_noise), C.c_float(noise_scale),
-                                            int(probability_flow), 0, None, None, p(out), _lib.stream()))
+                                            _lib.ptr_f64(sched_d), p(rot_noise), p(trans_noise), C.c_float(noise_scale),
+                                            int(probability_flow), 0, None, None, p(out), _lib.stream(rigids_t_7.device)))
+        return out
+
+    @staticmethod
+    def decoy_noise(shape, device, seed: int, first_decoy: int, stream_id: int, uniform: bool = False) -> torch.Tensor:
+        """[B, ...] draws keyed by global decoy id (s2s_rng_fill): decoy b of this call reads Philox subsequence first_decoy + b
+        of `seed`, so its values do not depend on the batch / rank / world size it is sampled in."""
+        out = torch.empty(*shape, device=device, dtype=torch.float32)
+        B = shape[0]
+        _lib.check(_lib.load().s2s_rng_fill(_lib.ptr(out), B, out.numel() // B, int(seed) & (2 ** 64 - 1), int(first_decoy),
+                                            int(stream_id), int(uniform), _lib.stream(out.device)))
         return out
 
     def forward_marginal(self, rigids_0: Rigid, t: torch.Tensor, diffuse_mask: torch.Tensor = None, as_tensor_7: bool = True,
-                         noise=None):
-        """`noise` = (axis [B,L,3] N(0,1), u [B,L] U[0,1), trans [B,L,3] N(0,1)) optionally injected; otherwise drawn
-        on the device in the reference's order (so3.py:259,262; r3.py:66).  Scores of the perturbation, which the
-        sampler discards (diffusion_module.py:274-279), are returned as None."""
+                         noise=None, seed: Optional[int] = None, first_decoy: int = 0):
+        """`noise` = (axis [B,L,3] N(0,1), u [B,L] U[0,1), trans [B,L,3] N(0,1)) optionally injected.  With `seed` the three
+        draws are keyed by global decoy id (`decoy_noise`); otherwise they come from torch's device generator in the
+        reference's order (so3.py:259,262; r3.py:66).  Scores of the perturbation, which the sampler discards
+        (diffusion_module.py:274-279), are returned as None."""
         rot0 = rigids_0.get_rots().get_rot_mats().to(torch.float32).contiguous()
         x0 = rigids_0.get_trans().to(torch.float32).contiguous()
         B, L = x0.shape[:2]
@@ -116,27 +127,36 @@ class FrameDiffuser:
         cdf = torch.from_numpy(np.stack([self.rot_diffuser.cdf_row(int(i)) for i in idx])).to(dev).contiguous()
         omega = self.rot_diffuser.discrete_omega.float().contiguous().to(dev)
         if noise is None:
-            noise = (torch.randn(B, L, 3, device=dev), torch.rand(B, L, device=dev), torch.randn(B, L, 3, device=dev))
+            if seed is not None:
+                noise = (self.decoy_noise((B, L, 3), dev, seed, first_decoy, 0), self.decoy_noise((B, L), dev, seed, first_decoy, 1, True),
+                         self.decoy_noise((B, L, 3), dev, seed, first_decoy, 2))
+            else:
+                noise = (torch.randn(B, L, 3, device=dev), torch.rand(B, L, device=dev), torch.randn(B, L, 3, device=dev))
         ax, u, zt = [n.to(dev, torch.float32).contiguous() for n in noise]
         dm = None if diffuse_mask is None else torch.as_tensor(diffuse_mask).to(dev, torch.float32).contiguous()
         out = torch.empty(B, L, 7, device=dev, dtype=torch.float32)
         p = _lib.ptr
-        _lib.check(_lib.load().s2s_se3_perturb(B, L, p(rot0), p(x0), p(dm), p(sf), p(cdf), p(omega), p(ax), p(u), p(zt), p(out),
-                                               _lib.stream()))
+        _lib.check(_lib.load().s2s_se3_perturb(B, L, p(rot0), p(x0), p(dm), p(sf), _lib.ptr_f64(cdf), p(omega), p(ax), p(u), p(zt), p(out),
+                                               _lib.stream(dev)))
         rigids_t = out if as_tensor_7 else Rigid.from_tensor_7(out)
         return {"rigids_t": rigids_t, "trans_score": None, "rot_score": None,
                 "trans_score_scaling": self.trans_diffuser.score_scaling(t), "rot_score_scaling": None}
 
     def sample_prior(self, shape, device, reference_rigids: Rigid = None, diffuse_mask: torch.Tensor = None,
-                     as_tensor_7: bool = False):
-        """frame.py:212-255 without reference rigids: rot ~ IGSO3(t=1) about a uniform axis, trans ~ N(0,1)/0.1."""
+                     as_tensor_7: bool = False, noise=None, seed: Optional[int] = None, first_decoy: int = 0):
+        """frame.py:212-255 without reference rigids (`backward_only: true`): rotation ~ IGSO3(t = 1) about a uniform axis
+        (so3.py:244-272 via sample_ref at t = 1: the identity composed with the sampled rotation vector), translation ~
+        N(0, 1) / coordinate_scaling (r3.py:76-77).  `noise` = (axis, u, trans) as in forward_marginal."""
         if reference_rigids is not None or diffuse_mask is not None:
             raise ValueError("sample_prior with reference_rigids is a motif-scaffolding path the sampler never takes")
         B, L = shape
-        eye = torch.eye(3, device=device).expand(B, L, 3, 3).contiguous()
         zero = Rigid.from_tensor_4x4(torch.eye(4, device=device).expand(B, L, 4, 4))
-        # identity frames perturbed at t=1: rotation = IGSO3 sample; translation = N(0,1) * sqrt(1-e^-beta(1)) ~ N(0,1)
-        out = self.forward_marginal(zero, torch.ones(B), None, as_tensor_7=True)["rigids_t"]
-        out[..., 4:] = torch.randn(B, L, 3, device=device) / self.trans_diffuser.coordinate_scaling
-        del eye
+        if noise is None and seed is None:
+            noise = (torch.randn(B, L, 3, device=device), torch.rand(B, L, device=device), torch.randn(B, L, 3, device=device))
+        elif noise is None:
+            noise = (self.decoy_noise((B, L, 3), device, seed, first_decoy, 0), self.decoy_noise((B, L), device, seed, first_decoy, 1, True),
+                     self.decoy_noise((B, L, 3), device, seed, first_decoy, 2))
+        # identity frames perturbed at t = 1 give the rotation; the translation is then replaced by the prior draw itself
+        out = self.forward_marginal(zero, torch.ones(B), None, as_tensor_7=True, noise=noise)["rigids_t"]
+        out[..., 4:] = noise[2].to(device, torch.float32) / self.trans_diffuser.coordinate_scaling
         return {"rigids_t": out if as_tensor_7 else Rigid.from_tensor_7(out)}

@@ -55,18 +55,26 @@ class SO3Diffuser:
         """Row `idx` of the reference's `_cdf` table (fp64 [num_omega])."""
         if idx not in self._cdf_rows:
             path = os.path.join(self.cache_dir, f"cdf_row_{idx}.npy")
+            row = None
             if os.path.exists(path):
-                row = np.load(path)
-            else:
+                try:
+                    row = np.load(path)
+                    if row.shape != (self.num_omega,):
+                        row = None
+                except (OSError, ValueError, EOFError):
+                    row = None  # unreadable / partly written by another process: recompute
+            if row is None:
                 omega = self.discrete_omega.numpy()
                 sig = self.discrete_sigma.numpy()[idx]
                 ls = np.arange(1000)[None]
                 om = omega[..., None]
                 f = ((2 * ls + 1) * np.exp(-ls * (ls + 1) * sig ** 2 / 2) * np.sin(om * (ls + 1 / 2)) / np.sin(om / 2)).sum(-1)
                 row = (f * (1.0 - np.cos(omega)) / np.pi).cumsum() / self.num_omega * np.pi
-                try:
+                try:  # write to a private temporary file, then rename: readers never see a partial row
                     os.makedirs(self.cache_dir, exist_ok=True)
-                    np.save(path, row)
+                    tmp = f"{path}.{os.getpid()}.tmp.npy"
+                    np.save(tmp, row)
+                    os.replace(tmp, path)
                 except OSError:
                     pass
             self._cdf_rows[idx] = row

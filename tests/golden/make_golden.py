@@ -121,11 +121,75 @@ def trajectory(net, diffuser, name, B, L, n, n_pad, n_fixed, seed):
         meta=np.array([B, L, n, n_pad, n_fixed, seed]))
 
 
+def teacher_forced(name, B, L, n, n_pad, seed, final_scale):
+    """Per-step records of the unmodified reference on the STRESS fixture (final_scale = 0.1): the state
+    entering every iteration (rigids_t, sc_ca_t, t) and what the reference makes of it (network output, next state), so
+    that a candidate can be driven step by step from the reference's own states and compared one step at a time."""
+    net, diffuser = build_reference(final_scale)
+    feats = synthetic.make_features(B, L, seed=seed, n_pad=n_pad, n_fixed=0, random_aatype=True)
+    q, x = synthetic.make_backbone(L, seed=seed)
+    r0 = rigid_from_quat_trans(q[None].repeat(B, 1, 1), x[None].repeat(B, 1, 1))
+    torch.manual_seed(123)
+    np.random.seed(123)
+    rigids_t = diffuser.forward_marginal(rigids_0=r0, t=0.5 * torch.ones(B), diffuse_mask=feats["residue_mask"],
+                                         as_tensor_7=True)["rigids_t"]
+    ts = np.linspace(0.01, 0.5, n)[::-1]
+    dt = 1.0 / n
+    _f = deepcopy(feats)
+    _f["rigids_t"] = rigids_t
+    rec = dict(state=[], sc=[], out=[], psi=[], nxt=[])
+    with torch.no_grad():
+        diffuse_mask = (1 - _f["fixed_mask"]) * _f["residue_mask"]
+        _f["sc_ca_t"] = torch.zeros_like(rigids_t[..., 4:])
+        _f["t"] = ts[0] * torch.ones(B)
+        _f["sc_ca_t"] = net(_f, as_tensor_7=True)["rigids"][..., 4:]
+        for t in ts[:-1]:
+            _f["t"] = t * torch.ones(B)
+            rec["state"].append(_f["rigids_t"].clone()); rec["sc"].append(_f["sc_ca_t"].clone())
+            out = net(_f, as_tensor_7=False)
+            o7 = out["rigids"].to_tensor_7()
+            rec["out"].append(o7.clone()); rec["psi"].append(out["psi"].clone())
+            _f["sc_ca_t"] = o7[..., 4:]
+            sc = diffuser.score(rigids_0=out["rigids"], rigids_t=Rigid.from_tensor_7(_f["rigids_t"]), t=_f["t"],
+                                mask=_f["residue_mask"])
+            nxt = diffuser.reverse(rigids_t=Rigid.from_tensor_7(_f["rigids_t"]), rot_score=sc["rot_score"],
+                                   trans_score=sc["trans_score"], t=_f["t"], dt=dt, diffuse_mask=diffuse_mask,
+                                   center_trans=True, noise_scale=1.0, probability_flow=True).to_tensor_7()
+            rec["nxt"].append(nxt.clone())
+            _f["rigids_t"] = nxt
+    npz(name, ts=ts[:-1], **{k: torch.stack(v) for k, v in rec.items()},
+        meta=np.array([B, L, n, n_pad, 0, seed]), final_scale=np.array(final_scale))
+
+
 def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else ""
+    if mode == "stress":
+        teacher_forced("stress_L64_n25_fs0p1.npz", 2, 64, 25, 3, 13, 0.1)
+        return
     net, diffuser = build_reference()
-    if len(sys.argv) > 1 and sys.argv[1] == "traj128":
+    if mode == "traj128":
         # a chain length the tcgen05 pair kernels take (L % 128 == 0), two decoys, padded tail: 20 denoising steps
         trajectory(net, diffuser, "traj_L128_n20.npz", 2, 128, 20, 4, 0, 9)
+        return
+    if mode == "traj256":
+        # BASELINE cfg 2's own size: L = 256, 100 denoising steps; two decoys with a padded tail
+        trajectory(net, diffuser, "traj_L256_n100.npz", 2, 256, 100, 6, 0, 11)
+        return
+    if mode == "prior":
+        # FrameDiffuser.sample_prior (backward_only: true) with the draws it consumes captured: randn [B,L,3] (axis),
+        # rand [B,L] (CPU generator, so3.py:262), randn [B,L,3] (translation, r3.py:37-38)
+        B, L = 3, 20
+        torch.manual_seed(31)
+        ax, u, zt = torch.randn(B, L, 3), torch.rand(B, L), torch.randn(B, L, 3)
+        torch.manual_seed(31)
+        pr = diffuser.sample_prior((B, L), torch.device("cpu"), as_tensor_7=True)["rigids_t"]
+        npz("sample_prior.npz", axis=ax, u=u, z=zt, rigids_t=pr, cdf_row_999=diffuser.rot_diffuser._cdf[999].numpy())
+        return
+    if mode == "ragged":
+        # chain lengths that are not a multiple of any tile size (the library pads them internally)
+        trajectory(net, diffuser, "traj_L57_n8.npz", 2, 57, 8, 3, 1, 15)
+        trajectory(net, diffuser, "traj_L100_n6.npz", 2, 100, 6, 0, 0, 17)
+        trajectory(net, diffuser, "traj_L250_n4.npz", 1, 250, 4, 5, 0, 19)
         return
 
     # --- A. one network forward, small, with padding / fixed residues / chain break / mixed aatype --------

@@ -16,7 +16,9 @@ from oracle import str2str_oracle as O
 from str2str_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
-# (pair_kernels, node_gemm): 0/0 = SIMT pair kernels + exact fp32 node GEMMs, 1/1 = tcgen05 everywhere (the default)
+# (pair_kernels, node_gemm): 0/0 = SIMT pair kernels + exact fp32 node GEMMs (on-device cross-check), 1/1 = tcgen05 everywhere
+# (the default; chain lengths that are not a multiple of 32 are padded inside the library).  The production configuration is
+# pinned directly against the oracle in tests/test_gpu_production.py.
 PAIR_MODES = [(0, 0), (1, 0), (1, 1)]
 
 
@@ -216,7 +218,7 @@ def test_pair_kernels_tc_vs_simt(params, L):
     feats["sc_ca_t"] = (x[None] + torch.randn(B, L, 3, generator=g)).float()
     feats["t"] = torch.tensor([0.4, 0.6])
     outs = []
-    for pair in (0, 1, 2):
+    for pair in (0, 1):
         net = make_net(params, pair, 0)
         eng = net.native("cuda")
         fc = cuda(feats)
@@ -224,9 +226,8 @@ def test_pair_kernels_tc_vs_simt(params, L):
         node, z = eng.embed(fc["t"], fc["residue_idx"], fc["fixed_mask"].float(), fc["sc_ca_t"], fc["residue_mask"].float())
         z2 = eng.edge_transition(0, node, z, fc["residue_mask"].float().contiguous())
         outs.append((z.float().cpu(), z2.float().cpu()))
-    for k in (1, 2):
-        assert rel(outs[k][0], outs[0][0]) < 3e-3   # bf16 output rounding of slightly different fp32 sums
-        assert rel(outs[k][1], outs[0][1]) < 3e-3, (k, rel(outs[k][1], outs[0][1]))
+    assert rel(outs[1][0], outs[0][0]) < 3e-3   # bf16 output rounding of slightly different fp32 sums
+    assert rel(outs[1][1], outs[0][1]) < 3e-3, rel(outs[1][1], outs[0][1])
 
 
 def test_se3_equivariance_full_size(params):

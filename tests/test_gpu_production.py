@@ -1,0 +1,436 @@
+"""GPU parity tests of the PRODUCTION configuration (tcgen05 pair kernels + tensor-core node track, the defaults) through
+the C ABI, directly against the CPU oracle and goldens of the unmodified reference.  Run on the B200 box: pytest -m gpu
+
+What is pinned here (each against the oracle / the reference, never against another kernel of this repo):
+  * the tcgen05 EdgeTransition and edge-embedder kernels at L = 128 / 256 / 384 (row tiles inside one i row) and at chain
+    lengths that are not a multiple of any tile (flattened tiles + internal padding);
+  * the whole network forward at L = 24 ... 300, trajectories at ragged lengths and at BASELINE cfg 2's own size
+    (256 residues x 100 denoise steps) against trajectories of the unmodified reference;
+  * the stress fixture (final_scale = 0.1) step by step from the reference's own states, with the oracle's
+    fp32 reordering noise floor printed beside every number;
+  * sample_prior / backward_only, the device RNG (KS test of the IGSO(3) angle marginal), decoy-id keyed seeding;
+  * module-level drop-ins (NodeTransition, TorsionAngleHead, BackboneUpdate, EdgeTransition forward).
+
+Tolerances (relative L2 unless stated): pair tensor z (stored in bf16 by design: 2^-9 = 2e-3 per element) 2.5e-3 with a
+max-abs bound; C-alpha of network outputs / trajectories 1e-4 (BASELINE.json north_star).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import str2str_oracle as O
+from str2str_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def load(golden_dir, name):
+    return {k: torch.as_tensor(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def cuda(d):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+def make_net(params, pair_kernels=1, node_gemm=1):
+    from str2str_b200.net import DenoisingNet, EmbeddingModule, TranslationIPA
+
+    net = DenoisingNet(
+        EmbeddingModule(init_embed_size=32, node_embed_size=256, edge_embed_size=128),
+        TranslationIPA(c_s=256, c_z=128, coordinate_scaling=0.1, no_ipa_blocks=4, skip_embed_size=64),
+        pair_kernels=pair_kernels, node_gemm=node_gemm,
+    )
+    net.load_state_dict(params, strict=True)
+    return net.cuda().eval()
+
+
+def make_diffuser(tmp="/tmp/str2str_b200_cache"):
+    from str2str_b200.score import FrameDiffuser, R3Diffuser, SO3Diffuser
+
+    return FrameDiffuser(R3Diffuser(0.1, 20.0, 0.1), SO3Diffuser(cache_dir=tmp), min_t=1e-2)
+
+
+class kernel_log:
+    """Names of the library kernels launched inside the block (the per-kernel event timing of s2s_profile_*)."""
+
+    def __enter__(self):
+        from str2str_b200 import _lib
+
+        self.lib = _lib.load()
+        self.lib.s2s_profile_reset()
+        self.lib.s2s_profile_enable(1)
+        self.names = {}
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.synchronize()
+        self.lib.s2s_profile_enable(0)
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.s2s_profile_list(buf, len(buf))
+        assert n >= 0
+        for ln in buf.value.decode().splitlines():
+            name, ms, cnt = ln.split("\t")
+            self.names[name] = int(cnt)
+        self.lib.s2s_profile_reset()
+
+
+def module_inputs(B, L, seed, n_pad):
+    """Masked node / pair embeddings of realistic scale plus frames: what the trunk hands its sub-modules."""
+    g = torch.Generator().manual_seed(seed)
+    nm = torch.ones(B, L)
+    if n_pad:
+        nm[B - 1, L - n_pad:] = 0
+    node = torch.randn(B, L, 256, generator=g) * nm[..., None]
+    edge = (torch.randn(B, L, L, 128, generator=g) * (nm[..., None] * nm[..., None, :])[..., None]).bfloat16()
+    return nm, node, edge
+
+
+# ---- (a) the production pair kernels, directly against the oracle -------------------------------------------------------
+@pytest.mark.parametrize("L", [128, 256, 384, 24, 57, 100, 160])
+def test_edge_transition_tcgen05_vs_oracle(params, L):
+    """s2s_edge_transition with the default (tcgen05) kernels against the fp32 oracle on the same bf16 pair tensor:
+    L % 128 == 0 (one i row per tile), L % 32 == 0 (flattened tiles: 160), and lengths the library pads (24, 57, 100).
+    Pure bf16 output rounding is ~1.1e-3 relative; the gate is 2.5e-3 plus a max-abs bound that a wrong u_i / p_i / n'_j row
+    (an O(1) shift of a whole row) cannot pass."""
+    B = 2 if L <= 256 else 1
+    nm, node, edge = module_inputs(B, L, 100 + L, 5 if L >= 57 else 2)
+    net = make_net(params)
+    eng = net.native("cuda")
+    eng.reserve(B, L)
+    with kernel_log() as kl:
+        out = eng.edge_transition(1, node.cuda().contiguous(), edge.cuda().contiguous(), nm.cuda().contiguous())
+    assert kl.names.get("edge_transition", 0) == 1 and "edge_transition_simt" not in kl.names, kl.names
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = O.edge_transition(params, "translator.trunk.edge_transition_1.", node, edge.float())
+    ref = ref * (nm[..., None] * nm[..., None, :])[..., None]
+    r, mx = rel(out.float(), ref), float((out.float().cpu() - ref).abs().max())
+    print(f"EdgeTransition tcgen05 L={L}: rel {r:.2e}, max|d| {mx:.3f} (values are LayerNorm outputs, O(1))")
+    assert r < 2.5e-3 and mx < 0.06
+    assert float(out.float().cpu()[B - 1, -1].abs().max()) == 0.0  # masked rows are exactly zero
+
+
+@pytest.mark.parametrize("L", [128, 256, 384, 24, 57, 100, 160])
+def test_edge_embedder_tcgen05_vs_oracle(params, L):
+    """s2s_embed with the default (tcgen05 pipeline) kernel against the oracle: chain break, fixed residues, per-decoy t."""
+    B = 2 if L <= 256 else 1
+    f = synthetic.make_features(B, L, seed=200 + L, n_pad=3, n_fixed=2)
+    ridx = f["residue_idx"].clone()
+    ridx[:, L // 2:] += 37  # chain break: offsets far outside [-L, L]
+    q, x = synthetic.make_backbone(L, seed=200 + L)
+    g = torch.Generator().manual_seed(L)
+    sc = (x[None] + 2.0 * torch.randn(B, L, 3, generator=g)).float()
+    t = torch.tensor([0.3, 0.7])[:B]
+    net = make_net(params)
+    eng = net.native("cuda")
+    eng.reserve(B, L, ridx)
+    rm = f["residue_mask"].float()
+    with kernel_log() as kl:
+        node, z = eng.embed(t.cuda(), ridx.cuda(), f["fixed_mask"].float().cuda(), sc.cuda(), rm.cuda())
+    assert kl.names.get("edge_embed", 0) == 1 and "edge_embed_simt" not in kl.names, kl.names
+    node_o, edge_o = O.embedder(params, ridx, t, f["fixed_mask"].float(), sc)
+    node_o = node_o * rm[..., None]
+    edge_o = edge_o * (rm[..., None] * rm[..., None, :])[..., None]
+    r, mx = rel(z.float(), edge_o), float((z.float().cpu() - edge_o).abs().max())
+    print(f"edge embedder tcgen05 L={L}: rel {r:.2e}, max|d| {mx:.3f}; node rel {rel(node, node_o):.2e}")
+    assert rel(node, node_o) < 2e-5
+    assert r < 2.5e-3 and mx < 0.06  # a wrong distogram bin or relative-position offset shifts a whole row by O(1)
+
+
+@pytest.mark.parametrize("L", [24, 57, 100, 250])
+def test_ipa_block_general_length_vs_oracle(params, L):
+    """IPA block (tensor-core projections, fused pair kernel) at chain lengths the library pads internally."""
+    from str2str_b200.rigid import Rigid
+
+    B = 2
+    nm, node, edge = module_inputs(B, L, 300 + L, 3)
+    q, x = synthetic.make_backbone(L, seed=300 + L)
+    g = torch.Generator().manual_seed(L)
+    rig = torch.cat([q, 0.1 * x], -1)[None].repeat(B, 1, 1) + 0.05 * torch.randn(B, L, 7, generator=g)
+    net = make_net(params)
+    out = net.translator.trunk["ipa_1"](node.cuda(), edge.cuda(), Rigid.from_tensor_7(rig.cuda()), nm.cuda())
+    ref = O.ipa(params, "translator.trunk.ipa_1.", node, edge.float(), rig[..., :4], rig[..., 4:], nm)
+    valid = nm.bool()
+    r = rel(out.cpu()[valid], ref[valid])
+    print(f"ipa (padded internally) L={L}: rel {r:.2e}")
+    assert r < 5e-3  # single-pass bf16 projections / logits / P.v by design (tools/precision_probe.py)
+
+
+# ---- whole forward at arbitrary chain lengths -------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [24, 57, 64, 100, 250, 300])
+def test_network_forward_any_length_vs_oracle(params, L):
+    """DenoisingNet.forward on the production path against the oracle at lengths that are / are not tile multiples, with
+    masked tail residues in the caller's batch (they stay keys of the sequence transformer with +1 bias, A.6) next to
+    the library's own padding (which must not)."""
+    B = 2
+    f = synthetic.make_features(B, L, seed=400 + L, n_pad=3, n_fixed=1, random_aatype=True)
+    q, x = synthetic.make_backbone(L, seed=400 + L)
+    g = torch.Generator().manual_seed(L)
+    f["rigids_t"] = (torch.cat([q, x], -1)[None].repeat(B, 1, 1) + 0.2 * torch.randn(B, L, 7, generator=g)).float()
+    f["sc_ca_t"] = (x[None] + torch.randn(B, L, 3, generator=g)).float()
+    f["t"] = torch.tensor([0.35, 0.6])
+    net = make_net(params)
+    with torch.no_grad(), kernel_log() as kl:
+        out = net(cuda(f), as_tensor_7=True)
+    assert kl.names.get("edge_transition", 0) == 3 and kl.names.get("edge_embed", 0) == 1 and kl.names.get("ipa_pair_attention", 0) == 4
+    assert not any(k.endswith("_simt") for k in kl.names), kl.names
+    ref = O.denoising_net(params, f)
+    valid = f["residue_mask"].bool()
+    r_ca = rel(out["rigids"].cpu()[valid][:, 4:], ref["rigids"][valid][:, 4:])
+    r_q = rel(out["rigids"].cpu()[valid][:, :4], ref["rigids"][valid][:, :4])
+    print(f"forward L={L}: C-alpha rel {r_ca:.2e}, quaternion rel {r_q:.2e}")
+    assert r_ca < 1e-4 and r_q < 1e-4
+    assert rel(out["atom37"].cpu()[valid][:, :5], ref["atom37"][valid][:, :5]) < 1e-4
+    assert tuple(out["rigids"].shape) == (B, L, 7) and tuple(out["atom37"].shape) == (B, L, 37, 3)
+
+
+def _run_traj(golden_dir, params, name, graph=True, gate=1e-4):
+    from str2str_b200.rigid import Rigid
+    from str2str_b200.sampler import ForwardBackwardSampler, InferenceConfig
+
+    g = load(golden_dir, name)
+    B, L, n, n_pad, n_fixed, seed = [int(v) for v in g["meta"]]
+    feats = synthetic.make_features(1, L, seed=seed, n_pad=n_pad, n_fixed=n_fixed, random_aatype=True)
+    net = make_net(params)
+    smp = ForwardBackwardSampler(net, make_diffuser(), InferenceConfig(num_timesteps=2 * n, min_t=0.01), use_cuda_graph=graph)
+    q, x = synthetic.make_backbone(L, seed=seed)
+    r0 = Rigid.from_tensor_7(torch.cat([q, x], -1)[None].repeat(B, 1, 1).cuda(), normalize_quats=True)
+    atom37, fin, psi = smp.forward_backward(cuda(feats), r0, 0.5, rigids_t=g["rigids_t"].cuda(), return_rigids=True)
+    valid = synthetic.make_features(B, L, seed=seed, n_pad=n_pad, n_fixed=n_fixed)["residue_mask"].bool()
+    ca, ca_ref = fin.cpu()[..., 4:][valid], g["final_rigids"][..., 4:][valid]
+    r = rel(ca, ca_ref)
+    print(f"{name} graph={graph}: C-alpha rel-L2 {r:.3e}, max|d| {float((ca - ca_ref).abs().max()):.3e} A, launches {smp.launches}")
+    assert r < gate
+    assert rel(torch.as_tensor(atom37)[valid][:, :5], g["final_atom37"][valid]) < gate
+    return r
+
+
+@pytest.mark.parametrize("name", ["traj_L57_n8.npz", "traj_L100_n6.npz", "traj_L250_n4.npz"])
+def test_trajectory_ragged_lengths_vs_reference_golden(golden_dir, params, name):
+    """Full trajectories of the UNMODIFIED reference at chain lengths 57 / 100 / 250 (padded tails, a fixed residue)."""
+    _run_traj(golden_dir, params, name)
+
+
+def test_trajectory_cfg2_size_vs_reference_golden(golden_dir, params):
+    """BASELINE.json configs[1]'s own size: 256 residues x 100 denoise steps (two decoys, padded tail), CUDA-graph replay as in
+    bench.py, against the trajectory of the UNMODIFIED reference: final C-alpha within 1e-4 relative."""
+    _run_traj(golden_dir, params, "traj_L256_n100.npz")
+
+
+# ---- (c) stress fixture, teacher-forced --------------------------------------------------------------------------------
+def test_stress_fixture_teacher_forced_per_step(golden_dir):
+    """final_scale = 0.1 (the reference's own fp32 noise floor exceeds 1e-4 on long trajectories there, so full
+    trajectories are not a meaningful gate): every iteration is started from the REFERENCE's state (rigids_t, sc_ca_t, t) and
+    the network output and the next state are compared with the reference's, one step at a time.  Beside every error the
+    oracle's reordering noise floor is printed: the oracle re-run with 1e-6 relative jitter on every nn.Linear output."""
+    from str2str_b200.sampler import InferenceConfig  # noqa: F401  (import check)
+
+    g = load(golden_dir, "stress_L64_n25_fs0p1.npz")
+    B, L, n, n_pad, _, seed = [int(v) for v in g["meta"]]
+    params = synthetic.make_state_dict(seed=0, final_scale=float(g["final_scale"]))
+    feats = synthetic.make_features(B, L, seed=seed, n_pad=n_pad, n_fixed=0, random_aatype=True)
+    net = make_net(params)
+    d = make_diffuser()
+    valid = feats["residue_mask"].bool()
+    diffuse = ((1 - feats["fixed_mask"]) * feats["residue_mask"]).float().cuda()
+    rmask = feats["residue_mask"].float().cuda()
+    worst_out = worst_nxt = worst_floor = 0.0
+    gen = torch.Generator().manual_seed(0)
+    orig_lin = O.lin
+    steps = range(len(g["ts"]))
+    for k in steps:
+        f = dict(feats, rigids_t=g["state"][k], sc_ca_t=g["sc"][k], t=float(g["ts"][k]) * torch.ones(B))
+        with torch.no_grad():
+            out = net(cuda(f), as_tensor_7=True)["rigids"]
+        e_out = rel(out.cpu()[valid][:, 4:], g["out"][k][valid][:, 4:])
+        sf, sd, _ = d._sched(f["t"], 1.0 / n, "cuda")
+        nxt = torch.empty(B, L, 7, device="cuda")
+        d.score_and_reverse(out, g["state"][k].cuda().contiguous(), rmask, diffuse, sf, sd, nxt)
+        e_nxt = rel(nxt.cpu()[valid][:, 4:], g["nxt"][k][valid][:, 4:])
+        floor = float("nan")
+        if k % 6 == 0:  # the oracle's own noise floor on this step
+            def jitter_lin(p, name, x):
+                y = orig_lin(p, name, x)
+                return y * (1 + 1e-6 * torch.randn(y.shape, generator=gen))
+            O.lin = jitter_lin
+            try:
+                with torch.no_grad():
+                    jo = O.denoising_net(params, f)["rigids"]
+            finally:
+                O.lin = orig_lin
+            floor = rel(jo[valid][:, 4:], g["out"][k][valid][:, 4:])
+            worst_floor = max(worst_floor, floor)
+        print(f"stress step {k:2d} t={float(g['ts'][k]):.3f}: net C-alpha rel {e_out:.2e}, next-state rel {e_nxt:.2e}, oracle jitter floor {floor:.2e}")
+        worst_out, worst_nxt = max(worst_out, e_out), max(worst_nxt, e_nxt)
+    print(f"stress fixture: worst per-step net error {worst_out:.2e}, next state {worst_nxt:.2e}, oracle noise floor {worst_floor:.2e}")
+    assert worst_out < 1e-4 and worst_nxt < 1e-4
+
+
+# ---- (d) prior sampling, device RNG, decoy-keyed seeding ---------------------------------------------------------------
+def test_sample_prior_vs_reference_golden(golden_dir):
+    """FrameDiffuser.sample_prior (frame.py:212-255, `backward_only: true`) with the reference's own draws injected."""
+    g = load(golden_dir, "sample_prior.npz")
+    d = make_diffuser()
+    assert np.array_equal(d.rot_diffuser.cdf_row(999), g["cdf_row_999"].numpy())
+    B, L = g["u"].shape
+    out = d.sample_prior((B, L), torch.device("cuda"), as_tensor_7=True, noise=(g["axis"], g["u"], g["z"]))["rigids_t"].cpu()
+    assert rel(out[..., 4:], g["rigids_t"][..., 4:]) < 1e-6
+    # the reference's matrix -> quaternion conversion does not fix the sign (A.6): compare rotations, not quaternions
+    Ra, Rb = O.quat_to_rotmat(out[..., :4].double()), O.quat_to_rotmat(g["rigids_t"][..., :4].double())
+    assert float((Ra - Rb).abs().max()) < 5e-6
+
+
+def test_backward_only_sampler_runs_from_prior(params):
+    """`inference.backward_only: true`: trajectories start from the prior at T = 1 (diffusion_module.py:262-263) and run
+    num_timesteps iterations; seeded draws make the run reproducible and independent of batching."""
+    from str2str_b200.rigid import Rigid
+    from str2str_b200.sampler import ForwardBackwardSampler, InferenceConfig
+
+    L = 40
+    feats = cuda(synthetic.make_features(1, L, seed=3))
+    q, x = synthetic.make_backbone(L, seed=3)
+    net = make_net(params)
+    smp = ForwardBackwardSampler(net, make_diffuser(), InferenceConfig(num_timesteps=6, min_t=0.01, backward_only=True))
+    r0 = lambda B: Rigid.from_tensor_7(torch.cat([q, x], -1)[None].repeat(B, 1, 1).cuda(), normalize_quats=True)
+    a = smp.forward_backward(feats, r0(3), 0.5, seed=11, first_decoy=0)
+    b = smp.forward_backward(feats, r0(2), 0.5, seed=11, first_decoy=1)  # decoys 1, 2 of the same job, different batch
+    assert a.shape == (3, L, 37, 3) and np.isfinite(a).all()
+    assert np.abs(a[1:, :, 1] - b[:, :, 1]).max() < 1e-3 * np.abs(a[:, :, 1]).max()
+    assert np.abs(a[0, :, 1] - a[1, :, 1]).max() > 1.0  # different decoys really differ
+
+
+def test_device_rng_igso3_angle_marginal_ks():
+    """The device perturbation (s2s_rng_fill -> s2s_se3_perturb) samples the IGSO(3) rotation angle by inverting the same CDF
+    row the reference interpolates (so3.py:262-268): Kolmogorov-Smirnov test of the angle of R_t R_0^T against that row,
+    uniformity of the axis, and the Gaussian moments of the translation noise."""
+    from scipy import stats
+
+    from str2str_b200.rigid import Rigid
+
+    d = make_diffuser()
+    B, L, t = 8, 512, 0.6
+    eye = Rigid.from_tensor_4x4(torch.eye(4, device="cuda").expand(B, L, 4, 4))
+    out = d.forward_marginal(eye, t * torch.ones(B), None, as_tensor_7=True, seed=2024, first_decoy=0)["rigids_t"].cpu().double()
+    qn = out[..., :4] / out[..., :4].norm(dim=-1, keepdim=True)
+    omega = (2 * torch.atan2(qn[..., 1:].norm(dim=-1), qn[..., 0].abs())).reshape(-1).numpy()
+    idx = int(d.rot_diffuser.t_to_idx(torch.tensor([t]))[0])
+    grid, cdf = d.rot_diffuser.discrete_omega.double().numpy(), d.rot_diffuser.cdf_row(idx)
+    ks = stats.kstest(omega, lambda w: np.interp(w, grid, cdf))
+    print(f"IGSO3 angle KS: D = {ks.statistic:.4f}, p = {ks.pvalue:.3f} over {omega.size} draws (sigma bucket {idx})")
+    assert ks.pvalue > 1e-3
+    axis = (qn[..., 1:] * torch.sign(qn[..., :1])).reshape(-1, 3)
+    axis = axis / axis.norm(dim=-1, keepdim=True)
+    assert float(axis.mean(0).abs().max()) < 0.03                      # isotropic
+    x = out[..., 4:].reshape(-1).numpy() * 0.1                         # x_t = sqrt(1 - e^-beta) z in scaled units
+    var = float(1 - np.exp(-(0.1 * t + 0.5 * 19.9 * t * t)))
+    assert abs(x.mean()) < 0.02 and abs(x.var() / var - 1) < 0.05
+    assert stats.kstest(x / np.sqrt(var), "norm").pvalue > 1e-3
+
+
+def test_decoy_keyed_draws_do_not_depend_on_batching():
+    """draws are Philox(seed, subsequence = global decoy id): a decoy's perturbation is bit-identical whether it is
+    sampled in one batch of 6 or as part of a 2-decoy shard starting at decoy 4."""
+    d = make_diffuser()
+    full = d.decoy_noise((6, 50, 3), "cuda", 7, 0, 0)
+    part = d.decoy_noise((2, 50, 3), "cuda", 7, 4, 0)
+    assert torch.equal(full[4:], part)
+    assert not torch.equal(full[0], full[1])
+    assert not torch.equal(d.decoy_noise((2, 50, 3), "cuda", 7, 4, 2), part)   # another draw of the same decoys
+    u = d.decoy_noise((4, 1000), "cuda", 7, 0, 1, uniform=True)
+    assert float(u.min()) >= 0.0 and float(u.max()) < 1.0 and abs(float(u.mean()) - 0.5) < 0.02
+
+
+# ---- engine / graph-cache hygiene -----------------------------------------------------------------------
+def test_graph_cache_is_dropped_when_the_engine_is_rebuilt(params):
+    """load_state_dict between two forward_backward calls of one sampler rebuilds the native engine (new weight images, new
+    workspace); the captured iteration of the first engine must not be replayed on the second."""
+    from str2str_b200.rigid import Rigid
+    from str2str_b200.sampler import ForwardBackwardSampler, InferenceConfig
+
+    L, B = 64, 2
+    net = make_net(params)
+    smp = ForwardBackwardSampler(net, make_diffuser(), InferenceConfig(num_timesteps=8, min_t=0.01), use_cuda_graph=True)
+    feats = cuda(synthetic.make_features(1, L, seed=1))
+    q, x = synthetic.make_backbone(L, seed=1)
+    r0 = Rigid.from_tensor_7(torch.cat([q, x], -1)[None].repeat(B, 1, 1).cuda(), normalize_quats=True)
+    g = torch.Generator().manual_seed(1)
+    rt = (torch.cat([q, x], -1)[None].repeat(B, 1, 1) + 0.3 * torch.randn(B, L, 7, generator=g)).float().cuda()
+    a1 = smp.forward_backward(feats, r0, 0.5, rigids_t=rt)
+    other = synthetic.make_state_dict(seed=5, final_scale=0.02)
+    net.load_state_dict(other, strict=True)
+    b1 = smp.forward_backward(feats, r0, 0.5, rigids_t=rt)
+    fresh = ForwardBackwardSampler(make_net(other), make_diffuser(), InferenceConfig(num_timesteps=8, min_t=0.01), use_cuda_graph=False)
+    b_ref = fresh.forward_backward(feats, r0, 0.5, rigids_t=rt)
+    assert np.abs(b1 - b_ref).max() < 1e-3 and np.abs(a1 - b1).max() > 1e-2
+    net.load_state_dict(params, strict=True)
+    a2 = smp.forward_backward(feats, r0, 0.5, rigids_t=rt)
+    assert np.array_equal(a1, a2)
+
+
+def test_relative_position_table_follows_the_indices(params):
+    """The engine's relative-position table is re-planned from the indices of every call: a sub-module call in between (which
+    re-plans nothing) and a new residue_idx tensor with a chain break must both give the oracle's pair embedding."""
+    from str2str_b200.rigid import Rigid
+
+    B, L = 1, 32
+    net = make_net(params)
+    f = synthetic.make_features(B, L, seed=2)
+    q, x = synthetic.make_backbone(L, seed=2)
+    f["rigids_t"] = torch.cat([q, x], -1)[None].float()
+    f["sc_ca_t"] = x[None].float()
+    f["t"] = torch.tensor([0.4])
+    for shift in (0, 500, 3):
+        ff = dict(f)
+        ridx = f["residue_idx"].clone()
+        ridx[:, L // 2:] += shift
+        ff["residue_idx"] = ridx
+        nm, node, edge = module_inputs(B, L, 5, 0)
+        net.translator.trunk["ipa_0"](node.cuda(), edge.cuda(), Rigid.from_tensor_7(f["rigids_t"].cuda()), nm.cuda())
+        with torch.no_grad():
+            out = net(cuda(ff), as_tensor_7=True)["rigids"].cpu()
+        ref = O.denoising_net(params, ff)["rigids"]
+        assert rel(out[..., 4:], ref[..., 4:]) < 1e-4, shift
+
+
+def test_wrong_dtype_is_an_error_not_garbage(params):
+    from str2str_b200 import _lib
+
+    with pytest.raises(TypeError):
+        _lib.ptr(torch.zeros(4, device="cuda", dtype=torch.float64))
+    with pytest.raises(TypeError):
+        _lib.ptr_i64(torch.zeros(4, device="cuda", dtype=torch.int32))
+
+
+# ---- module-level drop-ins ------------------------------------------------------------------------------------------------
+def test_trunk_submodules_forward_vs_oracle(params):
+    """NodeTransition / TorsionAngleHead / BackboneUpdate / EdgeTransition called on their own, with the reference's forward
+    signatures (layers.py:138-145,170-185,199-213,232-241), against the oracle's restatement of the same layers."""
+    import torch.nn.functional as F
+
+    B, L = 2, 40
+    g = torch.Generator().manual_seed(8)
+    s = torch.randn(B, L, 256, generator=g)
+    net = make_net(params)
+    tr = net.translator.trunk
+    p = params
+    nt = "translator.trunk.node_transition_2."
+    h = F.relu(O.lin(p, nt + "linear_2", F.relu(O.lin(p, nt + "linear_1", s))))
+    ref = O.lnorm(p, nt + "ln", O.lin(p, nt + "linear_3", h) + s)
+    assert rel(tr["node_transition_2"](s.cuda()), ref) < 3e-5
+    tp = "translator.torsion_pred."
+    u = O.lin(p, tp + "linear_final", O.lin(p, tp + "linear_2", F.relu(O.lin(p, tp + "linear_1", s))) + s)
+    ref = u / torch.sqrt(torch.clamp((u ** 2).sum(-1, keepdim=True), min=1e-8))
+    assert rel(net.translator.torsion_pred(s.cuda()), ref) < 1e-4
+    ref = O.lin(p, "translator.trunk.bb_update_1.linear", s)
+    assert rel(tr["bb_update_1"](s.cuda()), ref) < 2e-6
+    edge = torch.randn(B, L, L, 128, generator=g)
+    out = tr["edge_transition_0"](s.cuda(), edge.cuda())
+    ref = O.edge_transition(p, "translator.trunk.edge_transition_0.", s, edge.bfloat16().float())
+    assert out.dtype == edge.dtype and rel(out, ref) < 2.5e-3
