@@ -446,7 +446,7 @@ def test_linear_tc_vs_fp64(case):
     Rd = Cd if inplace else (R.cuda() if use_res else None)
     Hd = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if "h" in kinds else None
     Ld = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if "l" in kinds else None
-    p = lambda t: _lib.ptr(t) if t is not None else None
+    p = lambda t: _lib.ptr(t, None) if t is not None else None  # fp32 inputs / result, bf16 images
     _lib.check(lib.s2s_linear_tc(p(Ad), p(Wd), p(bd), p(Rd), p(Cd), p(Hd), p(Ld), M, N, K, passes, relu, _lib.stream()))
     torch.cuda.synchronize()
     tol = 3e-5 if passes == 3 else 1e-2

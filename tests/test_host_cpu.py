@@ -190,3 +190,39 @@ def test_bench_roofline_records():
     assert "bound" not in extra["gemm_tc"] and abs(sum(r["share_of_profiled"] for r in extra.values()) - 1.0) < 2e-3
     if roof["traffic"] is not None:      # committed ncu capture: DRAM traffic of the dominant kernel matches its algorithmic bytes
         assert abs(roof["traffic"] / extra["edge_transition"]["algorithmic_bytes"] - 1.0) < 0.05
+
+
+def test_ref_loop_reproduces_reference_golden(golden_dir):
+    """tools/ref_loop.py (the restated sampler closure around the IMPORTED reference modules that bench.py's reference arm and
+    `ref_gpu` record time) gives the golden trajectory bit for bit.  Needs the reference sources (build container or staged)."""
+    import numpy as np
+    import pytest
+    import torch
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import ref_loop
+    from str2str_b200 import synthetic
+
+    if not ref_loop.available():
+        pytest.skip("reference sources not present (neither /root/reference nor baseline/_ref)")
+    g = np.load(os.path.join(golden_dir, "traj_masked_L24_n6.npz"))
+    B, L, n, n_pad, n_fixed, seed = [int(v) for v in g["meta"]]
+    net, dif = ref_loop.build_reference()
+    feats = synthetic.make_features(B, L, seed=seed, n_pad=n_pad, n_fixed=n_fixed, random_aatype=True)
+    fin, _, a37, times = ref_loop.forward_backward(net, dif, feats, torch.as_tensor(g["rigids_t"]), 0.5, 2 * n)
+    assert np.array_equal(fin.numpy(), g["final_rigids"]) and len(times) == n + 1
+    _, _, _, t2 = ref_loop.forward_backward(net, dif, feats, torch.as_tensor(g["rigids_t"]), 0.5, 2 * n, max_forwards=3)
+    assert len(t2) == 3
+
+
+def test_bench_arms_share_one_config():
+    import importlib.util
+    import types
+
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = types.SimpleNamespace(length=256, denoise_steps=100, decoys=64, workload="cfg2")
+    c = bench.config_of(a)
+    assert "BASELINE cfg2" in c["workload"] and c["network_forwards_per_step"] == 101
+    assert "cfg5" in bench.config_of(types.SimpleNamespace(length=256, denoise_steps=100, decoys=64, workload="cfg5"))["workload"]

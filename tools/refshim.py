@@ -1,4 +1,7 @@
-"""Import shim for the read-only reference checkout (test tooling only; never imported by the product).
+"""Import shim for the unmodified reference (test / benchmark tooling only; never imported by the product).
+
+Looks for the reference at $STR2STR_REFERENCE, then /root/reference (build container), then the staged copy under
+baseline/_ref/ (tools/stage_reference.py; what the GPU box has).
 
 The reference (/root/reference) needs `dm-tree`, hydra and lightning at import time; none is installed.
 Two shims are enough for the hot-path modules: a file-backed `tree.map_structure`
@@ -10,12 +13,26 @@ import sys
 import tempfile
 import types
 
-REF = os.environ.get("STR2STR_REFERENCE", "/root/reference")
+_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def find_reference():
+    for cand in (os.environ.get("STR2STR_REFERENCE"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "src", "models", "net")):
+            return cand
+    return None
+
+
+REF = find_reference()
+
+
+def available() -> bool:
+    return REF is not None
 
 
 def install():
-    if not os.path.isdir(REF):
-        raise RuntimeError(f"reference checkout not found at {REF}")
+    if REF is None:
+        raise RuntimeError("reference sources not found (neither /root/reference nor baseline/_ref: run tools/stage_reference.py in the build container)")
     shim_dir = os.path.join(tempfile.gettempdir(), "str2str_refshim")
     os.makedirs(shim_dir, exist_ok=True)
     with open(os.path.join(shim_dir, "tree.py"), "w") as f:
