@@ -47,7 +47,10 @@ int s2s_finalize(s2s_ctx* ctx, void* stream);
  *          "node_gemm"    1 = tensor-core GEMMs where the parity budget allows (default), 0 = exact fp32 FFMA everywhere (tests);
  *          "ipa_kernels"  1 = second-generation IPA path (default; needs node_gemm = 1 and L <= 512, longer chains fall back
  *                         automatically): point-attention term folded into the logits GEMM, persistent TMA + tcgen05 pair kernel,
- *                         split-bf16 attention weights; 0 = first-generation kernels (A/B, tests). */
+ *                         split-bf16 attention weights; 0 = first-generation kernels (A/B, tests);
+ *          "embed_table"  1 = the edge embedder builds each decoy's (fixed_i, fixed_j, index offset, distogram bin) -> embedding
+ *                         table and expands it into the pair tensor whenever that table is well below L^2 rows (default; same
+ *                         values bit for bit), 0 = always run the MLP on every pair row (A/B, tests). */
 int s2s_set_option(s2s_ctx* ctx, const char* key, int value);
 /* Size the workspace for (B, L) and build the relative-position table for residue-index offsets in
  * [d_min, d_max] (= min/max of residue_idx[i] - residue_idx[j]); d_max < d_min keeps the table already planned

@@ -115,7 +115,7 @@ using namespace s2s;
 struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
-  int opt_pair = 1, opt_node = 1, opt_ipa = 1;
+  int opt_pair = 1, opt_node = 1, opt_ipa = 1, opt_table = 1;
   int tfm_passes = 1;  // sequence-transformer in_proj + attention GEMMs: 1 = single bf16 (default; trajectory error unchanged, tools/traj_parity.py), 3 = split-bf16 (S2S_TFM_PASSES=3)
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
@@ -133,6 +133,10 @@ struct s2s_ctx {
   float *pd_rig, *pd_sc, *pd_rmask, *pd_fixed, *pd_psi, *pd_hard, *pd_orig, *pd_opsi;
   long long* pd_ridx;
   const float* hard = nullptr;  // non-null while a padded call is running
+  // edge-embedder table (pair_tc4.cu MODE 2): allocated when it can pay for the reserved shape
+  bf16* ee_table = nullptr; size_t ee_table_elems = 0;
+  int* ee_ctl = nullptr;
+  unsigned char* ee_cls = nullptr;
   float *feat65, *tf33, *node, *init_node, *a256, *b256, *proj, *feats, *q_pts, *k_pts, *v_pts, *S, *opt;
   float *skip64, *x320, *t320, *y320, *qkv, *nprime, *u384, *v384, *p128, *q128, *Ti, *Tj, *Tpos, *relfeat;
   float *quat, *trans, *upd6, *psi_u, *diffuse, *keybias;
@@ -394,6 +398,9 @@ void do_reserve(s2s_ctx* c, int B, int L_user, int d_min, int d_max, cudaStream_
     add(R * N_H * PT_K, 2); add(R * N_H * PT_K, 2); add(R * N_H * VP_PITCH, 2); add(R * N_H * VP_PITCH, 2);
     add((size_t)B * N_H * Lc * Lc, 2); add(R * N_H, 4);
     add(R * 7, 4); add(R * 3, 4); add(R, 4); add(R, 4); add(R * 2, 4); add(R, 4); add(R * 7, 4); add(R * 2, 4); add(R, 8);
+    // the embedding table pays when its rows (offsets x 23 slots) are well below the L^2 pair rows of a decoy
+    const size_t tab_elems = ((size_t)cap_off * (N_BINS + 1) * 2 < (size_t)Lc * Lc) ? edge_embed_table_elems(B, cap_off, 4) : 0;
+    add(tab_elems, 2); add(edge_embed_ctl_ints(B), 4); add(R, 1);
     c->ws.cap = bytes + 4096;
     S2S_CUDA(cudaMalloc(&c->ws.base, c->ws.cap));
     Slab& w = c->ws;
@@ -426,6 +433,8 @@ void do_reserve(s2s_ctx* c, int B, int L_user, int d_min, int d_max, cudaStream_
     c->pd_rig = w.take<float>(R * 7); c->pd_sc = w.take<float>(R * 3); c->pd_rmask = w.take<float>(R); c->pd_fixed = w.take<float>(R);
     c->pd_psi = w.take<float>(R * 2); c->pd_hard = w.take<float>(R); c->pd_orig = w.take<float>(R * 7); c->pd_opsi = w.take<float>(R * 2);
     c->pd_ridx = w.take<long long>(R);
+    c->ee_table = tab_elems ? w.take<bf16>(tab_elems) : nullptr; c->ee_table_elems = tab_elems;
+    c->ee_ctl = w.take<int>(edge_embed_ctl_ints(B)); c->ee_cls = w.take<unsigned char>(R);
     c->cap_B = B; c->cap_L = Lc; c->cap_off = cap_off;
     c->n_off = 0;  // the table memory is new: rebuild it below
   }
@@ -467,6 +476,11 @@ void do_embed(s2s_ctx* c, int B, int L, const float* t, const long long* ridx, c
   a.W2 = c->ee_W2; a.W3 = c->ee_W3; a.W2t = c->ee_W2t; a.W3t = c->ee_W3t;
   a.b2 = c->P(ee + "2.bias"); a.b3 = c->P(ee + "4.bias"); a.ln_w = c->P(ee + "5.weight"); a.ln_b = c->P(ee + "5.bias");
   a.z_out = z_out; a.wimg = c->ee_wimg; a.vec4 = c->ee_vec;
+  // table mode (see pair_tc4.cu): when the distinct (offset, bin) rows of a decoy are well below its L^2 pair rows
+  if (c->opt_pair >= 1 && c->opt_table && c->ee_table && (size_t)c->n_off * (N_BINS + 1) * 2 < (size_t)L * L &&
+      edge_embed_table_elems(B, c->n_off, 4) <= c->ee_table_elems) {
+    a.table_variants = 4; a.fixed = fixed; a.table = c->ee_table; a.tab_ctl = c->ee_ctl; a.cls = c->ee_cls;
+  }
   // pair_kernels = 0 selects the SIMT cross-check kernels (same inputs, same rounding points); the tcgen05 kernel takes every
   // chain length the public entry points hand down (they pad to a multiple of 32)
   if (c->opt_pair >= 1) {
@@ -843,6 +857,7 @@ int s2s_set_option(s2s_ctx* c, const char* key, int value) {
     if (k == "pair_kernels") { S2S_CHECK(value == 0 || value == 1, "pair_kernels: 0|1"); c->opt_pair = value; }
     else if (k == "node_gemm") { S2S_CHECK(value == 0 || value == 1, "node_gemm: 0|1"); c->opt_node = value; }
     else if (k == "ipa_kernels") { S2S_CHECK(value == 0 || value == 1, "ipa_kernels: 0|1"); c->opt_ipa = value; }
+    else if (k == "embed_table") { S2S_CHECK(value == 0 || value == 1, "embed_table: 0|1"); c->opt_table = value; }
     else S2S_CHECK(false, "unknown option " + k);
   });
 }

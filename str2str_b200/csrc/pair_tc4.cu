@@ -15,9 +15,22 @@
 // through mbarriers only.  Same arithmetic and rounding points as pair_simt.cu, except that the LayerNorm statistics are
 // taken in one shifted pass (sum and sum of squares of y - y_0).
 //
-// Tiles are 128 consecutive rows of the flattened pair tensor [B*L*L][128].  FLAT = false (L % 128 == 0): a tile lies in one
-// (decoy, i) row.  FLAT = true (any other L with B*L*L % 128 == 0; api.cu pads chains to a multiple of 32): every row
+// Tiles are 128 consecutive rows of the flattened pair tensor [B*L*L][128].  MODE 0 (L % 128 == 0): a tile lies in one
+// (decoy, i) row.  MODE 1 (any other L with B*L*L % 128 == 0; api.cu pads chains to a multiple of 32): every row
 // carries its own (decoy, i, j), so short chains fill their tiles with several i rows.
+//
+// MODE 2 — the embedding TABLE.  The layer-1 input of a pair row is t_i | t_j | pos(idx_i - idx_j) | one-hot distogram bin
+// (denoising_ipa.py:126-158), and t_i = [time embedding of the decoy | fixed_i]: apart from the fixed flag nothing in a pair
+// row's input depends on (i, j) except the index offset and the bin.  So inside one decoy the whole 3-layer MLP + LayerNorm
+// is a function of (fixed_i, fixed_j, offset, bin): n_off x 23 distinct rows (x 4 when the decoy has fixed residues)
+// instead of L^2 — 11 753 instead of 65 536 at L = 256, 23 529 instead of 262 144 at L = 512.  MODE 2 runs the same pipeline
+// over those table rows (the G station builds layer 1 from the row's (offset, bin) instead of from a pair), and
+// edge_embed_expand_kernel then writes z by copying each pair's table row: the embedder becomes an HBM-write-bound copy
+// plus 1/5 - 1/11 of the matrix work.  Bit-identical to MODE 0 / 1: a table row is the same fp32 sum (t_i + t_j) + pos (+ bin
+// row) and goes through the same MMAs, statistics and bf16 rounding as the pair rows it stands for.  A setup kernel groups
+// each decoy's residues by their fixed value; inputs the table cannot represent (more than two distinct fixed values in a
+// decoy, masks other than 0 / 1) raise a device flag that turns the table kernels into no-ops and lets the direct kernel,
+// launched after them, do the work instead.
 //
 // What bounded the first cut of this pipeline (ncu, profiles/r01c_gemm_and_embedder_experiments.log): the LSU data pipe at 76 % of its
 // wavefront rate, not latency.  Row-per-thread 16-byte global stores cost 32 wavefronts each (32 different 128-byte
@@ -82,10 +95,19 @@ struct EePipeArgs {
   EdgeEmbedArgs e;
   const bf16* wimg;
   int n_tiles;
+  // table mode (MODE 2) / fallback control: ctl[0] = active table blocks, ctl[1] = "table not applicable" flag,
+  // ctl[2 ..] = active (decoy * 4 + variant) blocks, then rep[B][2] = representative residue row per fixed class (-1: none)
+  const int* ctl = nullptr;
+  int only_if_flag = 0;  // MODE 0 / 1 launched behind the table kernels: run only when ctl[1] is set
 };
 
-template <bool FLAT>
+constexpr int TAB_SLOTS = N_BINS + 1;  // no bin, bin 0 .. 21
+__host__ __device__ inline int tab_rows_per_block(int n_off) { return (n_off * TAB_SLOTS + TM - 1) / TM * TM; }
+
+template <int MODE>
 __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArgs a) {
+  constexpr bool FLAT = MODE == 1, TABLE = MODE == 2;
+  if (a.only_if_flag && a.ctl[1] == 0) return;  // the table kernels did the work
   extern __shared__ __align__(1024) unsigned char smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   float* wd_s = reinterpret_cast<float*>(smem + P_OFF_VEC);
@@ -125,7 +147,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int tiles_per_i = FLAT ? 1 : e.L / TM;
+  const int tiles_per_i = (FLAT || TABLE) ? 1 : e.L / TM;
+  const int rpb = tab_rows_per_block(e.n_off), tiles_per_blk = rpb / TM;  // table mode: rows / tiles per (decoy, variant) block
+  const int* const blk_list = a.ctl + 2;
+  const int* const rep = a.ctl + 2 + 4 * e.B;
+  if constexpr (TABLE) a.n_tiles = a.ctl[0] * tiles_per_blk;  // 0 when the flag is raised
   const int n_local = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   constexpr uint32_t IDESC = make_idesc(128, 128);
 
@@ -183,7 +209,32 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
       const int r_begin = g * 18, r_cnt = g == P_G_WARPS - 1 ? TM - r_begin : 18;
       const uint32_t s = k & 1, ph = (k >> 1) & 1;
       unsigned char* const dst = dst0 + s * 2 * TILE_BYTES;
-      if constexpr (FLAT) {
+      if constexpr (TABLE) {
+        // table row idx of block (decoy b, variant v): offset = idx / 23, slot = idx % 23 (0 = no bin, k + 1 = bin k)
+        const int blk = tile / tiles_per_blk, idx0 = (tile - blk * tiles_per_blk) * TM + r_begin;
+        const int bv = blk_list[blk], b = bv >> 2;
+        const int ri = rep[2 * b + ((bv >> 1) & 1)], rj = rep[2 * b + (bv & 1)];
+        const int idx_l = idx0 + (lane < r_cnt ? lane : 0);
+        const bool ok_l = idx_l < e.n_off * TAB_SLOTS;
+        const int off_l = ok_l ? idx_l / TAB_SLOTS : 0;
+        const int bin_l = ok_l ? idx_l - off_l * TAB_SLOTS - 1 : -1;
+        const float4 tiv = __ldg(reinterpret_cast<const float4*>(e.Ti + (size_t)ri * C_Z + c));
+        const float4 tjv = __ldg(reinterpret_cast<const float4*>(e.Tj + (size_t)rj * C_Z + c));
+        mbar_wait(&a1_empty[s], ph ^ 1);
+#pragma unroll 6
+        for (int r16 = 0; r16 < r_cnt; ++r16) {
+          const int bin = __shfl_sync(0xffffffffu, bin_l, r16);
+          const int off = __shfl_sync(0xffffffffu, off_l, r16);
+          const float4 tpv = __ldg(reinterpret_cast<const float4*>(e.Tpos + (size_t)off * C_Z + c));
+          float4 h = make_float4(tiv.x + tjv.x + tpv.x, tiv.y + tjv.y + tpv.y, tiv.z + tjv.z + tpv.z, tiv.w + tjv.w + tpv.w);
+          if (bin >= 0) {
+            const float4 wv = *reinterpret_cast<const float4*>(wd_s + bin * P_WD_PITCH + c);
+            h.x += wv.x; h.y += wv.y; h.z += wv.z; h.w += wv.w;
+          }
+          *reinterpret_cast<uint2*>(dst + sw128_offset(r_begin + r16, c % KBLK)) =
+              make_uint2(pack_bf16(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f)), pack_bf16(fmaxf(h.z, 0.f), fmaxf(h.w, 0.f)));
+        }
+      } else if constexpr (FLAT) {
         // lane l classifies flattened row tile*128 + r_begin + l: its (decoy, i) row bi, its key row bj, bin and offset
         const long f = (long)tile * TM + r_begin + (lane < r_cnt ? lane : 0);
         const int bi_l = (int)(f / e.L);
@@ -283,17 +334,20 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
     unsigned char* const obuf = smem + P_OFF_OUT + q * (32 * 256);
     for (int k = 0; k < n_local; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
-      int bi, jr;
-      if constexpr (FLAT) {
-        const long f = (long)tile * TM + r;
-        bi = (int)(f / e.L);
-        jr = (int)(f - (long)bi * e.L);
-      } else {
-        bi = tile / tiles_per_i;
-        jr = (tile % tiles_per_i) * TM + r;
+      float m = 1.f;  // table rows are stored unmasked: the expand kernel writes zeros for masked pairs
+      if constexpr (!TABLE) {
+        int bi, jr;
+        if constexpr (FLAT) {
+          const long f = (long)tile * TM + r;
+          bi = (int)(f / e.L);
+          jr = (int)(f - (long)bi * e.L);
+        } else {
+          bi = tile / tiles_per_i;
+          jr = (tile % tiles_per_i) * TM + r;
+        }
+        const size_t bj = (size_t)(bi / e.L) * e.L + jr;
+        m = __ldg(e.mask + bi) * __ldg(e.mask + bj);
       }
-      const size_t bj = (size_t)(bi / e.L) * e.L + jr;
-      const float m = __ldg(e.mask + bi) * __ldg(e.mask + bj);
       const uint32_t s = k & 1, ph = (k >> 1) & 1;
       mbar_wait_backoff(&acc3_full[s], ph);
       tc_fence_after();
@@ -336,7 +390,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
       }
       __syncwarp();
       {
-        unsigned char* const gbase = reinterpret_cast<unsigned char*>(e.z_out + ((size_t)tile * TM + q * 32) * C_Z);
+        size_t row0 = (size_t)tile * TM + q * 32;
+        if constexpr (TABLE) {  // block (b, v) of the table lives at row (b * 4 + v) * rpb whether or not earlier blocks are active
+          const int blk = tile / tiles_per_blk;
+          row0 = (size_t)blk_list[blk] * rpb + (size_t)(tile - blk * tiles_per_blk) * TM + q * 32;
+        }
+        unsigned char* const gbase = reinterpret_cast<unsigned char*>((TABLE ? e.table : e.z_out) + row0 * C_Z);
         const int rr = lane >> 4, ch = lane & 15;
 #pragma unroll
         for (int i16 = 0; i16 < 16; ++i16) {
@@ -353,26 +412,123 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// Groups every decoy's residues by their fixed value (class 0 = the value of residue 0, class 1 = the other value) and lists
+// the table blocks to build.  One CTA; thread per decoy for the scan (B x L reads), thread 0 for the list.
+__global__ void embed_table_setup_kernel(int B, int L, const float* __restrict__ fixed, const float* __restrict__ mask,
+                                         unsigned char* __restrict__ cls, int* __restrict__ ctl, int variants) {
+  __shared__ int bad_s;
+  if (threadIdx.x == 0) bad_s = 0;
+  __syncthreads();
+  int* const rep = ctl + 2 + 4 * B;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float f0 = fixed[(size_t)b * L];
+    float f1 = 0.f;
+    int rep1 = -1, bad = 0;
+    for (int i = 0; i < L; ++i) {
+      const float f = fixed[(size_t)b * L + i], m = mask[(size_t)b * L + i];
+      if (m != 0.f && m != 1.f) bad = 1;
+      int c = 0;
+      if (f != f0) {
+        if (rep1 < 0) { rep1 = i; f1 = f; }
+        if (f != f1) bad = 1;  // a third distinct value (or NaN)
+        c = 1;
+      }
+      cls[(size_t)b * L + i] = (unsigned char)c;
+    }
+    if (rep1 >= 0 && variants < 4) bad = 1;  // the host planned a table without fixed-residue variants
+    rep[2 * b] = b * L;
+    rep[2 * b + 1] = rep1 < 0 ? -1 : b * L + rep1;
+    if (bad) atomicOr(&bad_s, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int b = 0; b < B; ++b) {
+      ctl[2 + n++] = b * 4;
+      if (rep[2 * b + 1] >= 0)
+        for (int v = 1; v < 4; ++v) ctl[2 + n++] = b * 4 + v;
+    }
+    ctl[0] = bad_s ? 0 : n;
+    ctl[1] = bad_s;
+  }
+}
+
+// z[b,i,j,:] = table row of (class_i, class_j, idx_i - idx_j, bin(|ca_i - ca_j|)), or zeros for masked pairs.  A warp takes 32
+// consecutive pair rows: lanes classify one row each, then the warp copies the rows two at a time (half a warp per 256-byte
+// row), all sixteen 16-byte loads of a lane in flight at once.  Reads come from L2 (a decoy's table is ~3 MB), writes are the
+// 1 GB of z: the kernel is bound by the HBM write.
+__global__ void __launch_bounds__(256) edge_embed_expand_kernel(EePipeArgs a, long n_rows) {
+  const EdgeEmbedArgs& e = a.e;
+  if (a.ctl[1]) return;  // table not applicable: the direct kernel runs instead
+  __shared__ float edge_s[N_BINS];
+  if (threadIdx.x < N_BINS) edge_s[threadIdx.x] = e.bin_lower[threadIdx.x];
+  __syncthreads();
+  const float inv_step = (float)(N_BINS - 1) / (edge_s[N_BINS - 1] - edge_s[0]);
+  const int lane = threadIdx.x & 31;
+  const int rpb = tab_rows_per_block(e.n_off);
+  const long warp_id = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long)gridDim.x * blockDim.x) >> 5;
+  const uint4* const tab = reinterpret_cast<const uint4*>(e.table);
+  uint4* const zo = reinterpret_cast<uint4*>(e.z_out);
+  for (long r0 = warp_id * 32; r0 < n_rows; r0 += n_warps * 32) {
+    const long f = r0 + lane;  // n_rows % 32 == 0
+    const int bi = (int)(f / e.L), j = (int)(f - (long)bi * e.L), b = bi / e.L;
+    const int bj = b * e.L + j;
+    long src_l = -1;
+    if (__ldg(e.mask + bi) * __ldg(e.mask + bj) != 0.f) {
+      const int bin = pair_distogram_bin_fast(e.sc_ca + (size_t)bi * 3, e.sc_ca + (size_t)bj * 3, edge_s, inv_step);
+      const int off = min(max((int)(e.ridx[bi] - e.ridx[bj]) - e.d_min, 0), e.n_off - 1);
+      const int v = e.cls[bi] * 2 + e.cls[bj];
+      src_l = ((long)(b * 4 + v) * rpb + off * TAB_SLOTS + bin + 1) * 16;  // in 16-byte pieces
+    }
+    const int half = lane >> 4, piece = lane & 15;
+    uint4 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const long src = __shfl_sync(0xffffffffu, src_l, 2 * k + half);
+      v[k] = src >= 0 ? __ldg(tab + src + piece) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) zo[(r0 + 2 * k + half) * 16 + piece] = v[k];
+  }
+}
+
 }  // namespace
+
+size_t edge_embed_table_elems(int B, int n_off, int variants) { return (size_t)B * 4 * tab_rows_per_block(n_off) * C_Z * (variants >= 1 ? 1 : 0); }
+size_t edge_embed_ctl_ints(int B) { return 2 + 4 * (size_t)B + 2 * (size_t)B; }
 
 void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st) {
   S2S_CHECK(((size_t)a.B * a.L * a.L) % TM == 0, "edge_embed_tc2 needs B*L*L % 128 == 0 (api.cu pads chain lengths to a multiple of 32)");
-  const bool flat = a.L % TM != 0;
   S2S_CHECK(a.wimg, "edge_embed_tc2: weight image missing");
+  const bool flat = a.L % TM != 0;
   EePipeArgs k;
   k.e = a; k.wimg = a.wimg; k.n_tiles = (int)((size_t)a.B * a.L * a.L / TM);
   static bool configured = false;
   if (!configured) {
-    S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-    S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    S2S_CUDA(cudaFuncSetAttribute(edge_embed_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
     configured = true;
   }
   S2S_CHECK(a.vec4, "edge_embed_tc2: packed bias / LayerNorm vector missing");
   S2S_CUDA(cudaMemcpyToSymbolAsync(c_ee, a.vec4, sizeof(float) * 4 * C_Z, 0, cudaMemcpyDeviceToDevice, st));
   S2S_PROF("edge_embed", st);
   const int cap = sm_count();
-  if (flat) edge_embed_pipe_kernel<true><<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
-  else edge_embed_pipe_kernel<false><<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
+  if (a.table_variants > 0) {
+    S2S_CHECK(a.table && a.tab_ctl && a.cls, "edge_embed_tc2: table buffers missing");
+    k.ctl = a.tab_ctl;
+    embed_table_setup_kernel<<<1, 256, 0, st>>>(a.B, a.L, a.fixed, a.mask, a.cls, a.tab_ctl, a.table_variants);
+    S2S_LAUNCH_CHECK();
+    const int max_tiles = a.B * a.table_variants * (tab_rows_per_block(a.n_off) / TM);
+    edge_embed_pipe_kernel<2><<<max_tiles < cap ? max_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
+    S2S_LAUNCH_CHECK();
+    const long n_rows = (long)a.B * a.L * a.L;
+    edge_embed_expand_kernel<<<cap * 8, 256, 0, st>>>(k, n_rows);
+    S2S_LAUNCH_CHECK();
+    k.only_if_flag = 1;  // the direct kernel below runs only if the setup kernel found inputs the table cannot represent
+  }
+  if (flat) edge_embed_pipe_kernel<1><<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
+  else edge_embed_pipe_kernel<0><<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
   S2S_LAUNCH_CHECK();
 }
 

@@ -104,7 +104,15 @@ struct EdgeEmbedArgs {
   bf16* z_out;             // [B,L,L,128]
   const bf16* wimg = nullptr;  // tcgen05 path: pre-swizzled weight blocks (build_ee_wimg)
   const float* vec4 = nullptr; // [b2 | b3 | ln_w | ln_b] packed, device (pipelined kernel: copied into its constant bank)
+  // embedding table (pair_tc4.cu, MODE 2): 0 = direct kernel only, 1 = table without fixed-residue variants, 4 = with
+  int table_variants = 0;
+  const float* fixed = nullptr;   // [B*L] fixed mask (the table's row classes)
+  bf16* table = nullptr;          // [B*4][tab_rows_per_block(n_off)][128]
+  int* tab_ctl = nullptr;         // edge_embed_ctl_ints(B) ints
+  unsigned char* cls = nullptr;   // [B*L]
 };
+size_t edge_embed_table_elems(int B, int n_off, int variants);
+size_t edge_embed_ctl_ints(int B);
 void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st);
 void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st);  // pipelined tcgen05 kernel, pair_tc4.cu
 

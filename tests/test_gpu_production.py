@@ -462,3 +462,40 @@ def test_trunk_submodules_forward_vs_oracle(params):
     out = tr["edge_transition_0"](s.cuda(), edge.cuda())
     ref = O.edge_transition(p, "translator.trunk.edge_transition_0.", s, edge.bfloat16().float())
     assert out.dtype == edge.dtype and rel(out, ref) < 4.5e-3
+
+
+# ---- the embedding table (pair_tc4.cu MODE 2) ------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,case", [(128, "plain"), (256, "plain"), (256, "fixed+break"), (160, "fixed+break"), (128, "three-valued fixed mask"),
+                                    (256, "float residue mask")])
+def test_edge_embed_table_is_bit_identical_to_direct(params, L, case):
+    """The edge embedder's table mode (per decoy: (fixed_i, fixed_j, index offset, distogram bin) -> embedding row, then a copy
+    per pair) must give the direct kernel's pair tensor bit for bit; inputs the table cannot represent (a third fixed value, a
+    non-binary residue mask) must fall back to the direct kernel on the device."""
+    B = 3
+    f = synthetic.make_features(B, L, seed=500 + L, n_pad=4, n_fixed=0)
+    ridx, fixed, rm = f["residue_idx"].clone(), f["fixed_mask"].float().clone(), f["residue_mask"].float().clone()
+    if case == "fixed+break":
+        ridx[:, L // 3:] += 21
+        fixed[0, 3:9] = 1.0
+        fixed[2, L - 20:] = 1.0
+    if case == "three-valued fixed mask":
+        fixed[1, 5] = 1.0
+        fixed[1, 6] = 0.5
+    if case == "float residue mask":
+        rm[0, 7] = 0.25
+    q, x = synthetic.make_backbone(L, seed=500 + L)
+    g = torch.Generator().manual_seed(L)
+    sc = (x[None] + 3.0 * torch.randn(B, L, 3, generator=g)).float()
+    t = torch.tensor([0.2, 0.5, 0.9])
+    net = make_net(params)
+    eng = net.native("cuda")
+    eng.reserve(B, L, ridx)
+    outs = []
+    for table in (0, 1):
+        eng.set_option("embed_table", table)
+        node, z = eng.embed(t.cuda(), ridx.cuda(), fixed.cuda(), sc.cuda(), rm.cuda())
+        outs.append(z.clone())
+    assert torch.equal(outs[0], outs[1]), f"table mode differs from the direct kernel ({case}, L={L})"
+    _, edge_o = O.embedder(params, ridx, t, fixed, sc)
+    edge_o = edge_o * (rm[..., None] * rm[..., None, :])[..., None]
+    assert rel(outs[1].float(), edge_o) < 4.5e-3
