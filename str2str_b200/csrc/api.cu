@@ -115,7 +115,7 @@ using namespace s2s;
 struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
-  int opt_pair = 1, opt_node = 1, opt_ipa = 1, opt_table = 1;
+  int opt_pair = 1, opt_node = 1, opt_ipa = 1, opt_table = 1, opt_et_pair = 0;
   int tfm_passes = 1;  // sequence-transformer in_proj + attention GEMMs: 1 = single bf16 (default; trajectory error unchanged, tools/traj_parity.py), 3 = split-bf16 (S2S_TFM_PASSES=3)
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
@@ -435,6 +435,7 @@ void do_reserve(s2s_ctx* c, int B, int L_user, int d_min, int d_max, cudaStream_
     c->pd_ridx = w.take<long long>(R);
     c->ee_table = tab_elems ? w.take<bf16>(tab_elems) : nullptr; c->ee_table_elems = tab_elems;
     c->ee_ctl = w.take<int>(edge_embed_ctl_ints(B)); c->ee_cls = w.take<unsigned char>(R);
+    S2S_CUDA(cudaMemsetAsync(c->ee_ctl, 0, edge_embed_ctl_ints(B) * sizeof(int), st));  // the setup kernel's arrival counter starts at 0
     c->cap_B = B; c->cap_L = Lc; c->cap_off = cap_off;
     c->n_off = 0;  // the table memory is new: rebuild it below
   }
@@ -624,7 +625,9 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   a.W1zt = w.W1zt; a.W2t = w.W2t; a.Wft = w.Wft; a.Wfzt = w.Wfzt;
   a.b2 = c->P(e + "trunk.2.bias"); a.ln_w = c->P(e + "layer_norm.weight"); a.ln_b = c->P(e + "layer_norm.bias");
   a.z_out = z_out; a.wimg3 = w.wimg3; a.wimg_copies = c->wimg_copies; a.nprime_bf16 = c->nprime_bf16;
-  if (tc) edge_transition_tc3(a, st); else edge_transition_simt(a, st);
+  if (!tc) edge_transition_simt(a, st);
+  else if (c->opt_et_pair && edge_transition_pair_supported(B, L)) edge_transition_pair(a, st);
+  else edge_transition_tc3(a, st);
 }
 
 void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {
@@ -819,6 +822,7 @@ s2s_ctx* s2s_create(const float* tfreq, const float* pdenom, const float* bin_lo
     c = new s2s_ctx();
     if (const char* e = getenv("S2S_WIMG_COPIES")) c->wimg_copies = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("S2S_TFM_PASSES")) c->tfm_passes = atoi(e) == 3 ? 3 : 1;
+    if (const char* e = getenv("S2S_ET_PAIR")) c->opt_et_pair = atoi(e) != 0;
     auto up = [&](const float* h, size_t n) {
       float* d;
       S2S_CUDA(cudaMalloc(&d, n * 4));
@@ -857,6 +861,7 @@ int s2s_set_option(s2s_ctx* c, const char* key, int value) {
     if (k == "pair_kernels") { S2S_CHECK(value == 0 || value == 1, "pair_kernels: 0|1"); c->opt_pair = value; }
     else if (k == "node_gemm") { S2S_CHECK(value == 0 || value == 1, "node_gemm: 0|1"); c->opt_node = value; }
     else if (k == "ipa_kernels") { S2S_CHECK(value == 0 || value == 1, "ipa_kernels: 0|1"); c->opt_ipa = value; }
+    else if (k == "et_pair") { S2S_CHECK(value == 0 || value == 1, "et_pair: 0|1"); c->opt_et_pair = value; }
     else if (k == "embed_table") { S2S_CHECK(value == 0 || value == 1, "embed_table: 0|1"); c->opt_table = value; }
     else S2S_CHECK(false, "unknown option " + k);
   });

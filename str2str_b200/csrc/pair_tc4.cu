@@ -96,7 +96,7 @@ struct EePipeArgs {
   const bf16* wimg;
   int n_tiles;
   // table mode (MODE 2) / fallback control: ctl[0] = active table blocks, ctl[1] = "table not applicable" flag,
-  // ctl[2 ..] = active (decoy * 4 + variant) blocks, then rep[B][2] = representative residue row per fixed class (-1: none)
+  // ctl[2], ctl[3] = setup scratch (zero between launches), ctl[4 ..] = active (decoy * 4 + variant) blocks, then rep[B][2] = representative residue row per fixed class (-1: none)
   const int* ctl = nullptr;
   int only_if_flag = 0;  // MODE 0 / 1 launched behind the table kernels: run only when ctl[1] is set
 };
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
   const uint32_t tmem = *tmem_slot;
   const int tiles_per_i = (FLAT || TABLE) ? 1 : e.L / TM;
   const int rpb = tab_rows_per_block(e.n_off), tiles_per_blk = rpb / TM;  // table mode: rows / tiles per (decoy, variant) block
-  const int* const blk_list = a.ctl + 2;
-  const int* const rep = a.ctl + 2 + 4 * e.B;
+  const int* const blk_list = a.ctl + 4;
+  const int* const rep = a.ctl + 4 + 4 * e.B;
   if constexpr (TABLE) a.n_tiles = a.ctl[0] * tiles_per_blk;  // 0 when the flag is raised
   const int n_local = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   constexpr uint32_t IDESC = make_idesc(128, 128);
@@ -413,43 +413,55 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
 }
 
 // Groups every decoy's residues by their fixed value (class 0 = the value of residue 0, class 1 = the other value) and lists
-// the table blocks to build.  One CTA; thread per decoy for the scan (B x L reads), thread 0 for the list.
-__global__ void embed_table_setup_kernel(int B, int L, const float* __restrict__ fixed, const float* __restrict__ mask,
-                                         unsigned char* __restrict__ cls, int* __restrict__ ctl, int variants) {
-  __shared__ int bad_s;
-  if (threadIdx.x == 0) bad_s = 0;
+// the table blocks to build.  One CTA per decoy scans its residues; the last CTA to finish writes the block list.
+__global__ void __launch_bounds__(256) embed_table_setup_kernel(int B, int L, const float* __restrict__ fixed, const float* __restrict__ mask,
+                                                                unsigned char* __restrict__ cls, int* __restrict__ ctl, int* __restrict__ sync_ws,
+                                                                int variants) {
+  __shared__ int rep1_s, bad_s, last_s;
+  const int b = blockIdx.x;
+  int* const rep = ctl + 4 + 4 * B;
+  if (threadIdx.x == 0) { rep1_s = L; bad_s = 0; }
   __syncthreads();
-  int* const rep = ctl + 2 + 4 * B;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const float f0 = fixed[(size_t)b * L];
-    float f1 = 0.f;
-    int rep1 = -1, bad = 0;
-    for (int i = 0; i < L; ++i) {
-      const float f = fixed[(size_t)b * L + i], m = mask[(size_t)b * L + i];
-      if (m != 0.f && m != 1.f) bad = 1;
-      int c = 0;
-      if (f != f0) {
-        if (rep1 < 0) { rep1 = i; f1 = f; }
-        if (f != f1) bad = 1;  // a third distinct value (or NaN)
-        c = 1;
-      }
-      cls[(size_t)b * L + i] = (unsigned char)c;
+  const float f0 = fixed[(size_t)b * L];
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float f = fixed[(size_t)b * L + i], m = mask[(size_t)b * L + i];
+    if (m != 0.f && m != 1.f) bad_s = 1;
+    const int c = f != f0;
+    cls[(size_t)b * L + i] = (unsigned char)c;
+    if (c) atomicMin(&rep1_s, i);
+  }
+  __syncthreads();
+  const int rep1 = rep1_s;
+  if (rep1 < L) {
+    const float f1 = fixed[(size_t)b * L + rep1];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+      const float f = fixed[(size_t)b * L + i];
+      if (f != f0 && f != f1) bad_s = 1;  // a third distinct value (or NaN)
     }
-    if (rep1 >= 0 && variants < 4) bad = 1;  // the host planned a table without fixed-residue variants
-    rep[2 * b] = b * L;
-    rep[2 * b + 1] = rep1 < 0 ? -1 : b * L + rep1;
-    if (bad) atomicOr(&bad_s, 1);
+    if (variants < 4) bad_s = 1;          // the host planned a table without fixed-residue variants
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    rep[2 * b] = b * L;
+    rep[2 * b + 1] = rep1 < L ? b * L + rep1 : -1;
+    if (bad_s) atomicOr(&sync_ws[1], 1);
+    __threadfence();
+    last_s = atomicAdd(&sync_ws[0], 1) == B - 1;
+  }
+  __syncthreads();
+  if (last_s && threadIdx.x == 0) {  // every decoy's rep[] is visible (fence + counter): build the list, reset the scratch
+    __threadfence();
     int n = 0;
-    for (int b = 0; b < B; ++b) {
-      ctl[2 + n++] = b * 4;
-      if (rep[2 * b + 1] >= 0)
-        for (int v = 1; v < 4; ++v) ctl[2 + n++] = b * 4 + v;
+    for (int d = 0; d < B; ++d) {
+      ctl[4 + n++] = d * 4;
+      if (((volatile int*)rep)[2 * d + 1] >= 0)
+        for (int v = 1; v < 4; ++v) ctl[4 + n++] = d * 4 + v;
     }
-    ctl[0] = bad_s ? 0 : n;
-    ctl[1] = bad_s;
+    const int bad = ((volatile int*)sync_ws)[1];
+    ctl[0] = bad ? 0 : n;
+    ctl[1] = bad;
+    sync_ws[0] = 0;
+    sync_ws[1] = 0;
   }
 }
 
@@ -495,7 +507,7 @@ __global__ void __launch_bounds__(256) edge_embed_expand_kernel(EePipeArgs a, lo
 }  // namespace
 
 size_t edge_embed_table_elems(int B, int n_off, int variants) { return (size_t)B * 4 * tab_rows_per_block(n_off) * C_Z * (variants >= 1 ? 1 : 0); }
-size_t edge_embed_ctl_ints(int B) { return 2 + 4 * (size_t)B + 2 * (size_t)B; }
+size_t edge_embed_ctl_ints(int B) { return 4 + 4 * (size_t)B + 2 * (size_t)B; }
 
 void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st) {
   S2S_CHECK(((size_t)a.B * a.L * a.L) % TM == 0, "edge_embed_tc2 needs B*L*L % 128 == 0 (api.cu pads chain lengths to a multiple of 32)");
@@ -517,7 +529,7 @@ void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st) {
   if (a.table_variants > 0) {
     S2S_CHECK(a.table && a.tab_ctl && a.cls, "edge_embed_tc2: table buffers missing");
     k.ctl = a.tab_ctl;
-    embed_table_setup_kernel<<<1, 256, 0, st>>>(a.B, a.L, a.fixed, a.mask, a.cls, a.tab_ctl, a.table_variants);
+    embed_table_setup_kernel<<<a.B, 256, 0, st>>>(a.B, a.L, a.fixed, a.mask, a.cls, a.tab_ctl, a.tab_ctl + 2, a.table_variants);
     S2S_LAUNCH_CHECK();
     const int max_tiles = a.B * a.table_variants * (tab_rows_per_block(a.n_off) / TM);
     edge_embed_pipe_kernel<2><<<max_tiles < cap ? max_tiles : cap, P_THREADS, P_SMEM, st>>>(k);

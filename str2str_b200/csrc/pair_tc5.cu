@@ -1,0 +1,528 @@
+// Fused EdgeTransition on CTA PAIRS (tcgen05 cta_group::2): the third-generation kernel (pair_tc3.cu: same TMEM map, same
+// epilogue, same arithmetic and rounding points) with every MMA issued once per pair of SMs as M = 256.
+//
+// Why: pair_tc3's ncu capture shows 23.8 GB of L2 -> SM traffic per launch against 2.1 GB of DRAM traffic: every 128-row tile
+// pulls all 40 weight blocks (640 KB) through shared memory, and shared-memory bandwidth (operand reads + TMA writes, ~1.6 MB
+// per tile) is one of the three resources that kernel runs into.  In a CTA pair the two SMs work on two row
+// tiles with ONE weight stream: each CTA stages only half of every weight block (64 of its 128 output columns, 8 KB) and the
+// pair's M = 256 MMA reads the B operand half from each SM, so per SM the weight traffic from L2, the shared-memory writes and
+// the B-operand reads all halve, and one instruction issue covers two tiles.
+//
+// Roles per CTA (same as pair_tc3): warp 0 = TMA producer (its own activation tile, its half of the weight stream), warp 1 =
+// tensor-memory allocation and, in the LEADER CTA (cluster rank 0), the MMA issuer for the pair; warps 2..17 = epilogue of the
+// CTA's own 128 rows.  The issuer has to know that BOTH CTAs' operands are in place (TMA'd tiles, h1 / h2 written to tensor
+// memory, accumulators drained): warp 1 of the peer CTA walks the same sequence of waits on the peer's local barriers and
+// forwards each completion with one remote mbarrier arrive onto a mirror barrier in the leader's shared memory ("relay").
+// Completions of the MMAs go to both CTAs with multicast tcgen05.commit.
+#include <cstdlib>
+
+#include "s2s_internal.cuh"
+#include "tc_common.cuh"
+
+namespace s2s {
+
+using namespace tc;
+
+namespace {
+
+constexpr int NSTAGE = 16;                  // ring of half weight blocks (8 KB each)
+constexpr int HALF_BYTES = TILE_BYTES / 2;  // [64 n x 64 k] bf16, SW128 K-major
+constexpr int WTILES = 40;                  // 12 (layer 1) + 18 (layer 2) + 10 (final) blocks per row tile
+constexpr int OFF_A0 = 0;                   // [z | n'_j] tile: 4 K-blocks
+constexpr int OFF_W = 4 * TILE_BYTES;       // weight ring
+constexpr int OFF_VEC = OFF_W + NSTAGE * HALF_BYTES;
+constexpr int NEW = 16;                     // epilogue warps
+constexpr int NPART = NEW / 4;
+constexpr int CW = 128 / NPART;
+constexpr int ET5_THREADS = 64 + 32 * NEW;
+constexpr int NSEG = 4;
+constexpr int VEC_FLOATS = NSEG * (D_ET + C_Z) + D_ET + C_Z + C_Z + 2 * NPART * 128;
+constexpr int OFF_BAR = OFF_VEC + VEC_FLOATS * 4;
+// local barriers: w_full[NSTAGE] w_empty[NSTAGE] a0_full a0_empty fullE full2 fullF emptyE empty2 h1p[3] h2p[3]
+// mirrors (used in the leader): m_w_full[NSTAGE] m_a0_full m_emptyE m_empty2 m_h1p[3] m_h2p[3]
+constexpr int N_LOCAL = 2 * NSTAGE + 13;
+constexpr int N_MIRROR = NSTAGE + 9;
+constexpr int N_BARS = N_LOCAL + N_MIRROR;
+constexpr int SMEM_BYTES = OFF_BAR + N_BARS * 8 + 16;
+
+constexpr uint32_t COL_H1 = 256;
+constexpr uint32_t COL_FIN = 256;
+__device__ __forceinline__ uint32_t h2_col(int kb) { return (kb < 2 ? 448u : kb < 4 ? 0u : 128u) + 32u * (kb & 1); }
+__device__ __forceinline__ uint32_t h2_chunk_col(int c) { return c == 0 ? 448u : c == 1 ? 0u : 128u; }
+
+struct Args {
+  const bf16* wimg;
+  const float *u, *p, *b2, *ln_w, *ln_b, *mask;
+  bf16* z_out;
+  int L, n_tiles, ncopy;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// ---- cta_group::2 forms of the tcgen05 instructions (one kernel may use one cta_group only) ----
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// completion of all MMAs issued so far by this thread -> barrier at the same shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <bool kAccumulate>
+__device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(DESC_HI_SW128)
+      : "memory");
+}
+template <bool kAccumulate>
+__device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(DESC_HI_SW128)
+      : "memory");
+}
+__device__ __forceinline__ void kblock2_ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool first) {
+  if (first) umma2_ss<false>(d, a_lo, b_lo, idesc); else umma2_ss<true>(d, a_lo, b_lo, idesc);
+  umma2_ss<true>(d, a_lo + 2, b_lo + 2, idesc);
+  umma2_ss<true>(d, a_lo + 4, b_lo + 4, idesc);
+  umma2_ss<true>(d, a_lo + 6, b_lo + 6, idesc);
+}
+__device__ __forceinline__ void kblock2_ts(uint32_t d, uint32_t a_col, uint32_t b_lo, uint32_t idesc, bool first) {
+  if (first) umma2_ts<false>(d, a_col, b_lo, idesc); else umma2_ts<true>(d, a_col, b_lo, idesc);
+  umma2_ts<true>(d, a_col + 8, b_lo + 2, idesc);
+  umma2_ts<true>(d, a_col + 16, b_lo + 4, idesc);
+  umma2_ts<true>(d, a_col + 24, b_lo + 6, idesc);
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// wait with cluster-scope acquire (pairs with the remote arrive above)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <bool FLAT>
+__global__ void __launch_bounds__(ET5_THREADS, 1)
+edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_n, Args a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
+  float* u_s = reinterpret_cast<float*>(smem + OFF_VEC);  // [NSEG][D_ET]
+  float* p_s = u_s + NSEG * D_ET;                         // [NSEG][C_Z]
+  float* b2_s = p_s + NSEG * C_Z;
+  float* lnw_s = b2_s + D_ET;
+  float* lnb_s = lnw_s + C_Z;
+  float* red_s = lnb_s + C_Z;  // [2 stats][NPART column parts][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = bars + NSTAGE;
+  uint64_t* a0_full = bars + 2 * NSTAGE;
+  uint64_t* a0_empty = a0_full + 1;
+  uint64_t* fullE = a0_full + 2;
+  uint64_t* full2 = a0_full + 3;
+  uint64_t* fullF = a0_full + 4;
+  uint64_t* emptyE = a0_full + 5;
+  uint64_t* empty2 = a0_full + 6;
+  uint64_t* h1p = a0_full + 7;    // [3]
+  uint64_t* h2p = a0_full + 10;   // [3]
+  uint64_t* m_w_full = bars + N_LOCAL;   // mirrors: completions of the peer CTA's barriers, forwarded by its relay warp
+  uint64_t* m_a0_full = m_w_full + NSTAGE;
+  uint64_t* m_emptyE = m_a0_full + 1;
+  uint64_t* m_empty2 = m_a0_full + 2;
+  uint64_t* m_h1p = m_a0_full + 3;
+  uint64_t* m_h2p = m_a0_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+      mbar_init(&m_w_full[s], 1);
+    }
+    mbar_init(a0_full, 1);
+    mbar_init(a0_empty, 1);
+    mbar_init(fullE, 1);
+    mbar_init(full2, 1);
+    mbar_init(fullF, 1);
+    mbar_init(emptyE, 32 * NEW);
+    mbar_init(empty2, 32 * NEW);
+    mbar_init(m_a0_full, 1);
+    mbar_init(m_emptyE, 1);
+    mbar_init(m_empty2, 1);
+    for (int k = 0; k < 3; ++k) {
+      mbar_init(&h1p[k], 32 * NEW);
+      mbar_init(&h2p[k], 32 * NEW);
+      mbar_init(&m_h1p[k], 1);
+      mbar_init(&m_h2p[k], 1);
+    }
+    fence_barrier_init();
+  }
+  for (int c = threadIdx.x; c < D_ET; c += blockDim.x) b2_s[c] = a.b2[c];
+  for (int c = threadIdx.x; c < C_Z; c += blockDim.x) {
+    lnw_s[c] = a.ln_w[c];
+    lnb_s[c] = a.ln_b[c];
+  }
+  __syncthreads();
+  cluster_sync_all();                          // both CTAs are resident and their barriers initialised
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);  // the same warp of both CTAs, as the 2-SM allocation requires
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // tensor memory is allocated in both CTAs before any MMA of the pair can target it
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int tiles_per_i = FLAT ? 1 : a.L / TM;
+  constexpr uint32_t IDESC256 = make_idesc(256, 128);  // M = 256 across the pair, N = 128
+  // this CTA's tiles: pair p of the grid takes tiles 2p, 2p+1, then strides by the number of pairs
+  const int n_pairs_grid = gridDim.x / 2, pair_id = blockIdx.x / 2;
+  const int n_pair_tiles = a.n_tiles / 2;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's activation tile and its half of every weight block =====
+    if (lane == 0) {
+      uint32_t cnt = 0, ph_a0 = 0;
+      const unsigned char* wimg = reinterpret_cast<const unsigned char*>(a.wimg) + (size_t)(pair_id % a.ncopy) * ((size_t)WTILES * TILE_BYTES) +
+                                  (size_t)crank * HALF_BYTES;
+      for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
+        const int tile = 2 * pt + (int)crank;
+        const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;  // (unused when FLAT)
+        const int b = bi / a.L;
+        mbar_wait(a0_empty, ph_a0 ^ 1);
+        ph_a0 ^= 1;
+        mbar_expect_tx(a0_full, 4 * TILE_BYTES);
+        tma_load_2d(smem + OFF_A0, &tmap_z, 0, tile * TM, a0_full);
+        tma_load_2d(smem + OFF_A0 + TILE_BYTES, &tmap_z, KBLK, tile * TM, a0_full);
+        if constexpr (FLAT) {
+#pragma unroll
+          for (int sg = 0; sg < NSEG; ++sg) {
+            const long f = (long)tile * TM + sg * 32;
+            const int bi_s = (int)(f / a.L), j_s = (int)(f - (long)bi_s * a.L);
+            const int nrow = (bi_s / a.L) * a.L + j_s;
+            tma_load_2d(smem + OFF_A0 + 2 * TILE_BYTES + sg * 4096, &tmap_n, 0, nrow, a0_full);
+            tma_load_2d(smem + OFF_A0 + 3 * TILE_BYTES + sg * 4096, &tmap_n, KBLK, nrow, a0_full);
+          }
+        } else {
+          tma_load_2d(smem + OFF_A0 + 2 * TILE_BYTES, &tmap_n, 0, b * a.L + j0, a0_full);
+          tma_load_2d(smem + OFF_A0 + 3 * TILE_BYTES, &tmap_n, KBLK, b * a.L + j0, a0_full);
+        }
+        for (int wt = 0; wt < WTILES; ++wt, ++cnt) {
+          const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_expect_tx(&w_full[s], HALF_BYTES);
+          tma_bulk_1d(smem + OFF_W + s * HALF_BYTES, wimg + (size_t)wt * TILE_BYTES, HALF_BYTES, &w_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== leader: MMA issuer of the pair; peer: relay of its local completions to the leader's mirror barriers.
+    //       Both walk the same sequence of synchronisation points; the whole warp runs the loop, one elected lane acts. =====
+    const uint32_t a0 = desc_lo_sw128(smem_u32(smem + OFF_A0)), wr = desc_lo_sw128(smem_u32(smem + OFF_W));
+    constexpr uint32_t BLK = TILE_BYTES >> 4;    // activation K-block stride in descriptor units
+    constexpr uint32_t HBLK = HALF_BYTES >> 4;   // weight ring slot stride
+    uint32_t cnt = 0, ph_a0 = 0, ph_h1 = 0, ph_h2 = 0;
+    uint32_t nE = 0, n2 = 0;
+    // one synchronisation point: the event has happened in this CTA (local) and, for the leader, in the peer (mirror).
+    // `real` = the wait is for an actual completion (not the trivially passing first use of a "previous drain" wait).
+    auto sync_point = [&](uint64_t* local, uint64_t* mirror, uint32_t parity, bool real) {
+      mbar_wait(local, parity);
+      if (leader) {
+        mbar_wait_cluster(mirror, parity);
+      } else if (real) {
+        tc_fence_after();   // the event may cover tensor-memory writes of this CTA's epilogue warps:
+        tc_fence_before();  // order them before the hand-over to the leader's issuer
+        if (elect_one()) mbar_arrive_remote(mirror, 0);
+        __syncwarp();
+      }
+    };
+    auto next_block = [&]() -> uint32_t {
+      const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
+      sync_point(&w_full[s], &m_w_full[s], ph, true);
+      tc_fence_after();
+      return wr + s * HBLK;
+    };
+    auto release_block = [&]() { umma_commit2(&w_empty[cnt % NSTAGE]); };  // elected lane of the leader
+    auto wait_prev = [&](uint64_t* bar, uint64_t* mirror, uint32_t& n) {     // wait #k waits for drain #(k-1): the first one passes
+      sync_point(bar, mirror, (n & 1) ^ 1, n > 0);
+      ++n;
+    };
+    for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
+      sync_point(a0_full, m_a0_full, ph_a0, true);
+      ph_a0 ^= 1;
+      tc_fence_after();
+      // ---- layer 1: three 128-column chunks in E, R2, E; A = [z | n'_j] from shared memory ----
+      for (int nc = 0; nc < 3; ++nc) {
+        uint32_t d;
+        if (nc == 1) { wait_prev(empty2, m_empty2, n2); d = tmem + 128; }
+        else { wait_prev(emptyE, m_emptyE, nE); d = tmem; }
+        tc_fence_after();
+        for (int kb = 0; kb < 4; ++kb, ++cnt) {
+          const uint32_t wb = next_block();
+          if (leader && elect_one()) {
+            kblock2_ss(d, a0 + kb * BLK, wb, IDESC256, kb == 0);
+            release_block();
+          }
+          __syncwarp();
+        }
+        if (leader && elect_one()) umma_commit2(nc == 1 ? full2 : fullE);
+        __syncwarp();
+      }
+      // ---- layer 2: three 128-column chunks in R2, E, R2; A = h1 from tensor memory ----
+      for (int c = 0; c < 3; ++c) {
+        uint32_t d;
+        if (c == 1) { wait_prev(emptyE, m_emptyE, nE); d = tmem; }
+        else { wait_prev(empty2, m_empty2, n2); d = tmem + 128; }
+        tc_fence_after();
+        for (int kb = 0; kb < 6; ++kb, ++cnt) {
+          if (c == 0 && !(kb & 1)) {
+            sync_point(&h1p[kb >> 1], &m_h1p[kb >> 1], ph_h1, true);
+            tc_fence_after();
+          }
+          const uint32_t wb = next_block();
+          if (leader && elect_one()) {
+            kblock2_ts(d, tmem + COL_H1 + kb * 32, wb, IDESC256, kb == 0);
+            release_block();
+          }
+          __syncwarp();
+        }
+        if (leader && elect_one()) umma_commit2(c == 1 ? fullE : full2);
+        __syncwarp();
+      }
+      ph_h1 ^= 1;
+      // ---- final layer into F (over the dead h1): [z | n'_j] terms, then h2 ----
+      for (int kb = 0; kb < 4; ++kb, ++cnt) {
+        const uint32_t wb = next_block();
+        if (leader && elect_one()) {
+          kblock2_ss(tmem + COL_FIN, a0 + kb * BLK, wb, IDESC256, kb == 0);
+          release_block();
+        }
+        __syncwarp();
+      }
+      if (leader && elect_one()) umma_commit2(a0_empty);  // both CTAs' activation tiles are free
+      __syncwarp();
+      for (int kb = 0; kb < 6; ++kb, ++cnt) {
+        if (!(kb & 1)) {
+          sync_point(&h2p[kb >> 1], &m_h2p[kb >> 1], ph_h2, true);
+          tc_fence_after();
+        }
+        const uint32_t wb = next_block();
+        if (leader && elect_one()) {
+          kblock2_ts(tmem + COL_FIN, tmem + h2_col(kb), wb, IDESC256, false);
+          release_block();
+        }
+        __syncwarp();
+      }
+      ph_h2 ^= 1;
+      if (leader && elect_one()) umma_commit2(fullF);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue of this CTA's own 128 rows: identical to pair_tc3.cu =====
+    const int ew = warp - 2, q = warp & 3, part = ew >> 2, r = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint32_t fE = 0, f2 = 0, fF = 0;
+    for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
+      const int tile = 2 * pt + (int)crank;
+      int bi, jr;
+      if constexpr (FLAT) {
+        const long f = (long)tile * TM + r;
+        bi = (int)(f / a.L);
+        jr = (int)(f - (long)bi * a.L);
+      } else {
+        bi = tile / tiles_per_i;
+        jr = (tile % tiles_per_i) * TM + r;
+      }
+      const int b = bi / a.L;
+      named_bar_sync(1, 32 * NEW);
+      if constexpr (FLAT) {
+        for (int c = et; c < NSEG * D_ET; c += 32 * NEW) {
+          const int sg = c / D_ET;
+          u_s[c] = a.u[(size_t)(((long)tile * TM + sg * 32) / a.L) * D_ET + (c - sg * D_ET)];
+        }
+        {
+          const int sg = et / C_Z;
+          p_s[et] = a.p[(size_t)(((long)tile * TM + sg * 32) / a.L) * C_Z + (et - sg * C_Z)];
+        }
+      } else {
+        for (int c = et; c < D_ET; c += 32 * NEW) u_s[c] = a.u[(size_t)bi * D_ET + c];
+        if (et < C_Z) p_s[et] = a.p[(size_t)bi * C_Z + et];
+      }
+      named_bar_sync(1, 32 * NEW);
+      const float* u_q = FLAT ? u_s + q * D_ET : u_s;
+      const float* p_q = FLAT ? p_s + q * C_Z : p_s;
+      const float m = a.mask[bi] * a.mask[(size_t)b * a.L + jr];
+      float y[CW];
+      auto wait_full = [&](uint64_t* bar, uint32_t& n) {
+        mbar_wait(bar, n & 1);
+        ++n;
+        tc_fence_after();
+      };
+      auto add_vec = [&](const float* vec) {
+#pragma unroll
+        for (int e = 0; e < CW; e += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(vec + e);
+          y[e] += t.x; y[e + 1] += t.y; y[e + 2] += t.z; y[e + 3] += t.w;
+        }
+      };
+      auto load_cols = [&](uint32_t col) {
+        tmem_ld32_issue(tmem + lane_off + col, y);
+        tmem_wait_ld();
+      };
+      auto store_packed = [&](uint32_t col) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
+        tmem_st16(tmem + lane_off + col, pk);
+      };
+      // ---- layer 1: + u_i, relu, pack, into tensor memory as layer 2's A operand ----
+      for (int nc = 0; nc < 3; ++nc) {
+        const uint32_t base = nc == 1 ? 128u : 0u;
+        if (nc == 1) wait_full(full2, f2); else wait_full(fullE, fE);
+        load_cols(base + part * CW);
+        add_vec(u_q + nc * 128 + part * CW);
+        store_packed(COL_H1 + nc * 64 + part * (CW / 2));
+        tc_fence_before();
+        mbar_arrive(nc == 1 ? empty2 : emptyE);
+        mbar_arrive(&h1p[nc]);
+      }
+      // ---- layer 2: + b2, relu, pack, in place (chunks 1, 2) or into the spare strip (chunk 0) ----
+      for (int c = 0; c < 3; ++c) {
+        const uint32_t base = c == 1 ? 0u : 128u;
+        if (c == 1) wait_full(fullE, fE); else wait_full(full2, f2);
+        load_cols(base + part * CW);
+        add_vec(b2_s + c * 128 + part * CW);
+        if (c > 0) {
+          tc_fence_before();
+          named_bar_sync(2 + q, 32 * NPART);
+          tc_fence_after();
+        }
+        store_packed(h2_chunk_col(c) + part * (CW / 2));
+        tc_fence_before();
+        mbar_arrive(c == 1 ? emptyE : empty2);
+        mbar_arrive(&h2p[c]);
+      }
+      // ---- output: + p_i, LayerNorm over 128 channels, * edge mask, bf16 store ----
+      {
+        wait_full(fullF, fF);
+        load_cols(COL_FIN + part * CW);
+        tc_fence_before();
+        add_vec(p_q + part * CW);
+        float sum = 0.f;
+#pragma unroll
+        for (int e = 0; e < CW; ++e) sum += y[e];
+        red_s[part * 128 + r] = sum;
+        named_bar_sync(2 + q, 32 * NPART);
+        float tot = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NPART; ++pp) tot += red_s[pp * 128 + r];
+        const float mean = tot * (1.f / C_Z);
+        float sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < CW; ++e) {
+          const float d = y[e] - mean;
+          sq += d * d;
+        }
+        red_s[(NPART + part) * 128 + r] = sq;
+        named_bar_sync(2 + q, 32 * NPART);
+        float tsq = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NPART; ++pp) tsq += red_s[(NPART + pp) * 128 + r];
+        const float rstd = rsqrtf(tsq * (1.f / C_Z) + 1e-5f);
+        bf16* orow = a.z_out + ((size_t)tile * TM + r) * C_Z + part * CW;
+        const float* lw = lnw_s + part * CW;
+        const float* lb = lnb_s + part * CW;
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 8) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = ((y[c0 + e] - mean) * rstd * lw[c0 + e] + lb[c0 + e]) * m;
+          *reinterpret_cast<uint4*>(orow + c0) =
+              make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves (or frees tensor memory) while the pair's MMAs or remote arrives may still target it
+  if (warp == 1) tmem_dealloc2(tmem, 512);
+}
+
+}  // namespace
+
+bool edge_transition_pair_supported(int B, int L) { return L % 32 == 0 && (((size_t)B * L * L / TM) % 2 == 0); }
+
+void edge_transition_pair(const EdgeTransitionArgs& a, cudaStream_t st) {
+  S2S_CHECK(edge_transition_pair_supported(a.B, a.L), "edge_transition_pair needs L % 32 == 0 and an even number of row tiles");
+  static_assert(NEW == 16 && CW == 32, "the in-place h2 stores assume 4 column parts of 32");
+  static_assert(32 * NEW == NSEG * C_Z, "p_i staging assumes one element per epilogue thread");
+  S2S_CHECK(a.wimg3 && a.nprime_bf16, "edge_transition_pair: weight image / bf16 node embedding missing");
+  const bool flat = a.L % TM != 0;
+  const size_t rows = (size_t)a.B * a.L * a.L;
+  const CUtensorMap mz = make_bf16_2d_map(a.z_in, rows, C_Z, C_Z);
+  const CUtensorMap mn = make_bf16_2d_map(a.nprime_bf16, (size_t)a.B * a.L, C_Z, C_Z, flat ? 32 : 128);
+  Args k;
+  k.wimg = a.wimg3; k.u = a.u; k.p = a.p; k.b2 = a.b2; k.ln_w = a.ln_w; k.ln_b = a.ln_b; k.mask = a.mask;
+  k.z_out = a.z_out; k.L = a.L; k.n_tiles = (int)(rows / TM); k.ncopy = a.wimg_copies;
+  static bool configured = false;
+  const int smem = SMEM_BYTES + 1024;
+  if (!configured) {
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2S_CUDA(cudaFuncSetAttribute(edge_transition_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  S2S_PROF("edge_transition", st);
+  int grid = k.n_tiles < sm_count() ? k.n_tiles : sm_count();
+  grid &= ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ET5_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  // persistent kernel: never launch more clusters than can be co-resident (GPCs with an odd SM count strand one SM)
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    S2S_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, edge_transition_pair_kernel<false>, &cfg));
+    S2S_CHECK(max_clusters > 0, "edge_transition_pair: no 2-CTA cluster fits");
+  }
+  if (grid > 2 * max_clusters) grid = 2 * max_clusters;
+  cfg.gridDim = dim3(grid);
+  if (flat) S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_pair_kernel<true>, mz, mn, k));
+  else S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_pair_kernel<false>, mz, mn, k));
+  S2S_LAUNCH_CHECK();
+}
+
+}  // namespace s2s

@@ -134,6 +134,8 @@ struct EdgeTransitionArgs {
 };
 void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st);
 void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st);
+void edge_transition_pair(const EdgeTransitionArgs& a, cudaStream_t st);  // pair_tc5.cu: CTA pairs, cta_group::2 MMAs
+bool edge_transition_pair_supported(int B, int L);
 size_t et3_wimg_elems();
 void build_et3_wimg(const float* W1, const float* W2, const float* Wf, bf16* dst, cudaStream_t st);
 size_t ee_wimg_elems();

@@ -499,3 +499,25 @@ def test_edge_embed_table_is_bit_identical_to_direct(params, L, case):
     _, edge_o = O.embedder(params, ridx, t, fixed, sc)
     edge_o = edge_o * (rm[..., None] * rm[..., None, :])[..., None]
     assert rel(outs[1].float(), edge_o) < 4.5e-3
+
+
+# ---- EdgeTransition on CTA pairs (pair_tc5.cu, cta_group::2) -----------------------------------------------------------------
+@pytest.mark.parametrize("L,B", [(128, 2), (256, 2), (160, 3), (57, 2), (384, 1), (256, 7)])
+def test_edge_transition_cta_pair_kernel(params, L, B):
+    """The CTA-pair EdgeTransition kernel (M = 256 MMAs issued once per pair of SMs, half of the weight stream per SM) against
+    the oracle and against the single-CTA kernel: same arithmetic per row, so the two kernels must agree bit for bit."""
+    nm, node, edge = module_inputs(B, L, 700 + L, 4)
+    net = make_net(params)
+    eng = net.native("cuda")
+    eng.reserve(B, L)
+    outs = []
+    for pair in (0, 1):
+        eng.set_option("et_pair", pair)
+        outs.append(eng.edge_transition(2, node.cuda().contiguous(), edge.cuda().contiguous(), nm.cuda().contiguous()).clone())
+    torch.cuda.synchronize()
+    pre = "translator.trunk.edge_transition_2."
+    ref = O.edge_transition(params, pre, node, edge.float()) * (nm[..., None] * nm[..., None, :])[..., None]
+    r = rel(outs[1].float(), ref)
+    print(f"EdgeTransition CTA-pair kernel L={L} B={B}: vs fp32 oracle rel {r:.2e}; equal to the single-CTA kernel: {torch.equal(outs[0], outs[1])}")
+    assert r < 4.5e-3
+    assert torch.equal(outs[0], outs[1])
