@@ -10,10 +10,14 @@
 //
 // Roles per CTA (same as pair_tc3): warp 0 = TMA producer (its own activation tile, its half of the weight stream), warp 1 =
 // tensor-memory allocation and, in the LEADER CTA (cluster rank 0), the MMA issuer for the pair; warps 2..17 = epilogue of the
-// CTA's own 128 rows.  The issuer has to know that BOTH CTAs' operands are in place (TMA'd tiles, h1 / h2 written to tensor
-// memory, accumulators drained): warp 1 of the peer CTA walks the same sequence of waits on the peer's local barriers and
-// forwards each completion with one remote mbarrier arrive onto a mirror barrier in the leader's shared memory ("relay").
-// Completions of the MMAs go to both CTAs with multicast tcgen05.commit.
+// CTA's own 128 rows.  Everything the issuer waits for lives in the LEADER's shared memory and is signalled by both CTAs:
+//   * operand barriers (w_full, a0_full): armed by the leader's producer for the bytes of BOTH CTAs; the peer's TMA loads
+//     (cp.async.bulk.tensor ... cta_group::2) complete their bytes on the leader's barrier;
+//   * hand-over barriers (h1 / h2 written to tensor memory, accumulators drained): one arrival per epilogue WARP, local in the
+//     leader, a remote mbarrier arrive (release.cluster) from the peer.
+// Completions of the MMAs go to both CTAs with multicast tcgen05.commit.  (A first cut that forwarded the peer's local
+// barriers through a relay warp was bit-exact but 2.4x slower — 6.18 ms vs 2.57 ms at cfg2: every one of the ~56 hand-overs
+// per tile pair paid a poll + remote arrive + poll chain on the critical path.)
 #include <cstdlib>
 
 #include "s2s_internal.cuh"
@@ -38,11 +42,9 @@ constexpr int ET5_THREADS = 64 + 32 * NEW;
 constexpr int NSEG = 4;
 constexpr int VEC_FLOATS = NSEG * (D_ET + C_Z) + D_ET + C_Z + C_Z + 2 * NPART * 128;
 constexpr int OFF_BAR = OFF_VEC + VEC_FLOATS * 4;
-// local barriers: w_full[NSTAGE] w_empty[NSTAGE] a0_full a0_empty fullE full2 fullF emptyE empty2 h1p[3] h2p[3]
-// mirrors (used in the leader): m_w_full[NSTAGE] m_a0_full m_emptyE m_empty2 m_h1p[3] m_h2p[3]
-constexpr int N_LOCAL = 2 * NSTAGE + 13;
-constexpr int N_MIRROR = NSTAGE + 9;
-constexpr int N_BARS = N_LOCAL + N_MIRROR;
+// barriers: w_full[NSTAGE] w_empty[NSTAGE] a0_full a0_empty fullE full2 fullF emptyE empty2 h1p[3] h2p[3]
+// (w_full, a0_full, emptyE, empty2, h1p, h2p are used in the leader CTA only)
+constexpr int N_BARS = 2 * NSTAGE + 13;
 constexpr int SMEM_BYTES = OFF_BAR + N_BARS * 8 + 16;
 
 constexpr uint32_t COL_H1 = 256;
@@ -112,11 +114,22 @@ __device__ __forceinline__ void kblock2_ts(uint32_t d, uint32_t a_col, uint32_t 
   umma2_ts<true>(d, a_col + 16, b_lo + 4, idesc);
   umma2_ts<true>(d, a_col + 24, b_lo + 6, idesc);
 }
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+// shared::cluster address of the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t cluster_addr(const void* p, uint32_t cta) {
   uint32_t raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(p)), "r"(cta));
+  return raddr;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// 2-D tensor TMA load of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are completed on the barrier at
+// `bar_cluster_addr`, which may belong to the other CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+               : "memory");
 }
 // wait with cluster-scope acquire (pairs with the remote arrive above)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
@@ -134,7 +147,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) 
 
 template <bool FLAT>
 __global__ void __launch_bounds__(ET5_THREADS, 1)
-edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_n, Args a) {
+edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_n,
+                            const __grid_constant__ CUtensorMap tmap_w, Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   float* u_s = reinterpret_cast<float*>(smem + OFF_VEC);  // [NSEG][D_ET]
@@ -155,12 +169,6 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
   uint64_t* empty2 = a0_full + 6;
   uint64_t* h1p = a0_full + 7;    // [3]
   uint64_t* h2p = a0_full + 10;   // [3]
-  uint64_t* m_w_full = bars + N_LOCAL;   // mirrors: completions of the peer CTA's barriers, forwarded by its relay warp
-  uint64_t* m_a0_full = m_w_full + NSTAGE;
-  uint64_t* m_emptyE = m_a0_full + 1;
-  uint64_t* m_empty2 = m_a0_full + 2;
-  uint64_t* m_h1p = m_a0_full + 3;
-  uint64_t* m_h2p = m_a0_full + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -168,25 +176,19 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
   const bool leader = crank == 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], 1);
-      mbar_init(&m_w_full[s], 1);
+      mbar_init(&w_full[s], 1);   // leader: one arrive.expect_tx covering the half blocks of both CTAs
+      mbar_init(&w_empty[s], 1);  // one multicast commit
     }
     mbar_init(a0_full, 1);
     mbar_init(a0_empty, 1);
     mbar_init(fullE, 1);
     mbar_init(full2, 1);
     mbar_init(fullF, 1);
-    mbar_init(emptyE, 32 * NEW);
-    mbar_init(empty2, 32 * NEW);
-    mbar_init(m_a0_full, 1);
-    mbar_init(m_emptyE, 1);
-    mbar_init(m_empty2, 1);
+    mbar_init(emptyE, 2 * NEW);   // leader: one arrival per epilogue warp of the pair
+    mbar_init(empty2, 2 * NEW);
     for (int k = 0; k < 3; ++k) {
-      mbar_init(&h1p[k], 32 * NEW);
-      mbar_init(&h2p[k], 32 * NEW);
-      mbar_init(&m_h1p[k], 1);
-      mbar_init(&m_h2p[k], 1);
+      mbar_init(&h1p[k], 2 * NEW);
+      mbar_init(&h2p[k], 2 * NEW);
     }
     fence_barrier_init();
   }
@@ -210,142 +212,133 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
   const int n_pair_tiles = a.n_tiles / 2;
 
   if (warp == 0) {
-    // ===== TMA producer: this CTA's activation tile and its half of every weight block =====
+    // ===== TMA producer: this CTA's activation tile and its half of every weight block; all bytes complete on the LEADER's
+    //       barriers, which the leader's producer arms for both CTAs =====
     if (lane == 0) {
       uint32_t cnt = 0, ph_a0 = 0;
-      const unsigned char* wimg = reinterpret_cast<const unsigned char*>(a.wimg) + (size_t)(pair_id % a.ncopy) * ((size_t)WTILES * TILE_BYTES) +
-                                  (size_t)crank * HALF_BYTES;
+      const int wrow0 = (pair_id % a.ncopy) * (WTILES * TM) + (int)crank * 64;  // row of this CTA's half of block 0 in the weight map
+      const uint32_t a0_full_l = cluster_addr(a0_full, 0);
       for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
         const int tile = 2 * pt + (int)crank;
         const int bi = tile / tiles_per_i, j0 = (tile % tiles_per_i) * TM;  // (unused when FLAT)
         const int b = bi / a.L;
         mbar_wait(a0_empty, ph_a0 ^ 1);
         ph_a0 ^= 1;
-        mbar_expect_tx(a0_full, 4 * TILE_BYTES);
-        tma_load_2d(smem + OFF_A0, &tmap_z, 0, tile * TM, a0_full);
-        tma_load_2d(smem + OFF_A0 + TILE_BYTES, &tmap_z, KBLK, tile * TM, a0_full);
+        if (leader) mbar_expect_tx(a0_full, 2 * 4 * TILE_BYTES);
+        tma_load_2d_pair(smem + OFF_A0, &tmap_z, 0, tile * TM, a0_full_l);
+        tma_load_2d_pair(smem + OFF_A0 + TILE_BYTES, &tmap_z, KBLK, tile * TM, a0_full_l);
         if constexpr (FLAT) {
 #pragma unroll
           for (int sg = 0; sg < NSEG; ++sg) {
             const long f = (long)tile * TM + sg * 32;
             const int bi_s = (int)(f / a.L), j_s = (int)(f - (long)bi_s * a.L);
             const int nrow = (bi_s / a.L) * a.L + j_s;
-            tma_load_2d(smem + OFF_A0 + 2 * TILE_BYTES + sg * 4096, &tmap_n, 0, nrow, a0_full);
-            tma_load_2d(smem + OFF_A0 + 3 * TILE_BYTES + sg * 4096, &tmap_n, KBLK, nrow, a0_full);
+            tma_load_2d_pair(smem + OFF_A0 + 2 * TILE_BYTES + sg * 4096, &tmap_n, 0, nrow, a0_full_l);
+            tma_load_2d_pair(smem + OFF_A0 + 3 * TILE_BYTES + sg * 4096, &tmap_n, KBLK, nrow, a0_full_l);
           }
         } else {
-          tma_load_2d(smem + OFF_A0 + 2 * TILE_BYTES, &tmap_n, 0, b * a.L + j0, a0_full);
-          tma_load_2d(smem + OFF_A0 + 3 * TILE_BYTES, &tmap_n, KBLK, b * a.L + j0, a0_full);
+          tma_load_2d_pair(smem + OFF_A0 + 2 * TILE_BYTES, &tmap_n, 0, b * a.L + j0, a0_full_l);
+          tma_load_2d_pair(smem + OFF_A0 + 3 * TILE_BYTES, &tmap_n, KBLK, b * a.L + j0, a0_full_l);
         }
         for (int wt = 0; wt < WTILES; ++wt, ++cnt) {
           const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
           mbar_wait(&w_empty[s], ph ^ 1);
-          mbar_expect_tx(&w_full[s], HALF_BYTES);
-          tma_bulk_1d(smem + OFF_W + s * HALF_BYTES, wimg + (size_t)wt * TILE_BYTES, HALF_BYTES, &w_full[s]);
+          if (leader) mbar_expect_tx(&w_full[s], 2 * HALF_BYTES);
+          // the weight image is pre-swizzled: copied verbatim as a [64 rows x 128 B] box of an un-swizzled 2-D view
+          tma_load_2d_pair(smem + OFF_W + s * HALF_BYTES, &tmap_w, 0, wrow0 + wt * TM, cluster_addr(&w_full[s], 0));
         }
       }
     }
   } else if (warp == 1) {
-    // ===== leader: MMA issuer of the pair; peer: relay of its local completions to the leader's mirror barriers.
-    //       Both walk the same sequence of synchronisation points; the whole warp runs the loop, one elected lane acts. =====
-    const uint32_t a0 = desc_lo_sw128(smem_u32(smem + OFF_A0)), wr = desc_lo_sw128(smem_u32(smem + OFF_W));
-    constexpr uint32_t BLK = TILE_BYTES >> 4;    // activation K-block stride in descriptor units
-    constexpr uint32_t HBLK = HALF_BYTES >> 4;   // weight ring slot stride
-    uint32_t cnt = 0, ph_a0 = 0, ph_h1 = 0, ph_h2 = 0;
-    uint32_t nE = 0, n2 = 0;
-    // one synchronisation point: the event has happened in this CTA (local) and, for the leader, in the peer (mirror).
-    // `real` = the wait is for an actual completion (not the trivially passing first use of a "previous drain" wait).
-    auto sync_point = [&](uint64_t* local, uint64_t* mirror, uint32_t parity, bool real) {
-      mbar_wait(local, parity);
-      if (leader) {
-        mbar_wait_cluster(mirror, parity);
-      } else if (real) {
-        tc_fence_after();   // the event may cover tensor-memory writes of this CTA's epilogue warps:
-        tc_fence_before();  // order them before the hand-over to the leader's issuer
-        if (elect_one()) mbar_arrive_remote(mirror, 0);
-        __syncwarp();
-      }
-    };
-    auto next_block = [&]() -> uint32_t {
-      const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
-      sync_point(&w_full[s], &m_w_full[s], ph, true);
-      tc_fence_after();
-      return wr + s * HBLK;
-    };
-    auto release_block = [&]() { umma_commit2(&w_empty[cnt % NSTAGE]); };  // elected lane of the leader
-    auto wait_prev = [&](uint64_t* bar, uint64_t* mirror, uint32_t& n) {     // wait #k waits for drain #(k-1): the first one passes
-      sync_point(bar, mirror, (n & 1) ^ 1, n > 0);
-      ++n;
-    };
-    for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
-      sync_point(a0_full, m_a0_full, ph_a0, true);
-      ph_a0 ^= 1;
-      tc_fence_after();
-      // ---- layer 1: three 128-column chunks in E, R2, E; A = [z | n'_j] from shared memory ----
-      for (int nc = 0; nc < 3; ++nc) {
-        uint32_t d;
-        if (nc == 1) { wait_prev(empty2, m_empty2, n2); d = tmem + 128; }
-        else { wait_prev(emptyE, m_emptyE, nE); d = tmem; }
+    // ===== leader: MMA issuer of the pair (the whole warp runs the loop, one elected lane issues); the peer's warp 1 only
+    //       owns its half of the tensor-memory allocation =====
+    if (leader) {
+      const uint32_t a0 = desc_lo_sw128(smem_u32(smem + OFF_A0)), wr = desc_lo_sw128(smem_u32(smem + OFF_W));
+      constexpr uint32_t BLK = TILE_BYTES >> 4;    // activation K-block stride in descriptor units
+      constexpr uint32_t HBLK = HALF_BYTES >> 4;   // weight ring slot stride
+      uint32_t cnt = 0, ph_a0 = 0, ph_h1 = 0, ph_h2 = 0;
+      uint32_t nE = 0, n2 = 0;
+      auto next_block = [&]() -> uint32_t {
+        const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
+        mbar_wait(&w_full[s], ph);
         tc_fence_after();
+        return wr + s * HBLK;
+      };
+      auto release_block = [&]() { umma_commit2(&w_empty[cnt % NSTAGE]); };  // elected lane
+      auto wait_prev = [&](uint64_t* bar, uint32_t& n) {  // wait #k waits for drain #(k-1): the first one passes
+        mbar_wait_cluster(bar, (n & 1) ^ 1);
+        ++n;
+      };
+      for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
+        mbar_wait(a0_full, ph_a0);
+        ph_a0 ^= 1;
+        tc_fence_after();
+        // ---- layer 1: three 128-column chunks in E, R2, E; A = [z | n'_j] from shared memory ----
+        for (int nc = 0; nc < 3; ++nc) {
+          uint32_t d;
+          if (nc == 1) { wait_prev(empty2, n2); d = tmem + 128; }
+          else { wait_prev(emptyE, nE); d = tmem; }
+          tc_fence_after();
+          for (int kb = 0; kb < 4; ++kb, ++cnt) {
+            const uint32_t wb = next_block();
+            if (elect_one()) {
+              kblock2_ss(d, a0 + kb * BLK, wb, IDESC256, kb == 0);
+              release_block();
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit2(nc == 1 ? full2 : fullE);
+          __syncwarp();
+        }
+        // ---- layer 2: three 128-column chunks in R2, E, R2; A = h1 from tensor memory ----
+        for (int c = 0; c < 3; ++c) {
+          uint32_t d;
+          if (c == 1) { wait_prev(emptyE, nE); d = tmem; }
+          else { wait_prev(empty2, n2); d = tmem + 128; }
+          tc_fence_after();
+          for (int kb = 0; kb < 6; ++kb, ++cnt) {
+            if (c == 0 && !(kb & 1)) {
+              mbar_wait_cluster(&h1p[kb >> 1], ph_h1);
+              tc_fence_after();
+            }
+            const uint32_t wb = next_block();
+            if (elect_one()) {
+              kblock2_ts(d, tmem + COL_H1 + kb * 32, wb, IDESC256, kb == 0);
+              release_block();
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit2(c == 1 ? fullE : full2);
+          __syncwarp();
+        }
+        ph_h1 ^= 1;
+        // ---- final layer into F (over the dead h1): [z | n'_j] terms, then h2 ----
         for (int kb = 0; kb < 4; ++kb, ++cnt) {
           const uint32_t wb = next_block();
-          if (leader && elect_one()) {
-            kblock2_ss(d, a0 + kb * BLK, wb, IDESC256, kb == 0);
+          if (elect_one()) {
+            kblock2_ss(tmem + COL_FIN, a0 + kb * BLK, wb, IDESC256, kb == 0);
             release_block();
           }
           __syncwarp();
         }
-        if (leader && elect_one()) umma_commit2(nc == 1 ? full2 : fullE);
+        if (elect_one()) umma_commit2(a0_empty);  // both CTAs' activation tiles are free
         __syncwarp();
-      }
-      // ---- layer 2: three 128-column chunks in R2, E, R2; A = h1 from tensor memory ----
-      for (int c = 0; c < 3; ++c) {
-        uint32_t d;
-        if (c == 1) { wait_prev(emptyE, m_emptyE, nE); d = tmem; }
-        else { wait_prev(empty2, m_empty2, n2); d = tmem + 128; }
-        tc_fence_after();
         for (int kb = 0; kb < 6; ++kb, ++cnt) {
-          if (c == 0 && !(kb & 1)) {
-            sync_point(&h1p[kb >> 1], &m_h1p[kb >> 1], ph_h1, true);
+          if (!(kb & 1)) {
+            mbar_wait_cluster(&h2p[kb >> 1], ph_h2);
             tc_fence_after();
           }
           const uint32_t wb = next_block();
-          if (leader && elect_one()) {
-            kblock2_ts(d, tmem + COL_H1 + kb * 32, wb, IDESC256, kb == 0);
+          if (elect_one()) {
+            kblock2_ts(tmem + COL_FIN, tmem + h2_col(kb), wb, IDESC256, false);
             release_block();
           }
           __syncwarp();
         }
-        if (leader && elect_one()) umma_commit2(c == 1 ? fullE : full2);
+        ph_h2 ^= 1;
+        if (elect_one()) umma_commit2(fullF);
         __syncwarp();
       }
-      ph_h1 ^= 1;
-      // ---- final layer into F (over the dead h1): [z | n'_j] terms, then h2 ----
-      for (int kb = 0; kb < 4; ++kb, ++cnt) {
-        const uint32_t wb = next_block();
-        if (leader && elect_one()) {
-          kblock2_ss(tmem + COL_FIN, a0 + kb * BLK, wb, IDESC256, kb == 0);
-          release_block();
-        }
-        __syncwarp();
-      }
-      if (leader && elect_one()) umma_commit2(a0_empty);  // both CTAs' activation tiles are free
-      __syncwarp();
-      for (int kb = 0; kb < 6; ++kb, ++cnt) {
-        if (!(kb & 1)) {
-          sync_point(&h2p[kb >> 1], &m_h2p[kb >> 1], ph_h2, true);
-          tc_fence_after();
-        }
-        const uint32_t wb = next_block();
-        if (leader && elect_one()) {
-          kblock2_ts(tmem + COL_FIN, tmem + h2_col(kb), wb, IDESC256, false);
-          release_block();
-        }
-        __syncwarp();
-      }
-      ph_h2 ^= 1;
-      if (leader && elect_one()) umma_commit2(fullF);
-      __syncwarp();
     }
   } else {
     // ===== epilogue of this CTA's own 128 rows: identical to pair_tc3.cu =====
@@ -353,6 +346,19 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
     const int et = threadIdx.x - 64;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t fE = 0, f2 = 0, fF = 0;
+    // hand-over barriers live in the leader: shared::cluster addresses (the leader's own window for the leader itself)
+    const uint32_t emptyE_l = cluster_addr(emptyE, 0), empty2_l = cluster_addr(empty2, 0);
+    const uint32_t h1p_l = cluster_addr(h1p, 0), h2p_l = cluster_addr(h2p, 0);
+    // one arrival per warp: every lane has finished its tensor-memory reads / writes (tcgen05.wait + fence) before the
+    // __syncwarp that precedes lane 0's release-arrive
+    auto hand_over = [&](uint32_t bar_a, uint32_t bar_b) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(bar_a);
+        mbar_arrive_cluster(bar_b);
+      }
+    };
     for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
       const int tile = 2 * pt + (int)crank;
       int bi, jr;
@@ -413,9 +419,7 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
         load_cols(base + part * CW);
         add_vec(u_q + nc * 128 + part * CW);
         store_packed(COL_H1 + nc * 64 + part * (CW / 2));
-        tc_fence_before();
-        mbar_arrive(nc == 1 ? empty2 : emptyE);
-        mbar_arrive(&h1p[nc]);
+        hand_over(nc == 1 ? empty2_l : emptyE_l, h1p_l + nc * 8);
       }
       // ---- layer 2: + b2, relu, pack, in place (chunks 1, 2) or into the spare strip (chunk 0) ----
       for (int c = 0; c < 3; ++c) {
@@ -429,9 +433,7 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
           tc_fence_after();
         }
         store_packed(h2_chunk_col(c) + part * (CW / 2));
-        tc_fence_before();
-        mbar_arrive(c == 1 ? emptyE : empty2);
-        mbar_arrive(&h2p[c]);
+        hand_over(c == 1 ? emptyE_l : empty2_l, h2p_l + c * 8);
       }
       // ---- output: + p_i, LayerNorm over 128 channels, * edge mask, bf16 store ----
       {
@@ -493,6 +495,8 @@ void edge_transition_pair(const EdgeTransitionArgs& a, cudaStream_t st) {
   const size_t rows = (size_t)a.B * a.L * a.L;
   const CUtensorMap mz = make_bf16_2d_map(a.z_in, rows, C_Z, C_Z);
   const CUtensorMap mn = make_bf16_2d_map(a.nprime_bf16, (size_t)a.B * a.L, C_Z, C_Z, flat ? 32 : 128);
+  // the pre-swizzled weight image as [copies * 40 blocks * 128 rows][64] bf16: a 64-row box is one CTA's half of a block, verbatim
+  const CUtensorMap mw = make_bf16_2d_map(a.wimg3, (size_t)a.wimg_copies * WTILES * TM, KBLK, KBLK, 64, false);
   Args k;
   k.wimg = a.wimg3; k.u = a.u; k.p = a.p; k.b2 = a.b2; k.ln_w = a.ln_w; k.ln_b = a.ln_b; k.mask = a.mask;
   k.z_out = a.z_out; k.L = a.L; k.n_tiles = (int)(rows / TM); k.ncopy = a.wimg_copies;
@@ -520,8 +524,8 @@ void edge_transition_pair(const EdgeTransitionArgs& a, cudaStream_t st) {
   }
   if (grid > 2 * max_clusters) grid = 2 * max_clusters;
   cfg.gridDim = dim3(grid);
-  if (flat) S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_pair_kernel<true>, mz, mn, k));
-  else S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_pair_kernel<false>, mz, mn, k));
+  if (flat) S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_pair_kernel<true>, mz, mn, mw, k));
+  else S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_pair_kernel<false>, mz, mn, mw, k));
   S2S_LAUNCH_CHECK();
 }
 

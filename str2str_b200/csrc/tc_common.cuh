@@ -213,7 +213,7 @@ __device__ __forceinline__ void kblock_ts(uint32_t d, uint32_t a_col, uint32_t b
 }  // namespace tc
 
 // host helpers (tc_host.cu)
-CUtensorMap make_bf16_2d_map(const void* base, size_t rows, size_t cols, size_t row_pitch_elems, int box_rows = 128);
+CUtensorMap make_bf16_2d_map(const void* base, size_t rows, size_t cols, size_t row_pitch_elems, int box_rows = 128, bool swizzle = true);
 int sm_count();
 
 }  // namespace s2s

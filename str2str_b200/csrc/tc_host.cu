@@ -36,16 +36,16 @@ EncodeTiledFn encode_tiled() {
 }
 }  // namespace
 
-// [rows][cols] bf16 row-major tensor (row pitch in elements), boxes of box_rows rows x 64 columns, 128-byte swizzle;
-// out-of-bounds box elements read as zero
-CUtensorMap make_bf16_2d_map(const void* base, size_t rows, size_t cols, size_t row_pitch_elems, int box_rows) {
+// [rows][cols] bf16 row-major tensor (row pitch in elements), boxes of box_rows rows x 64 columns, 128-byte swizzle (or, with
+// swizzle = false, a verbatim copy: used for pre-swizzled weight images); out-of-bounds box elements read as zero
+CUtensorMap make_bf16_2d_map(const void* base, size_t rows, size_t cols, size_t row_pitch_elems, int box_rows, bool swizzle) {
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)row_pitch_elems * 2};
   cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUresult rc = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   S2S_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
   return m;
