@@ -120,8 +120,13 @@ __device__ __forceinline__ uint32_t cluster_addr(const void* p, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(p)), "r"(cta));
   return raddr;
 }
+// Remote arrive with RELAXED semantics.  What the issuer needs from a hand-over is ordering of tcgen05 operations (the
+// arriving warp's tcgen05.ld / st have completed: tcgen05.wait + tcgen05.fence::before_thread_sync precede the arrive), not
+// visibility of generic-proxy memory: the data stays in the peer's tensor memory and is read there by the peer's tensor core.
+// A release.cluster arrive compiles to MEMBAR.ALL.GPU + CCTL.IVALL per hand-over and an acquire.cluster wait to an L1
+// invalidation per successful poll (measured: 2.99 ms per launch with them, against 2.59 ms for the single-CTA kernel).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 // 2-D tensor TMA load of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are completed on the barrier at
 // `bar_cluster_addr`, which may belong to the other CTA of the pair
@@ -131,20 +136,6 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
                "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
                : "memory");
 }
-// wait with cluster-scope acquire (pairs with the remote arrive above)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(b)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-
 template <bool FLAT>
 __global__ void __launch_bounds__(ET5_THREADS, 1)
 edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_n,
@@ -266,7 +257,7 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
       };
       auto release_block = [&]() { umma_commit2(&w_empty[cnt % NSTAGE]); };  // elected lane
       auto wait_prev = [&](uint64_t* bar, uint32_t& n) {  // wait #k waits for drain #(k-1): the first one passes
-        mbar_wait_cluster(bar, (n & 1) ^ 1);
+        mbar_wait(bar, (n & 1) ^ 1);
         ++n;
       };
       for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
@@ -298,7 +289,7 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
           tc_fence_after();
           for (int kb = 0; kb < 6; ++kb, ++cnt) {
             if (c == 0 && !(kb & 1)) {
-              mbar_wait_cluster(&h1p[kb >> 1], ph_h1);
+              mbar_wait(&h1p[kb >> 1], ph_h1);
               tc_fence_after();
             }
             const uint32_t wb = next_block();
@@ -325,7 +316,7 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
         __syncwarp();
         for (int kb = 0; kb < 6; ++kb, ++cnt) {
           if (!(kb & 1)) {
-            mbar_wait_cluster(&h2p[kb >> 1], ph_h2);
+            mbar_wait(&h2p[kb >> 1], ph_h2);
             tc_fence_after();
           }
           const uint32_t wb = next_block();
