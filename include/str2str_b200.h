@@ -48,6 +48,9 @@ int s2s_finalize(s2s_ctx* ctx, void* stream);
  *          "ipa_kernels"  1 = second-generation IPA path (default; needs node_gemm = 1 and L <= 512, longer chains fall back
  *                         automatically): point-attention term folded into the logits GEMM, persistent TMA + tcgen05 pair kernel,
  *                         split-bf16 attention weights; 0 = first-generation kernels (A/B, tests);
+ *          "et_pair"      1 = EdgeTransition on CTA pairs (tcgen05 cta_group::2: M = 256 MMAs issued once per pair of SMs, half of the
+ *                         weight stream per SM; default; measured 2.22 vs 2.49 ms per launch at cfg2, same values bit for bit),
+ *                         0 = one CTA per row tile (A/B, tests);
  *          "embed_table"  1 = the edge embedder builds each decoy's (fixed_i, fixed_j, index offset, distogram bin) -> embedding
  *                         table and expands it into the pair tensor whenever that table is well below L^2 rows (default; same
  *                         values bit for bit), 0 = always run the MLP on every pair row (A/B, tests). */

@@ -115,7 +115,7 @@ using namespace s2s;
 struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
-  int opt_pair = 1, opt_node = 1, opt_ipa = 1, opt_table = 1, opt_et_pair = 0;
+  int opt_pair = 1, opt_node = 1, opt_ipa = 1, opt_table = 1, opt_et_pair = 1;
   int tfm_passes = 1;  // sequence-transformer in_proj + attention GEMMs: 1 = single bf16 (default; trajectory error unchanged, tools/traj_parity.py), 3 = split-bf16 (S2S_TFM_PASSES=3)
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
