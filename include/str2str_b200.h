@@ -126,6 +126,10 @@ int s2s_se3_perturb(int B, int L, const float* rot0, const float* trans0, const 
  * rotation / translation noise of SDE iteration k).  uniform = 0: N(0,1); 1: U[0,1).  A decoy's draws therefore do not depend
  * on the batch, rank or world size it is sampled in. */
 int s2s_rng_fill(float* out, int B, int64_t n_per_decoy, uint64_t seed, int64_t first_decoy, int stream_id, int uniform, void* stream);
+/* The same draws for rows that belong to different decoys / iterations (continuous batching of trajectories): row b draws for
+ * decoy decoy_ids[b] (device int64 [B]; a negative id leaves the row untouched), block stream_ids[b] (device int32 [B]). */
+int s2s_rng_fill_rows(float* out, int B, int64_t n_per_decoy, uint64_t seed, const int64_t* decoy_ids, const int32_t* stream_ids,
+                      int uniform, void* stream);
 /* compute_backbone (reference src/common/all_atom.py:141-173): atom37 [B,L,37,3], atom14 [B,L,14,3] (nullable).
  * aatype may be NULL (all alanine, as the reference does for aatype=None). */
 int s2s_backbone_atoms(s2s_ctx* ctx, int rows, const float* rigids, const float* psi, const int64_t* aatype,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "s2s_se3_step": (_i, [_i, _i] + [_vp] * 8 + [_f, _i, _i] + [_vp] * 4),
     "s2s_se3_perturb": (_i, [_i, _i] + [_vp] * 11),
     "s2s_rng_fill": (_i, [_vp, _i, _i64, C.c_uint64, _i64, _i, _i, _vp]),
+    "s2s_rng_fill_rows": (_i, [_vp, _i, _i64, C.c_uint64, _vp, _vp, _i, _vp]),
     "s2s_backbone_atoms": (_i, [_vp, _i] + [_vp] * 6),
     "s2s_linear_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "s2s_linear_tc": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),

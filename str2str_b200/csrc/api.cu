@@ -1048,6 +1048,14 @@ int s2s_rng_fill(float* out, int B, int64_t n_per_decoy, uint64_t seed, int64_t 
   });
 }
 
+int s2s_rng_fill_rows(float* out, int B, int64_t n_per_decoy, uint64_t seed, const int64_t* decoy_ids, const int32_t* stream_ids,
+                      int uniform, void* stream) {
+  return guarded([&] {
+    S2S_CHECK(out && B > 0 && n_per_decoy > 0 && decoy_ids && stream_ids, "s2s_rng_fill_rows: bad argument");
+    philox_fill(out, B, (long)n_per_decoy, seed, 0, 0, uniform, (cudaStream_t)stream, (const long long*)decoy_ids, (const int*)stream_ids);
+  });
+}
+
 int s2s_backbone_atoms(s2s_ctx* c, int rows, const float* rigids, const float* psi, const int64_t* aatype, float* atom37,
                        float* atom14, void* stream) {
   return guarded([&] {

@@ -13,15 +13,21 @@ namespace s2s {
 
 namespace {
 
+// decoy_ids / stream_ids (optional, per row): row b draws for decoy decoy_ids[b] (else first_decoy + b), block stream_ids[b]
+// (else stream_id); rows with a negative decoy id are left untouched (idle rows of a continuous batch)
 __global__ void philox_fill_kernel(float* __restrict__ out, int B, long n_per_decoy, unsigned long long seed, long long first_decoy,
-                                   unsigned long long stream_id, int uniform) {
+                                   unsigned long long stream_id, int uniform, const long long* __restrict__ decoy_ids,
+                                   const int* __restrict__ stream_ids) {
   const long quads = (n_per_decoy + 3) / 4;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * quads) return;
   const int b = (int)(idx / quads);
   const long qd = idx - (long)b * quads;
+  const long long decoy = decoy_ids ? decoy_ids[b] : first_decoy + b;
+  if (decoy < 0) return;
+  if (stream_ids) stream_id = (unsigned long long)stream_ids[b];
   curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)(first_decoy + b), (stream_id << 24) + 4ull * (unsigned long long)qd, &st);
+  curand_init(seed, (unsigned long long)decoy, (stream_id << 24) + 4ull * (unsigned long long)qd, &st);
   float4 v;
   if (uniform) {
     v = curand_uniform4(&st);  // (0, 1]
@@ -40,10 +46,11 @@ __global__ void philox_fill_kernel(float* __restrict__ out, int B, long n_per_de
 }  // namespace
 
 void philox_fill(float* out, int B, long n_per_decoy, unsigned long long seed, long long first_decoy, unsigned long long stream_id,
-                 int uniform, cudaStream_t st) {
+                 int uniform, cudaStream_t st, const long long* decoy_ids, const int* stream_ids) {
   S2S_CHECK(n_per_decoy > 0 && n_per_decoy < (1l << 24), "philox_fill: at most 2^24 - 1 elements per decoy and draw");
   const long quads = (n_per_decoy + 3) / 4;
-  philox_fill_kernel<<<ceil_div((long)B * quads, 256), 256, 0, st>>>(out, B, n_per_decoy, seed, first_decoy, stream_id, uniform);
+  philox_fill_kernel<<<ceil_div((long)B * quads, 256), 256, 0, st>>>(out, B, n_per_decoy, seed, first_decoy, stream_id, uniform, decoy_ids,
+                                                                     stream_ids);
   S2S_LAUNCH_CHECK();
 }
 

@@ -231,6 +231,6 @@ void backbone_atoms(const float* rig7, const float* psi, const long long* aatype
 
 // ---- rng.cu -------------------------------------------------------------------------------------------
 void philox_fill(float* out, int B, long n_per_decoy, unsigned long long seed, long long first_decoy, unsigned long long stream_id,
-                 int uniform, cudaStream_t st);
+                 int uniform, cudaStream_t st, const long long* decoy_ids = nullptr, const int* stream_ids = nullptr);
 
 }  // namespace s2s

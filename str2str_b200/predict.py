@@ -63,11 +63,13 @@ def merge_pdbfiles(files: List[str], output_file: str) -> int:
 
 
 def predict_step(sampler: ForwardBackwardSampler, batch: Dict[str, torch.Tensor], output_dir: Optional[str] = None,
-                 continuous: bool = False) -> str:
+                 continuous: bool = True, seed: Optional[int] = None) -> str:
     """One protein (batch size 1, like the reference asserts) through the whole δ-sweep; returns the all_delta directory.
-    `continuous=True` streams all (δ, replica) trajectories through one persistent batch (`scheduler.TrajectoryScheduler`:
-    same per-trajectory results, ~18 % fewer network iterations at the reference's default sweep) instead of running each δ
-    in batches of `replica_per_batch`; the files written are laid out identically."""
+    `continuous=True` (default) streams all (δ, replica) trajectories through one persistent batch
+    (`scheduler.TrajectoryScheduler`: same per-trajectory results, ~18 % fewer network iterations at the reference's default
+    sweep; ODE and SDE samplers); `continuous=False` runs each δ in batches of `replica_per_batch` like the reference.  The
+    files written are laid out identically.  With `seed`, replica r of the d-th δ is job-wide decoy d * n_replica + r in
+    either mode, so both modes sample the same ensemble."""
     cfg = sampler.cfg
     output_dir = output_dir or cfg.output_dir
     if output_dir is None:
@@ -82,13 +84,13 @@ def predict_step(sampler: ForwardBackwardSampler, batch: Dict[str, torch.Tensor]
     extra = {k: batch[k][0].detach().cpu().numpy() for k in ("aatype", "chain_index", "residue_index") if k in batch}
     saved = []
     streamed = None
-    if continuous and cfg.probability_flow and not cfg.backward_only:
+    if continuous and not cfg.backward_only and batch["aatype"].is_cuda:
         from .scheduler import TrajectoryScheduler
 
-        streamed = TrajectoryScheduler(sampler).run(batch, [(d, n_replica) for d in deltas])
-    for t_delta in deltas:
+        streamed = TrajectoryScheduler(sampler).run(batch, [(d, n_replica) for d in deltas], seed=seed)
+    for k, t_delta in enumerate(deltas):
         # [n_replica, L, 37, 3]: from the continuous schedule, or replica_per_batch at a time
-        atom37 = streamed[t_delta] if streamed is not None else sampler.sample(batch, t_delta, n_replica)
+        atom37 = streamed[t_delta] if streamed is not None else sampler.sample(batch, t_delta, n_replica, seed=seed, first_decoy=k * n_replica)
         d = os.path.join(output_dir, f"{t_delta}")
         os.makedirs(d, exist_ok=True)
         saved.append(atom37_to_pdb(save_to=os.path.join(d, f"{accession}.pdb"), atom_positions=atom37, **extra))

@@ -521,3 +521,57 @@ def test_edge_transition_cta_pair_kernel(params, L, B):
     print(f"EdgeTransition CTA-pair kernel L={L} B={B}: vs fp32 oracle rel {r:.2e}; equal to the single-CTA kernel: {torch.equal(outs[0], outs[1])}")
     assert r < 4.5e-3
     assert torch.equal(outs[0], outs[1])
+
+
+# ---- the caller of the path: continuous batching of (delta, replica) trajectories ------------------------------------------
+@pytest.mark.parametrize("sde", [False, True])
+def test_trajectory_scheduler_vs_oracle(params, sde):
+    """TrajectoryScheduler (str2str_b200/scheduler.py): trajectories of two deltas (6 and 10 denoising steps) stream through a 2-row
+    persistent batch, ODE and SDE sampler; every trajectory is compared with the CPU ORACLE's forward_backward of its delta
+    (diffusion_module.py:260-334) from the same perturbed start frames — and, for the SDE sampler, the same per-step noise, which
+    both sides key by (seed, job-wide decoy id, iteration)."""
+    from str2str_b200.rigid import Rigid
+    from str2str_b200.sampler import ForwardBackwardSampler, InferenceConfig
+    from str2str_b200.scheduler import TrajectoryScheduler
+
+    L, seed = 64, 77
+    feats = synthetic.make_features(1, L, seed=21, n_pad=3, random_aatype=True)
+    q, x = synthetic.make_backbone(L, seed=21)
+    gt = torch.zeros(1, L, 8, 4, 4)
+    gt[0, :, 0, :3, :3] = O.quat_to_rotmat(torch.nn.functional.normalize(q, dim=-1))
+    gt[0, :, 0, :3, 3] = x
+    gt[0, :, 0, 3, 3] = 1.0
+    batch = cuda(dict(feats, rigidgroups_gt_frames=gt))
+    net = make_net(params)
+    cfg = InferenceConfig(num_timesteps=20, min_t=0.01, probability_flow=not sde, noise_scale=0.6)
+    d = make_diffuser()
+    smp = ForwardBackwardSampler(net, d, cfg, use_cuda_graph=True)
+    work = [(0.3, 3), (0.5, 2)]
+    gen = torch.Generator().manual_seed(9)
+    start = {}
+    for delta, n in work:
+        r0 = Rigid.from_tensor_7(torch.cat([q, x], -1)[None].repeat(n, 1, 1).cuda(), normalize_quats=True)
+        noise = (torch.randn(n, L, 3, generator=gen), torch.rand(n, L, generator=gen), torch.randn(n, L, 3, generator=gen))
+        start[delta] = d.forward_marginal(r0, delta * torch.ones(n), diffuse_mask=torch.ones(n, L, dtype=torch.float64), noise=noise)["rigids_t"]
+    sched = TrajectoryScheduler(smp, slots=2)
+    atom37, rig = sched.run(batch, work, rigids_t=start, return_rigids=True, seed=seed)
+    assert sched.iterations == 25 and sched.row_iterations == 3 * 7 + 2 * 11   # row 0: 7 + 7 + 11 phases, row 1: 7 + 11 (1 + n each)
+    first = 0
+    for delta, n in work:
+        steps = int(20 * delta)
+        noises = None
+        if sde:
+            noises = [(d.decoy_noise((n, L, 3), "cuda", seed, first, 16 + 2 * k).cpu(), d.decoy_noise((n, L, 3), "cuda", seed, first, 17 + 2 * k).cpu())
+                      for k in range(steps)]
+        fB = synthetic.make_features(n, L, seed=21, n_pad=3, random_aatype=True)
+        fin, _, a37 = O.forward_backward(params, fB, start[delta].cpu(), delta, 20, noise_scale=0.6, probability_flow=not sde, noises=noises)
+        valid = fB["residue_mask"].bool()
+        r = rel(rig[delta].cpu()[..., 4:][valid], fin[..., 4:][valid])
+        print(f"scheduler {'SDE' if sde else 'ODE'} delta={delta}: C-alpha rel vs oracle {r:.2e}")
+        assert r < 1e-4
+        assert np.abs(atom37[delta][valid.numpy()][:, :5] - a37.numpy()[valid.numpy()][:, :5]).max() < 5e-3
+        # the same trajectories from the per-delta sampler (own batch, same decoy ids): equal up to fp32 reordering noise
+        r0 = Rigid.from_tensor_7(torch.cat([q, x], -1)[None].repeat(n, 1, 1).cuda(), normalize_quats=True)
+        _, rig_ref, _ = smp.forward_backward(batch, r0, delta, rigids_t=start[delta], return_rigids=True, seed=seed, first_decoy=first)
+        assert rel(rig[delta][..., 4:], rig_ref[..., 4:]) < 2e-5
+        first += n

@@ -138,26 +138,12 @@ def test_decoy_sharding_all_gather_gloo_world2(tmp_path):
 
 
 def test_trajectory_scheduler_plan_and_phases():
-    """Continuous batching of (delta, replica) trajectories (str2str_b200/scheduler.py): phase bookkeeping of one trajectory and
-    the occupancy arithmetic against the reference's per-delta batching (configs/model/diffusion.yaml:88-100 defaults)."""
-    from str2str_b200.sampler import InferenceConfig
-    from str2str_b200.scheduler import Trajectory, plan_iterations
-    from str2str_b200.score import FrameDiffuser, R3Diffuser, SO3Diffuser
+    """Continuous batching of (delta, replica) trajectories (str2str_b200/scheduler.py): the occupancy arithmetic against the
+    reference's per-delta batching (configs/model/diffusion.yaml:88-100 defaults)."""
+    from str2str_b200.scheduler import plan_iterations
 
-    cfg = InferenceConfig(num_timesteps=20, min_t=0.01)
-    diffuser = FrameDiffuser(R3Diffuser(0.1, 20.0, 0.1), SO3Diffuser(cache_dir="/tmp/str2str_b200_cache"), min_t=1e-2)
-    cache = {}
-    tr = Trajectory(0.5, 0, cfg, cache, diffuser)
-    assert tr.n == 10 and tr.n_phases == 11 and abs(tr.dt - 0.1) < 1e-15
-    assert tr.is_priming() and tr.step_index() == 0
-    tr.phase = 1
-    assert not tr.is_priming() and tr.step_index() == 0 and not tr.is_last()      # the first denoising iteration reuses ts[0]
-    tr.phase = 10
-    assert tr.is_last() and tr.step_index() == 9 and abs(float(tr.ts[9]) - cfg.min_t) < 1e-12
-    assert abs(float(tr.rows[0, 0]) - 0.5) < 1e-7 and tr.rows.shape == (10, 8)
-    assert Trajectory(0.5, 1, cfg, cache, diffuser).rows is tr.rows               # one schedule table per delta
-    no_sc = Trajectory(0.5, 0, InferenceConfig(num_timesteps=20, min_t=0.01, self_conditioning=False), {}, diffuser)
-    assert no_sc.n_phases == 10 and not no_sc.is_priming()
+    assert plan_iterations([10, 10, 6], 2) == (18, 18)     # rows: 11 + 7 | 11; the reference: 11 (two rows) + 7
+    assert plan_iterations([6, 6, 6, 10, 10], 2, prime=1) == (25, 25)
     # reference defaults: delta 0.25 .. 0.70 step 0.05, 100 replicas each, 64 rows: every delta runs 64 + 36
     steps = [int(1000 * d / 100) for d in range(25, 75, 5) for _ in range(100)]
     cont, ref = plan_iterations(steps, 64)
