@@ -14,6 +14,7 @@ namespace s2s {
 
 long long g_launch_count = 0;
 bool g_profile_on = false;
+bool g_pdl = [] { const char* e = getenv("S2S_PDL"); return e ? atoi(e) != 0 : true; }();
 static thread_local std::string g_error;
 
 struct ProfRec { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; double ms = 0; long long n = 0; };

@@ -7,6 +7,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace s2s {
 
@@ -64,9 +65,31 @@ const char* prof_intern(const std::string& name);  // stable storage for dynamic
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch.  Every kernel of the denoising iteration is launched with the programmatic-stream-
+// serialization attribute and calls pdl_sync() before its first access to global memory: the grid may then become resident
+// (barrier init, tensor-memory allocation, index arithmetic) while the previous kernel of the stream drains, instead of
+// paying launch latency + prologue after it.  pdl_sync() waits until the prerequisite grid has completed and its memory
+// operations are visible, and only THEN allows the next launch: at most one successor is staged behind a running kernel.
+// The attribute and the wait go together: a kernel launched through launch_pdl() without a pdl_sync() would race.
+extern bool g_pdl;  // api.cu; S2S_PDL=0 launches every kernel fully serialised (A/B timing)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  S2S_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+}
+
 typedef __nv_bfloat16 bf16;
 
 // ---- small device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

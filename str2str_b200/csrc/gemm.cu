@@ -13,6 +13,7 @@ constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, NT = 256;
 
 template <bool B_KN>
 __global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmArgs g) {
+  pdl_sync();
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
   const int bz = blockIdx.z;
@@ -121,9 +122,9 @@ void gemm_f32(const GemmArgs& g, cudaStream_t st) {
   S2S_PROF(g_profile_on ? prof_intern("gemm_f32 M" + std::to_string(g.M) + " N" + std::to_string(g.N) + " K" + std::to_string(g.K) + " b" + std::to_string(g.nb * g.nh)) : "gemm", st);
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.nb * g.nh);
   if (g.b_kn)
-    gemm_f32_kernel<true><<<grid, NT, 0, st>>>(g);
+    launch_pdl(gemm_f32_kernel<true>, grid, NT, 0, st, g);
   else
-    gemm_f32_kernel<false><<<grid, NT, 0, st>>>(g);
+    launch_pdl(gemm_f32_kernel<false>, grid, NT, 0, st, g);
   S2S_LAUNCH_CHECK();
 }
 

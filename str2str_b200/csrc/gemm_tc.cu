@@ -81,6 +81,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // barriers and tensor memory are set up: from here on the kernel reads what the previous one wrote
   const int MT = (a.M + TM - 1) / TM, NT = (a.N + 127) / 128, KB = (a.K + KBLK - 1) / KBLK;
   const int KB2 = (a.K2 + KBLK - 1) / KBLK, KBT = KB + KB2;
   const int n_tiles = a.nb * a.nh * MT * NT;
@@ -515,6 +516,7 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // barriers and tensor memory are set up: from here on the kernel reads what the previous one wrote
   const int MT = (a.M + TM - 1) / TM, KB = a.K / KBLK;
   const int KB2 = (a.K2 + KBLK - 1) / KBLK, KBT = KB + KB2;  // second K segment (passes == 1): through the mAl / mBl maps
   const int NP = a.nb * a.nh * MT;                            // panels: (batch, head, 128-row tile)
@@ -803,6 +805,7 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
 
 __global__ void split_bf16_kernel(const float* __restrict__ src, long ld, int rows, int cols, bf16* __restrict__ hi,
                                   bf16* __restrict__ lo) {
+  pdl_sync();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long n4 = (long)rows * (cols / 4);
   if (i >= n4) return;
@@ -824,7 +827,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, long ld, int ro
 void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st) {
   S2S_CHECK(cols % 4 == 0 && ld % 4 == 0, "split_bf16: width must be a multiple of 4");
   S2S_PROF("split_bf16", st);
-  split_bf16_kernel<<<ceil_div((long)rows * (cols / 4), 256), 256, 0, st>>>(src, ld, rows, cols, hi, lo);
+  launch_pdl(split_bf16_kernel, ceil_div((long)rows * (cols / 4), 256), 256, 0, st, src, ld, rows, cols, hi, lo);
   S2S_LAUNCH_CHECK();
 }
 
@@ -899,7 +902,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
         S2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         pconf[epi] = true;
       }
-      kern<<<pgrid, G_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, k, pg);
+      launch_pdl(kern, pgrid, G_THREADS, smem, st, mAh, mAl, mBh, mBl, k, pg);
     };
     switch (epi) {
       case 1: plaunch(gemm_panel_kernel<1>); break;
@@ -923,7 +926,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
       S2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured[epi + 1] = true;
     }
-    kern<<<grid, G_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, k);
+    launch_pdl(kern, grid, G_THREADS, smem, st, mAh, mAl, mBh, mBl, k);
   };
   switch (epi) {
     case 1: launch(gemm_tc_kernel<1>); break;

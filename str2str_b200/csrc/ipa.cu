@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
                                                          const float* __restrict__ trans, float* __restrict__ q_pts,
                                                          float* __restrict__ k_pts, float* __restrict__ v_pts,
                                                          int rows, IpaPointsAug aug) {
+  pdl_sync();
   __shared__ float k2_s[N_H * P_Q];
   const int r = blockIdx.x;
   const int tid = threadIdx.x;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) ipa_points_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) ipa_point_logits_kernel(float* __restrict__ S, const float* __restrict__ q_pts,
                                                                const float* __restrict__ k_pts,
                                                                const float* __restrict__ pt_w, int L) {
+  pdl_sync();
   __shared__ __align__(16) float qs[32][P_Q * 3];
   const int bh = blockIdx.z, b = bh / N_H, h = bh % N_H;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 64;
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(256) ipa_point_logits_kernel(float* __restrict
 constexpr int ZP = C_Z + 8;  // padded bf16 row pitch (272 B): conflict-free ldmatrix
 
 __global__ void __launch_bounds__(256) ipa_pair_attention_kernel(IpaPairArgs a) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int L = a.L, Lp = (L + 15) & ~15;
   const int LP4 = Lp + 4, LP8 = Lp + 8;
@@ -305,6 +308,7 @@ __global__ void __launch_bounds__(96) ipa_finalize_points_kernel(const float* __
                                                                   const float* __restrict__ trans,
                                                                   float* __restrict__ feats, int rows,
                                                                   bf16* __restrict__ f_hi, bf16* __restrict__ f_lo) {
+  pdl_sync();
   const int r = blockIdx.x, k = threadIdx.x;  // k = h*12 + p
   if (r >= rows) return;
   float q[4] = {quat[r * 4], quat[r * 4 + 1], quat[r * 4 + 2], quat[r * 4 + 3]};
@@ -346,7 +350,7 @@ void ipa_points(const float* qp_raw, long ld_q, const float* kvp_raw, long ld_kv
                 const IpaPointsAug& aug) {
   S2S_PROF("ipa_points", st);
   S2S_CHECK(!aug.qp_aug || (aug.kp_aug && aug.colbias && aug.vp_hi && aug.vp_lo && aug.pt_w && aug.L > 0), "ipa_points: incomplete operand set");
-  ipa_points_kernel<<<rows, 256, 0, st>>>(qp_raw, ld_q, kvp_raw, ld_kv, quat, trans, q_pts, k_pts, v_pts, rows, aug);
+  launch_pdl(ipa_points_kernel, rows, 256, 0, st, qp_raw, ld_q, kvp_raw, ld_kv, quat, trans, q_pts, k_pts, v_pts, rows, aug);
   S2S_LAUNCH_CHECK();
 
 }
@@ -355,7 +359,7 @@ void ipa_point_logits(float* S, const float* q_pts, const float* k_pts, const fl
                       cudaStream_t st) {
   S2S_PROF("ipa_point_logits", st);
   dim3 grid(ceil_div(L, 64), ceil_div(L, 32), B * N_H);
-  ipa_point_logits_kernel<<<grid, 256, 0, st>>>(S, q_pts, k_pts, pt_w, L);
+  launch_pdl(ipa_point_logits_kernel, grid, 256, 0, st, S, q_pts, k_pts, pt_w, L);
   S2S_LAUNCH_CHECK();
 }
 
@@ -369,14 +373,14 @@ void ipa_pair_attention(const IpaPairArgs& a, cudaStream_t st) {
     configured = smem;
   }
   S2S_PROF("ipa_pair_attention", st);
-  ipa_pair_attention_kernel<<<a.B * a.L, 256, smem, st>>>(a);
+  launch_pdl(ipa_pair_attention_kernel, a.B * a.L, 256, smem, st, a);
   S2S_LAUNCH_CHECK();
 }
 
 void ipa_finalize_points(const float* opt_glob, const float* quat, const float* trans, float* feats, int rows,
                          cudaStream_t st, bf16* f_hi, bf16* f_lo) {
   S2S_PROF("ipa_finalize_points", st);
-  ipa_finalize_points_kernel<<<rows, 96, 0, st>>>(opt_glob, quat, trans, feats, rows, f_hi, f_lo);
+  launch_pdl(ipa_finalize_points_kernel, rows, 96, 0, st, opt_glob, quat, trans, feats, rows, f_hi, f_lo);
   S2S_LAUNCH_CHECK();
 }
 

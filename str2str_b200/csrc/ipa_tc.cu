@@ -109,6 +109,7 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // only weights (constant during an iteration) were read so far
   const int n_local = a.n_slabs > (int)blockIdx.x ? (a.n_slabs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 8) {
@@ -383,6 +384,7 @@ ipa_pair_tc_long_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // only weights (constant during an iteration) were read so far
   const int n_local = a.n_slabs > (int)blockIdx.x ? (a.n_slabs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   constexpr uint32_t BLK = TILE_BYTES >> 4;
 
@@ -635,7 +637,7 @@ void launch_pair_tc(const IpaPairArgs& a, const CUtensorMap& mz, const P2Args& k
     configured = true;
   }
   const int cap = sm_count() * (NKB == 1 ? 2 : 1);
-  ipa_pair_tc_kernel<NKB><<<k.n_slabs < cap ? k.n_slabs : cap, P2_THREADS, smem, st>>>(mz, k);
+  launch_pdl(ipa_pair_tc_kernel<NKB>, k.n_slabs < cap ? k.n_slabs : cap, P2_THREADS, smem, st, mz, k);
   S2S_LAUNCH_CHECK();
 }
 
@@ -648,7 +650,7 @@ void launch_pair_tc_long(const CUtensorMap& mz, const P2Args& k, cudaStream_t st
     S2S_CUDA(cudaFuncSetAttribute(ipa_pair_tc_long_kernel<NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  ipa_pair_tc_long_kernel<NKB><<<k.n_slabs < sm_count() ? k.n_slabs : sm_count(), PL_THREADS, smem, st>>>(mz, k);
+  launch_pdl(ipa_pair_tc_long_kernel<NKB>, k.n_slabs < sm_count() ? k.n_slabs : sm_count(), PL_THREADS, smem, st, mz, k);
   S2S_LAUNCH_CHECK();
 }
 

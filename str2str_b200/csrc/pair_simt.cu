@@ -72,6 +72,7 @@ __device__ __forceinline__ void ln_store_rows(const float* __restrict__ y_s, con
 
 // ---- edge embedder ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) edge_embed_simt_kernel(EdgeEmbedArgs a) {
+  pdl_sync();
   extern __shared__ float smem[];
   float* h0T = smem;                 // [128][RT]
   float* h1T = smem + C_Z * RT;      // [128][RT]
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(128) edge_embed_simt_kernel(EdgeEmbedArgs a) {
 
 // ---- EdgeTransition -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(D_ET) edge_transition_simt_kernel(EdgeTransitionArgs a) {
+  pdl_sync();
   extern __shared__ float smem[];
   float* xT = smem;                          // [128][RT]   z rows (bf16 values)
   float* h1T = xT + C_Z * RT;                // [384][RT]
@@ -181,7 +183,7 @@ void edge_embed_simt(const EdgeEmbedArgs& a, cudaStream_t st) {
   const long rows = (long)a.B * a.L * a.L;
   const size_t smem = 2 * C_Z * RT * sizeof(float);
   S2S_PROF("edge_embed_simt", st);
-  edge_embed_simt_kernel<<<ceil_div(rows, RT), 128, smem, st>>>(a);
+  launch_pdl(edge_embed_simt_kernel, ceil_div(rows, RT), 128, smem, st, a);
   S2S_LAUNCH_CHECK();
 }
 
@@ -194,7 +196,7 @@ void edge_transition_simt(const EdgeTransitionArgs& a, cudaStream_t st) {
     configured = true;
   }
   S2S_PROF("edge_transition_simt", st);
-  edge_transition_simt_kernel<<<ceil_div(rows, RT), D_ET, smem, st>>>(a);
+  launch_pdl(edge_transition_simt_kernel, ceil_div(rows, RT), D_ET, smem, st, a);
   S2S_LAUNCH_CHECK();
 }
 

@@ -143,6 +143,7 @@ edge_transition_tc3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __g
   if constexpr (MC) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // only weights (constant during an iteration) were read so far
   const int tiles_per_i = FLAT ? 1 : a.L / TM;  // FLAT tiles are addressed by flattened row, not by (decoy, i)
   constexpr uint32_t IDESC128 = make_idesc(128, 128), IDESC64 = make_idesc(128, 64);
   const uint32_t crank = MC ? cluster_ctarank() : 0u;
@@ -539,7 +540,7 @@ void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st) {
     grid &= ~1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ET3_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
@@ -551,12 +552,15 @@ void edge_transition_tc3(const EdgeTransitionArgs& a, cudaStream_t st) {
     }
     if (grid > 2 * max_clusters) grid = 2 * max_clusters;
     cfg.gridDim = dim3(grid);
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see launch_pdl (common.cuh)
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = g_pdl ? 2 : 1;
     if (flat) S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_tc3_kernel<true, true>, mz, mn, k));
     else S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_tc3_kernel<true, false>, mz, mn, k));
   } else if (flat) {
-    edge_transition_tc3_kernel<false, true><<<grid, ET3_THREADS, smem, st>>>(mz, mn, k);
+    launch_pdl(edge_transition_tc3_kernel<false, true>, grid, ET3_THREADS, smem, st, mz, mn, k);
   } else {
-    edge_transition_tc3_kernel<false, false><<<grid, ET3_THREADS, smem, st>>>(mz, mn, k);
+    launch_pdl(edge_transition_tc3_kernel<false, false>, grid, ET3_THREADS, smem, st, mz, mn, k);
   }
   S2S_LAUNCH_CHECK();
 }

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // only weights (constant during an iteration) were read so far
   const int tiles_per_i = (FLAT || TABLE) ? 1 : e.L / TM;
   const int rpb = tab_rows_per_block(e.n_off), tiles_per_blk = rpb / TM;  // table mode: rows / tiles per (decoy, variant) block
   const int* const blk_list = a.ctl + 4;
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) edge_embed_pipe_kernel(EePipeArg
 __global__ void __launch_bounds__(256) embed_table_setup_kernel(int B, int L, const float* __restrict__ fixed, const float* __restrict__ mask,
                                                                 unsigned char* __restrict__ cls, int* __restrict__ ctl, int* __restrict__ sync_ws,
                                                                 int variants) {
+  pdl_sync();
   __shared__ int rep1_s, bad_s, last_s;
   const int b = blockIdx.x;
   int* const rep = ctl + 4 + 4 * B;
@@ -470,6 +472,7 @@ __global__ void __launch_bounds__(256) embed_table_setup_kernel(int B, int L, co
 // row), all sixteen 16-byte loads of a lane in flight at once.  Reads come from L2 (a decoy's table is ~3 MB), writes are the
 // 1 GB of z: the kernel is bound by the HBM write.
 __global__ void __launch_bounds__(256) edge_embed_expand_kernel(EePipeArgs a, long n_rows) {
+  pdl_sync();
   const EdgeEmbedArgs& e = a.e;
   if (a.ctl[1]) return;  // table not applicable: the direct kernel runs instead
   __shared__ float edge_s[N_BINS];
@@ -529,18 +532,18 @@ void edge_embed_tc2(const EdgeEmbedArgs& a, cudaStream_t st) {
   if (a.table_variants > 0) {
     S2S_CHECK(a.table && a.tab_ctl && a.cls, "edge_embed_tc2: table buffers missing");
     k.ctl = a.tab_ctl;
-    embed_table_setup_kernel<<<a.B, 256, 0, st>>>(a.B, a.L, a.fixed, a.mask, a.cls, a.tab_ctl, a.tab_ctl + 2, a.table_variants);
+    launch_pdl(embed_table_setup_kernel, a.B, 256, 0, st, a.B, a.L, a.fixed, a.mask, a.cls, a.tab_ctl, a.tab_ctl + 2, a.table_variants);
     S2S_LAUNCH_CHECK();
     const int max_tiles = a.B * a.table_variants * (tab_rows_per_block(a.n_off) / TM);
-    edge_embed_pipe_kernel<2><<<max_tiles < cap ? max_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
+    launch_pdl(edge_embed_pipe_kernel<2>, max_tiles < cap ? max_tiles : cap, P_THREADS, P_SMEM, st, k);
     S2S_LAUNCH_CHECK();
     const long n_rows = (long)a.B * a.L * a.L;
-    edge_embed_expand_kernel<<<cap * 8, 256, 0, st>>>(k, n_rows);
+    launch_pdl(edge_embed_expand_kernel, cap * 8, 256, 0, st, k, n_rows);
     S2S_LAUNCH_CHECK();
     k.only_if_flag = 1;  // the direct kernel below runs only if the setup kernel found inputs the table cannot represent
   }
-  if (flat) edge_embed_pipe_kernel<1><<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
-  else edge_embed_pipe_kernel<0><<<k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st>>>(k);
+  if (flat) launch_pdl(edge_embed_pipe_kernel<1>, k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st, k);
+  else launch_pdl(edge_embed_pipe_kernel<0>, k.n_tiles < cap ? k.n_tiles : cap, P_THREADS, P_SMEM, st, k);
   S2S_LAUNCH_CHECK();
 }
 

@@ -196,6 +196,7 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
   cluster_sync_all();                          // tensor memory is allocated in both CTAs before any MMA of the pair can target it
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // only weights (constant during an iteration) were read so far
   const int tiles_per_i = FLAT ? 1 : a.L / TM;
   constexpr uint32_t IDESC256 = make_idesc(256, 128);  // M = 256 across the pair, N = 128
   // this CTA's tiles: pair p of the grid takes tiles 2p, 2p+1, then strides by the number of pairs
@@ -503,7 +504,7 @@ void edge_transition_pair(const EdgeTransitionArgs& a, cudaStream_t st) {
   grid &= ~1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ET5_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
@@ -515,6 +516,9 @@ void edge_transition_pair(const EdgeTransitionArgs& a, cudaStream_t st) {
   }
   if (grid > 2 * max_clusters) grid = 2 * max_clusters;
   cfg.gridDim = dim3(grid);
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see launch_pdl (common.cuh)
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   if (flat) S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_pair_kernel<true>, mz, mn, mw, k));
   else S2S_CUDA(cudaLaunchKernelEx(&cfg, edge_transition_pair_kernel<false>, mz, mn, mw, k));
   S2S_LAUNCH_CHECK();

@@ -140,6 +140,7 @@ __device__ float igso3_score_scale(float omega, float sigma) {
 // ---- frame update (rigid_utils.py:1042-1066, 590-619) -------------------------------------------------
 __global__ void frame_update_kernel(float* __restrict__ quat, float* __restrict__ trans,
                                     const float* __restrict__ upd, const float* __restrict__ diffuse, int rows) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float q[4] = {quat[r * 4], quat[r * 4 + 1], quat[r * 4 + 2], quat[r * 4 + 3]};
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(256) bb_update_frame_kernel(const float* __res
                                                               const float* __restrict__ bias, float* __restrict__ quat,
                                                               float* __restrict__ trans, const float* __restrict__ diffuse,
                                                               int rows) {
+  pdl_sync();
   const int lane = threadIdx.x % 32;
   const int r = blockIdx.x * 8 + threadIdx.x / 32;
   if (r >= rows) return;
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(256) bb_update_frame_kernel(const float* __res
 
 __global__ void split_rigids_kernel(const float* __restrict__ rig, float* __restrict__ quat,
                                     float* __restrict__ trans, int rows) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
 #pragma unroll
@@ -222,6 +225,7 @@ __global__ void split_rigids_kernel(const float* __restrict__ rig, float* __rest
 }
 __global__ void join_rigids_kernel(const float* __restrict__ quat, const float* __restrict__ trans,
                                    float* __restrict__ rig, int rows) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
 #pragma unroll
@@ -232,6 +236,7 @@ __global__ void join_rigids_kernel(const float* __restrict__ quat, const float* 
 
 // ---- score + reverse (frame.py:109-210, so3.py:274-371, r3.py:79-137) ---------------------------------
 __global__ void __launch_bounds__(256) se3_step_kernel(Se3StepArgs a) {
+  pdl_sync();
   extern __shared__ double xs[];  // [L][3] un-centred new translations (nm)
   __shared__ double red[3][8];
   const int b = blockIdx.x, L = a.L, tid = threadIdx.x;
@@ -354,6 +359,7 @@ __global__ void __launch_bounds__(256) se3_step_kernel(Se3StepArgs a) {
 
 // ---- forward perturbation (frame.py:36-107, so3.py:244-272,315-331, r3.py:49-74) ----------------------
 __global__ void se3_perturb_kernel(Se3PerturbArgs a) {
+  pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.B * a.L) return;
   const int b = idx / a.L;
@@ -410,6 +416,7 @@ __global__ void se3_perturb_kernel(Se3PerturbArgs a) {
 __global__ void backbone_atoms_kernel(const float* __restrict__ rig, const float* __restrict__ psi,
                                       const long long* __restrict__ aatype, const float* __restrict__ table,
                                       float* __restrict__ atom37, float* __restrict__ atom14, int rows) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int aa = aatype ? (int)aatype[r] : 0;
@@ -461,21 +468,21 @@ __global__ void backbone_atoms_kernel(const float* __restrict__ rig, const float
 }  // namespace
 
 void frame_update(float* quat, float* trans, const float* upd6, const float* diffuse, int rows, cudaStream_t st) {
-  frame_update_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(quat, trans, upd6, diffuse, rows);
+  launch_pdl(frame_update_kernel, ceil_div(rows, 128), 128, 0, st, quat, trans, upd6, diffuse, rows);
   S2S_LAUNCH_CHECK();
 }
 void bb_update_frame(const float* node, const float* W, const float* bias, float* quat, float* trans, const float* diffuse,
                      int rows, cudaStream_t st) {
   S2S_PROF("bb_update_frame", st);
-  bb_update_frame_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(node, W, bias, quat, trans, diffuse, rows);
+  launch_pdl(bb_update_frame_kernel, ceil_div(rows, 8), 256, 0, st, node, W, bias, quat, trans, diffuse, rows);
   S2S_LAUNCH_CHECK();
 }
 void split_rigids(const float* rig7, float* quat, float* trans_nm, int rows, cudaStream_t st) {
-  split_rigids_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(rig7, quat, trans_nm, rows);
+  launch_pdl(split_rigids_kernel, ceil_div(rows, 128), 128, 0, st, rig7, quat, trans_nm, rows);
   S2S_LAUNCH_CHECK();
 }
 void join_rigids(const float* quat, const float* trans_nm, float* rig7, int rows, cudaStream_t st) {
-  join_rigids_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(quat, trans_nm, rig7, rows);
+  launch_pdl(join_rigids_kernel, ceil_div(rows, 128), 128, 0, st, quat, trans_nm, rig7, rows);
   S2S_LAUNCH_CHECK();
 }
 void se3_step(const Se3StepArgs& a, cudaStream_t st) {
@@ -483,16 +490,16 @@ void se3_step(const Se3StepArgs& a, cudaStream_t st) {
   S2S_CHECK(a.probability_flow || (a.rot_noise && a.trans_noise) || a.mode == 1, "se3_step: SDE mode needs noise");
   const size_t smem = (size_t)a.L * 3 * sizeof(double);
   S2S_CHECK(smem <= 48 * 1024, "se3_step: chain too long (L <= 2048)");
-  se3_step_kernel<<<a.B, 256, smem, st>>>(a);
+  launch_pdl(se3_step_kernel, a.B, 256, smem, st, a);
   S2S_LAUNCH_CHECK();
 }
 void se3_perturb(const Se3PerturbArgs& a, cudaStream_t st) {
-  se3_perturb_kernel<<<ceil_div((long)a.B * a.L, 128), 128, 0, st>>>(a);
+  launch_pdl(se3_perturb_kernel, ceil_div((long)a.B * a.L, 128), 128, 0, st, a);
   S2S_LAUNCH_CHECK();
 }
 void backbone_atoms(const float* rig7, const float* psi, const long long* aatype, const float* table,
                     float* atom37, float* atom14, int rows, cudaStream_t st) {
-  backbone_atoms_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(rig7, psi, aatype, table, atom37, atom14, rows);
+  launch_pdl(backbone_atoms_kernel, ceil_div(rows, 128), 128, 0, st, rig7, psi, aatype, table, atom37, atom14, rows);
   S2S_LAUNCH_CHECK();
 }
 

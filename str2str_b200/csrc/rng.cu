@@ -18,6 +18,7 @@ namespace {
 __global__ void philox_fill_kernel(float* __restrict__ out, int B, long n_per_decoy, unsigned long long seed, long long first_decoy,
                                    unsigned long long stream_id, int uniform, const long long* __restrict__ decoy_ids,
                                    const int* __restrict__ stream_ids) {
+  pdl_sync();
   const long quads = (n_per_decoy + 3) / 4;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * quads) return;
@@ -49,7 +50,7 @@ void philox_fill(float* out, int B, long n_per_decoy, unsigned long long seed, l
                  int uniform, cudaStream_t st, const long long* decoy_ids, const int* stream_ids) {
   S2S_CHECK(n_per_decoy > 0 && n_per_decoy < (1l << 24), "philox_fill: at most 2^24 - 1 elements per decoy and draw");
   const long quads = (n_per_decoy + 3) / 4;
-  philox_fill_kernel<<<ceil_div((long)B * quads, 256), 256, 0, st>>>(out, B, n_per_decoy, seed, first_decoy, stream_id, uniform, decoy_ids,
+  launch_pdl(philox_fill_kernel, ceil_div((long)B * quads, 256), 256, 0, st, out, B, n_per_decoy, seed, first_decoy, stream_id, uniform, decoy_ids,
                                                                      stream_ids);
   S2S_LAUNCH_CHECK();
 }

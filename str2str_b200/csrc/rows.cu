@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         const float* __restrict__ rowscale, float* __restrict__ y,
                                                         int rows, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo) {
+  pdl_sync();
   // one warp per row; a lane owns groups of 4 consecutive channels (16-byte loads and stores, 8-byte bf16 image stores)
   constexpr int G4 = D / 4, PER = (G4 + 31) / 32;
   const int row = blockIdx.x * 8 + threadIdx.x / 32;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) softmax_keybias_kernel(float* __restrict__ S, const float* __restrict__ keybias,
                                                               int L, int rows_per_batch, long rows,
                                                               bf16* __restrict__ P_hi, bf16* __restrict__ P_lo) {
+  pdl_sync();
   const long row = (long)blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -139,6 +141,7 @@ __global__ void node_features_kernel(const float* __restrict__ t, const long lon
                                      const float* __restrict__ fixed, const float* __restrict__ tfreq,
                                      const float* __restrict__ pdenom, float* __restrict__ feat,
                                      float* __restrict__ tf, int B, int L) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B * L) return;
   const int b = r / L;
@@ -181,6 +184,7 @@ __global__ void relpos_features_kernel(const float* __restrict__ pdenom, float* 
 // (layers.py:205-213, denoising_ipa.py:192-194)
 __global__ void psi_finalize_kernel(const float* __restrict__ u, const float* __restrict__ gt_psi,
                                     const float* __restrict__ fixed, float* __restrict__ psi, int rows) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const float a = u[2 * r], b = u[2 * r + 1];
@@ -198,6 +202,7 @@ __global__ void psi_finalize_kernel(const float* __restrict__ u, const float* __
 __global__ void concat_skip_kernel(const float* __restrict__ node, const float* __restrict__ skip,
                                    float* __restrict__ out, long rows, bf16* __restrict__ out_hi,
                                    bf16* __restrict__ out_lo) {
+  pdl_sync();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * D_TFM) return;
   const long r = i / D_TFM;
@@ -213,6 +218,7 @@ __global__ void concat_skip_kernel(const float* __restrict__ node, const float* 
 
 __global__ void masks_kernel(const float* __restrict__ rmask, const float* __restrict__ fixed, const float* __restrict__ hard,
                              float* __restrict__ diffuse, float* __restrict__ keybias, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   diffuse[i] = (1.f - fixed[i]) * rmask[i];
@@ -231,6 +237,7 @@ __global__ void pad_inputs_kernel(int B, int L, int Lp, const float* __restrict_
                                   const float* __restrict__ fixed, const float* __restrict__ psi, float* __restrict__ o_rig,
                                   float* __restrict__ o_sc, long long* __restrict__ o_ridx, float* __restrict__ o_rmask,
                                   float* __restrict__ o_fixed, float* __restrict__ o_psi, float* __restrict__ o_hard) {
+  pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * Lp) return;
   const int b = idx / Lp, j = idx - b * Lp;
@@ -257,6 +264,7 @@ __global__ void pad_inputs_kernel(int B, int L, int Lp, const float* __restrict_
 // dst [B][Ld][W] <- src [B][Ls][W]: rows j < min(Ls, Ld) are copied, rows beyond Ls are filled with zeros
 template <typename T>
 __global__ void repitch_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int Ls, int Ld, int W) {
+  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * Ld * W) return;
   const int w = (int)(idx % W);
@@ -267,6 +275,7 @@ __global__ void repitch_rows_kernel(const T* __restrict__ src, T* __restrict__ d
 
 // pair tensor dst [B][Ld][Ld][128] <- src [B][Ls][Ls][128] (bf16, 16-byte pieces), zero outside the source square
 __global__ void repitch_pair_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int Ls, int Ld) {
+  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte piece: 16 per pair row
   if (idx >= (long)B * Ld * Ld * 16) return;
   const int piece = (int)(idx & 15);
@@ -284,11 +293,11 @@ void layernorm(const float* x, const float* res, const float* w, const float* b,
   S2S_PROF("layernorm", st);
   const int grid = ceil_div(rows, 8);
   if (D == 128)
-    layernorm_kernel<128><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows, y_hi, y_lo);
+    launch_pdl(layernorm_kernel<128>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo);
   else if (D == 256)
-    layernorm_kernel<256><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows, y_hi, y_lo);
+    launch_pdl(layernorm_kernel<256>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo);
   else if (D == 320)
-    layernorm_kernel<320><<<grid, 256, 0, st>>>(x, res, w, b, rowscale, y, rows, y_hi, y_lo);
+    launch_pdl(layernorm_kernel<320>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo);
   else
     S2S_CHECK(false, "layernorm: unsupported width");
   S2S_LAUNCH_CHECK();
@@ -297,13 +306,13 @@ void layernorm(const float* x, const float* res, const float* w, const float* b,
 void softmax_keybias(float* S, const float* keybias, int nb, int nh, int L, cudaStream_t st, bf16* P_hi, bf16* P_lo) {
   const long rows = (long)nb * nh * L;
   S2S_PROF("softmax", st);
-  softmax_keybias_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(S, keybias, L, nh * L, rows, P_hi, P_lo);
+  launch_pdl(softmax_keybias_kernel, ceil_div(rows, 8), 256, 0, st, S, keybias, L, nh * L, rows, P_hi, P_lo);
   S2S_LAUNCH_CHECK();
 }
 
 void node_features(const float* t, const long long* ridx, const float* fixed, const float* tfreq,
                    const float* pdenom, float* feat, float* tf, int B, int L, cudaStream_t st) {
-  node_features_kernel<<<ceil_div((long)B * L, 128), 128, 0, st>>>(t, ridx, fixed, tfreq, pdenom, feat, tf, B, L);
+  launch_pdl(node_features_kernel, ceil_div((long)B * L, 128), 128, 0, st, t, ridx, fixed, tfreq, pdenom, feat, tf, B, L);
   S2S_LAUNCH_CHECK();
 }
 
@@ -313,32 +322,32 @@ void relpos_features(const float* pdenom, float* out, int d_min, int n, cudaStre
 }
 
 void psi_finalize(const float* u, const float* gt_psi, const float* fixed, float* psi, int rows, cudaStream_t st) {
-  psi_finalize_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(u, gt_psi, fixed, psi, rows);
+  launch_pdl(psi_finalize_kernel, ceil_div(rows, 128), 128, 0, st, u, gt_psi, fixed, psi, rows);
   S2S_LAUNCH_CHECK();
 }
 
 void concat_skip(const float* node, const float* skip, float* out, long rows, cudaStream_t st, bf16* out_hi, bf16* out_lo) {
   S2S_PROF("concat_skip", st);
-  concat_skip_kernel<<<ceil_div(rows * D_TFM, 256), 256, 0, st>>>(node, skip, out, rows, out_hi, out_lo);
+  launch_pdl(concat_skip_kernel, ceil_div(rows * D_TFM, 256), 256, 0, st, node, skip, out, rows, out_hi, out_lo);
   S2S_LAUNCH_CHECK();
 }
 
 void make_masks(const float* rmask, const float* fixed, const float* hard, float* diffuse, float* keybias, int n, cudaStream_t st) {
-  masks_kernel<<<ceil_div(n, 256), 256, 0, st>>>(rmask, fixed, hard, diffuse, keybias, n);
+  launch_pdl(masks_kernel, ceil_div(n, 256), 256, 0, st, rmask, fixed, hard, diffuse, keybias, n);
   S2S_LAUNCH_CHECK();
 }
 
 void pad_inputs(const PadInputs& a, cudaStream_t st) {
-  pad_inputs_kernel<<<ceil_div((long)a.B * a.Lp, 128), 128, 0, st>>>(a.B, a.L, a.Lp, a.rig, a.sc, a.ridx, a.rmask, a.fixed, a.psi, a.o_rig,
+  launch_pdl(pad_inputs_kernel, ceil_div((long)a.B * a.Lp, 128), 128, 0, st, a.B, a.L, a.Lp, a.rig, a.sc, a.ridx, a.rmask, a.fixed, a.psi, a.o_rig,
                                                                      a.o_sc, a.o_ridx, a.o_rmask, a.o_fixed, a.o_psi, a.o_hard);
   S2S_LAUNCH_CHECK();
 }
 void repitch_rows(const float* src, float* dst, int B, int Ls, int Ld, int W, cudaStream_t st) {
-  repitch_rows_kernel<float><<<ceil_div((long)B * Ld * W, 256), 256, 0, st>>>(src, dst, B, Ls, Ld, W);
+  launch_pdl(repitch_rows_kernel<float>, ceil_div((long)B * Ld * W, 256), 256, 0, st, src, dst, B, Ls, Ld, W);
   S2S_LAUNCH_CHECK();
 }
 void repitch_pair(const bf16* src, bf16* dst, int B, int Ls, int Ld, cudaStream_t st) {
-  repitch_pair_kernel<<<ceil_div((long)B * Ld * Ld * 16, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), B, Ls, Ld);
+  launch_pdl(repitch_pair_kernel, ceil_div((long)B * Ld * Ld * 16, 256), 256, 0, st, reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), B, Ls, Ld);
   S2S_LAUNCH_CHECK();
 }
 

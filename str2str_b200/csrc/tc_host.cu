@@ -16,6 +16,7 @@ __global__ void build_wtile_kernel(const float* __restrict__ src, int ld, int n0
   *reinterpret_cast<bf16*>(dst + sw128_offset(r, c)) = __float2bfloat16_rn(src[(size_t)(n0 + r) * ld + k0 + c]);
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+  pdl_sync();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
@@ -74,7 +75,7 @@ void build_ee_wimg(const float* W2, const float* W3, bf16* dst, cudaStream_t st)
     }
 }
 void f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t st) {
-  f32_to_bf16_kernel<<<ceil_div(n, 256), 256, 0, st>>>(src, dst, n);
+  launch_pdl(f32_to_bf16_kernel, ceil_div(n, 256), 256, 0, st, src, dst, n);
   S2S_LAUNCH_CHECK();
 }
 

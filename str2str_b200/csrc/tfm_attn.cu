@@ -89,6 +89,7 @@ tfm_attention_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_co
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
+  pdl_sync();
   if (threadIdx.x < 256) kb_s[threadIdx.x] = threadIdx.x < L ? a.keybias[row0 + threadIdx.x] * 1.4426950408889634f : 0.f;  // log2 e folded in
   tc_fence_before();
   __syncthreads();
@@ -241,7 +242,7 @@ void tfm_attention(const bf16* qkv, const float* keybias, float* y, bf16* y_hi, 
     configured = true;
   }
   S2S_PROF("tfm_attention", st);
-  tfm_attention_kernel<<<B * TFM_H * k.MT, TA_THREADS, TA_SMEM, st>>>(mqk, mv, k);
+  launch_pdl(tfm_attention_kernel, B * TFM_H * k.MT, TA_THREADS, TA_SMEM, st, mqk, mv, k);
   S2S_LAUNCH_CHECK();
 }
 
