@@ -53,7 +53,12 @@ int s2s_finalize(s2s_ctx* ctx, void* stream);
  *                         0 = one CTA per row tile (A/B, tests);
  *          "embed_table"  1 = the edge embedder builds each decoy's (fixed_i, fixed_j, index offset, distogram bin) -> embedding
  *                         table and expands it into the pair tensor whenever that table is well below L^2 rows (default; same
- *                         values bit for bit), 0 = always run the MLP on every pair row (A/B, tests). */
+ *                         values bit for bit), 0 = always run the MLP on every pair row (A/B, tests);
+ *          "chain"        the row-local layers of the node track between two attention kernels (sequence-transformer out_proj /
+ *                         norm1 / linear1 / linear2 / norm2, the next in_proj or the post-transformer linear, NodeTransition,
+ *                         the per-residue terms of the EdgeTransition, the torsion head) as ONE launch each (gemm_chain.cu,
+ *                         LayerNorm as a step epilogue; 162 -> 88 launches per forward, same values bit for bit):
+ *                         1 = from 8192 residue rows up (default: below that separate launches are faster), 2 = always, 0 = never. */
 int s2s_set_option(s2s_ctx* ctx, const char* key, int value);
 /* Size the workspace for (B, L) and build the relative-position table for residue-index offsets in
  * [d_min, d_max] (= min/max of residue_idx[i] - residue_idx[j]); d_max < d_min keeps the table already planned

@@ -117,6 +117,7 @@ struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
   int opt_pair = 1, opt_node = 1, opt_ipa = 1, opt_table = 1, opt_et_pair = 1;
+  int opt_chain = 1;  // row-local layers of the node track fused into gemm_chain launches: 0 never, 1 from 8192 rows up, 2 always (do_trunk)
   int tfm_passes = 1;  // sequence-transformer in_proj + attention GEMMs: 1 = single bf16 (default; trajectory error unchanged, tools/traj_parity.py), 3 = split-bf16 (S2S_TFM_PASSES=3)
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
@@ -139,6 +140,8 @@ struct s2s_ctx {
   int* ee_ctl = nullptr;
   unsigned char* ee_cls = nullptr;
   float *feat65, *tf33, *node, *init_node, *a256, *b256, *proj, *feats, *q_pts, *k_pts, *v_pts, *S, *opt;
+  float *skip_w_all = nullptr, *skip_b_all = nullptr;  // the four skip_embed layers stacked: [4 * 64][256], [4 * 64]
+  float* skip_all = nullptr;                            // [R][4 * 64]: skip_embed_b(init_node) of every block, computed once
   float *skip64, *x320, *t320, *y320, *qkv, *nprime, *u384, *v384, *p128, *q128, *Ti, *Tj, *Tpos, *relfeat;
   float *quat, *trans, *upd6, *psi_u, *diffuse, *keybias;
   bf16 *z, *nprime_bf16;
@@ -332,6 +335,14 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
     const char* vn[4] = {"embedder.edge_embed.2.bias", "embedder.edge_embed.4.bias", "embedder.edge_embed.5.weight", "embedder.edge_embed.5.bias"};
     for (int v = 0; v < 4; ++v) S2S_CUDA(cudaMemcpyAsync(c->ee_vec + v * 128, c->P(vn[v]), 128 * 4, cudaMemcpyDeviceToDevice, st));
   }
+  // the skip connections of all four blocks read the same init_node (ipa.py:353-356): one stacked GEMM serves them
+  c->skip_w_all = c->wslab.take<float>(N_BLK * D_SKIP * 256);
+  c->skip_b_all = c->wslab.take<float>(N_BLK * D_SKIP);
+  for (int b = 0; b < N_BLK; ++b) {
+    const std::string sk = t + "skip_embed_" + std::to_string(b);
+    S2S_CUDA(cudaMemcpyAsync(c->skip_w_all + (size_t)b * D_SKIP * 256, c->P(sk + ".weight"), (size_t)D_SKIP * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    S2S_CUDA(cudaMemcpyAsync(c->skip_b_all + b * D_SKIP, c->P(sk + ".bias"), D_SKIP * 4, cudaMemcpyDeviceToDevice, st));
+  }
   // bf16 hi/lo images of every matrix the tensor-core node track multiplies by
   c->wsplit.clear();
   auto reg = [&](const float* W, size_t numel, int cols) {
@@ -354,6 +365,7 @@ void do_finalize(s2s_ctx* c, cudaStream_t st) {
     reg(c->P(n), ps.numel, cols);
   }
   for (int b = 0; b < N_BLK; ++b) reg(c->ipa[b].proj_w, (size_t)6816 * 256, 256);
+  reg(c->skip_w_all, (size_t)N_BLK * D_SKIP * 256, 256);
   // Wfh above holds the full [128][384] final-layer image; only its action on h2 (all 384 inputs) is used:
   // final_layer(h2 + x) = Wf h2 + Wf[:, :128] z + Wf[:,128:256] n_i + Wf[:,256:] n_j.
   c->finalized = true;
@@ -387,6 +399,7 @@ void do_reserve(s2s_ctx* c, int B, int L_user, int d_min, int d_max, cudaStream_
     add(R * 6816, 4); add(R * IPA_FEAT, 4); add(R * 192, 4); add(R * 192, 4); add(R * 288, 4);
     add((size_t)B * N_H * Lc * Lc, 4); add(R * 288, 4);
     add(R * 64, 4); for (int k = 0; k < 3; ++k) add(R * 320, 4); add(R * 960, 4);
+    add(R * N_BLK * D_SKIP, 4);
     add(R * 128, 4); add(R * 384, 4); add(R * 384, 4); add(R * 128, 4); add(R * 128, 4); add(R * 128, 4); add(R * 128, 4);
     add((size_t)cap_off * 128, 4); add((size_t)cap_off * 32, 4);
     add(R * 4, 4); add(R * 3, 4); add(R * 6, 4); add(R * 2, 4); add(R, 4); add(R, 4);
@@ -410,6 +423,7 @@ void do_reserve(s2s_ctx* c, int B, int L_user, int d_min, int d_max, cudaStream_
     c->proj = w.take<float>(R * 6816); c->feats = w.take<float>(R * IPA_FEAT);
     c->q_pts = w.take<float>(R * 192); c->k_pts = w.take<float>(R * 192); c->v_pts = w.take<float>(R * 288);
     c->S = w.take<float>((size_t)B * N_H * Lc * Lc); c->opt = w.take<float>(R * 288);
+    c->skip_all = w.take<float>(R * N_BLK * D_SKIP);
     c->skip64 = w.take<float>(R * 64); c->x320 = w.take<float>(R * 320); c->t320 = w.take<float>(R * 320); c->y320 = w.take<float>(R * 320);
     c->qkv = w.take<float>(R * 960);
     c->nprime = w.take<float>(R * 128); c->u384 = w.take<float>(R * 384); c->v384 = w.take<float>(R * 384);
@@ -600,19 +614,24 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
          IPA_FEAT, st, 0, res, 256, nullptr, row_post, TC3, fused ? Split{c->sa_hi, c->sa_lo} : Split());
 }
 
+// prep_done: the per-residue terms (n' = initial_embed(node) with its bf16 image, u = W1[:,128:256] n' + b1, p = Wf[:,128:256] n' + bf)
+// were already produced by the node-track chain of this block (do_trunk)
 void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z_in, const float* rmask,
-                        bf16* z_out, cudaStream_t st, Split node_sp = Split()) {
+                        bf16* z_out, cudaStream_t st, Split node_sp = Split(), bool prep_done = false) {
   const int R = B * L;
   const std::string e = "translator.trunk.edge_transition_" + std::to_string(blk) + ".";
   const float *W1 = c->P(e + "trunk.0.weight"), *Wf = c->P(e + "final_layer.weight");
   const bool tcn = c->opt_node == 1 && c->cur_prec != EXACT && L % 16 == 0;
   const Split np = tcn ? Split{c->nprime_hi, c->nprime_lo} : Split();
-  linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st, 0,
-         nullptr, 0, nullptr, nullptr, -1, node_sp, np);
   const bool tc = c->opt_pair >= 1;
   S2S_CHECK(!tc || L % 32 == 0, "internal: the tcgen05 EdgeTransition was handed an un-padded chain length");
-  linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
-  linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
+  S2S_CHECK(!prep_done || (tc && np.hi), "internal: chained EdgeTransition terms need the tensor-core paths");
+  if (!prep_done) {
+    linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st, 0,
+           nullptr, 0, nullptr, nullptr, -1, node_sp, np);
+    linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
+    linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
+  }
   if (tc) {  // the n'_j terms ride along as extra K columns of the MMAs: they need n' in bf16 (= the hi image)
     if (!np.hi) f32_to_bf16(c->nprime, c->nprime_bf16, (long)R * 128, st);
   } else {
@@ -631,7 +650,9 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   else edge_transition_tc3(a, st);
 }
 
-void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {
+// self-attention of one sequence-transformer layer on c->x320 -> c->y320 (in_proj, q.k^T, key-biased softmax, P.v);
+// in_proj_done: the in_proj GEMM was the last step of the previous chain launch (c->tq_hi already holds q | k | v)
+void do_tfm_attention(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st, bool in_proj_done = false) {
   const int R = B * L;
   const float scale = 0.11180339887498948f;  // 1/sqrt(80)
   const bool tc = c->opt_node == 1 && L % 16 == 0;
@@ -645,7 +666,7 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     g.B_hi = w.first; g.B_lo = w.second; g.b_rows = 960; g.b_cols = 320; g.b_pitch = 320;
     g.M = R; g.N = 960; g.K = 320; g.passes = 3; g.bias = c->P(tl + "self_attn.in_proj_bias");
     g.out_hi = c->tq_hi; g.out_lo = sp ? c->tq_lo : nullptr; g.ldo = 960;
-    gemm_tc(g, st);
+    if (!in_proj_done) gemm_tc(g, st);
     static const int fused_attn = [] { const char* e = getenv("S2S_TFM_FUSED"); return e ? atoi(e) : 1; }();
     if (fused_attn && !sp && tfm_attention_supported(L)) {
       // q.k^T, key-biased softmax and P.v in one kernel: logits and weights never leave the SM
@@ -682,6 +703,13 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
     h.M = L; h.N = TFM_HD; h.K = L; h.nb = B; h.nh = TFM_H;
     gemm_f32(h, st);
   }
+}
+
+// the row-local rest of the layer (post-norm nn.TransformerEncoderLayer): out_proj + residual + norm1, linear1 + ReLU,
+// linear2 + residual + norm2, one launch per layer / LayerNorm
+void do_tfm_tail(s2s_ctx* c, const std::string& tl, int B, int L, cudaStream_t st) {
+  const int R = B * L;
+  const bool tc = c->opt_node == 1 && L % 16 == 0;
   const Split x_sp = tc ? Split{c->x320_hi, c->x320_lo} : Split();
   const Split t_sp = tc ? Split{c->t320_hi, c->t320_lo} : Split();
   const Split y_sp = tc ? Split{c->y320_hi, c->y320_lo} : Split();
@@ -691,6 +719,32 @@ void do_transformer_layer(s2s_ctx* c, const std::string& tl, int B, int L, cudaS
   linear(c, c->x320, 320, c->P(tl + "linear1.weight"), 320, c->P(tl + "linear1.bias"), c->t320, 320, R, 320, 320, st, 1, nullptr, 0, nullptr, nullptr, -1, x_sp, t_sp);
   linear(c, c->t320, 320, c->P(tl + "linear2.weight"), 320, c->P(tl + "linear2.bias"), c->y320, 320, R, 320, 320, st, 0, c->x320, 320, nullptr, nullptr, -1, t_sp);
   layernorm(c->y320, nullptr, c->P(tl + "norm2.weight"), c->P(tl + "norm2.bias"), nullptr, c->x320, R, 320, st, x_sp.hi, x_sp.lo);
+}
+
+
+// ---- gemm_chain steps (row-local layers fused into one launch; see gemm_chain.cu) ----
+ChainStep chain_step(const s2s_ctx* c, Split in, int K, const float* W, long ldw, const float* bias, int N, int relu = 0,
+                     float* C = nullptr, long ldc = 0, const float* res = nullptr, long ldres = 0, Split out = Split()) {
+  const auto w = weight_split(c, W);
+  ChainStep t;
+  t.A_hi = in.hi; t.A_lo = in.lo; t.W_hi = w.first; t.W_lo = w.second; t.ldw = ldw;
+  t.N = N; t.K = K; t.relu = relu; t.bias = bias; t.res = res; t.ldres = ldres; t.C = C; t.ldc = ldc;
+  t.out_hi = out.hi; t.out_lo = out.lo; t.ldo = N;
+  return t;
+}
+void chain_ln(ChainStep& t, const float* w, const float* b, const float* scale, float* out, Split img) {
+  t.ln_w = w; t.ln_b = b; t.ln_scale = scale; t.ln_out = out; t.ln_hi = img.hi; t.ln_lo = img.lo; t.ld_ln = t.N;
+}
+// do_tfm_tail as chain steps: y320 image -> x320 (+ image)
+void tfm_tail_steps(const s2s_ctx* c, const std::string& tl, std::vector<ChainStep>& v) {
+  const Split x_sp{c->x320_hi, c->x320_lo}, t_sp{c->t320_hi, c->t320_lo}, y_sp{c->y320_hi, c->y320_lo};
+  ChainStep o = chain_step(c, y_sp, 320, c->P(tl + "self_attn.out_proj.weight"), 320, c->P(tl + "self_attn.out_proj.bias"), 320, 0, c->t320, 320, c->x320, 320);
+  chain_ln(o, c->P(tl + "norm1.weight"), c->P(tl + "norm1.bias"), nullptr, c->x320, x_sp);
+  v.push_back(o);
+  v.push_back(chain_step(c, x_sp, 320, c->P(tl + "linear1.weight"), 320, c->P(tl + "linear1.bias"), 320, 1, nullptr, 0, nullptr, 0, t_sp));
+  ChainStep l2 = chain_step(c, t_sp, 320, c->P(tl + "linear2.weight"), 320, c->P(tl + "linear2.bias"), 320, 0, c->y320, 320, c->x320, 320);
+  chain_ln(l2, c->P(tl + "norm2.weight"), c->P(tl + "norm2.bias"), nullptr, c->x320, x_sp);
+  v.push_back(l2);
 }
 
 // TranslationIPA.forward (ipa.py:331-387) on the node / pair embeddings already in c->node / c->z
@@ -703,6 +757,13 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
   // Split-bf16 images of the activations are written by whichever kernel produces them (LayerNorm, GEMM epilogue,
   // concat), so the tensor-core GEMMs that consume them need no separate conversion pass.
   const bool img = c->opt_node == 1 && L % 16 == 0;
+  // chain: the row-local layers between the attention kernels run as gemm_chain launches (same arithmetic, same bits).
+  // Measured on B200 (bench.py, CUDA-graph replay with programmatic dependent launch): 49.27 -> 49.44 and 49.11 -> 49.26
+  // conformations/s at cfg2 (16384 residue rows, 162 -> 88 launches per forward), but 130.4 -> 122.1 at L = 64 x 32 decoys and
+  // 46.7 -> 44.2 at L = 64 x 1: with fewer row panels than SMs a layer is bound by its own load -> stage -> MMA -> epilogue
+  // latency chain, which a step of the chain does not shorten, while separate launches overlap their prologues on idle SMs.
+  // So option "chain" = 1 (default) chains from 8192 rows up, 2 always (tests), 0 never.
+  const bool chain = img && (c->opt_chain == 2 || (c->opt_chain == 1 && R >= 8192));
   auto sp = [&](bf16* hi, bf16* lo) { return img ? Split{hi, lo} : Split(); };
   const Split node_sp = sp(c->node_hi, c->node_lo), init_sp = sp(c->init_hi, c->init_lo), a_sp = sp(c->a256_hi, c->a256_lo),
               b_sp = sp(c->b256_hi, c->b256_lo), x_sp = sp(c->x320_hi, c->x320_lo);
@@ -713,31 +774,78 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
     S2S_CUDA(cudaMemcpyAsync(c->init_lo, c->node_lo, (size_t)R * 256 * 2, cudaMemcpyDeviceToDevice, st));
   }
   split_rigids(rigids_t, c->quat, c->trans, R, st);
+  // every block's skip connection reads the same init_node (ipa.py:353-356): one stacked GEMM for the four of them
+  if (chain) linear(c, c->init_node, 256, c->skip_w_all, 256, c->skip_b_all, c->skip_all, N_BLK * D_SKIP, R, N_BLK * D_SKIP, 256, st, 0, nullptr, 0, nullptr, nullptr, -1, init_sp);
+  const std::string tp = "translator.torsion_pred.";
   for (int b = 0; b < N_BLK; ++b) {
     const std::string s = std::to_string(b);
+    const std::string nt = tk + "node_transition_" + s + ".", t0 = tk + "transformer_" + s + ".layers.0.", t1 = tk + "transformer_" + s + ".layers.1.";
     // node = LN(node + ipa(node, z, T) * mask)          (ipa.py:344-351)
     do_ipa(c, b, B, L, c->node, c->z, c->quat, c->trans, rmask, c->a256, c->node, rmask, st, node_sp);
-    layernorm(c->a256, nullptr, c->P(tk + "ipa_ln_" + s + ".weight"), c->P(tk + "ipa_ln_" + s + ".bias"), nullptr, c->node, R, 256, st);
-    // sequence transformer on [node | skip(init_node)]   (ipa.py:353-360)
-    linear(c, c->init_node, 256, c->P(tk + "skip_embed_" + s + ".weight"), 256, c->P(tk + "skip_embed_" + s + ".bias"), c->skip64, 64, R, 64, 256, st, 0,
-           nullptr, 0, nullptr, nullptr, -1, init_sp);
-    concat_skip(c->node, c->skip64, c->x320, R, st, x_sp.hi, x_sp.lo);
-    for (int l = 0; l < 2; ++l) do_transformer_layer(c, tk + "transformer_" + s + ".layers." + std::to_string(l) + ".", B, L, st);
-    linear(c, c->x320, 320, c->P(tk + "linear_" + s + ".weight"), 320, c->P(tk + "linear_" + s + ".bias"), c->node, 256, R, 256, 320, st, 0, c->node, 256,
-           nullptr, nullptr, -1, x_sp, node_sp);
-    // node transition + mask                              (layers.py:138-145, ipa.py:363-365)
-    const std::string nt = tk + "node_transition_" + s + ".";
-    linear(c, c->node, 256, c->P(nt + "linear_1.weight"), 256, c->P(nt + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, node_sp, a_sp);
-    linear(c, c->a256, 256, c->P(nt + "linear_2.weight"), 256, c->P(nt + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, a_sp, b_sp);
-    linear(c, c->b256, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), c->a256, 256, R, 256, 256, st, 0, c->node, 256, nullptr, nullptr, -1, b_sp);
-    layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, R, 256, st, node_sp.hi, node_sp.lo);
+    if (chain) {
+      // ... and the sequence transformer's input [node | skip(init_node)] (ipa.py:353-356) from the same LayerNorm launch
+      LnExtra ex;
+      ex.ld2 = D_TFM; ex.y2 = c->x320; ex.tail = c->skip_all + b * D_SKIP; ex.tail_ld = N_BLK * D_SKIP; ex.tail_w = D_SKIP;
+      layernorm(c->a256, nullptr, c->P(tk + "ipa_ln_" + s + ".weight"), c->P(tk + "ipa_ln_" + s + ".bias"), nullptr, c->node, R, 256, st, x_sp.hi, x_sp.lo, ex);
+      const bool sp3 = c->tfm_passes == 3;
+      std::vector<ChainStep> v;
+      // layer 0: attention, then its row-local tail and layer 1's in_proj in one launch
+      do_tfm_attention(c, t0, B, L, st);
+      tfm_tail_steps(c, t0, v);
+      v.push_back(chain_step(c, x_sp, 320, c->P(t1 + "self_attn.in_proj_weight"), 320, c->P(t1 + "self_attn.in_proj_bias"), 960, 0, nullptr, 0, nullptr, 0,
+                             Split{c->tq_hi, sp3 ? c->tq_lo : nullptr}));
+      gemm_chain(v.data(), (int)v.size(), R, st);
+      v.clear();
+      // layer 1: attention, then everything up to the next kernel that looks across residues
+      do_tfm_attention(c, t1, B, L, st, true);
+      tfm_tail_steps(c, t1, v);
+      // node += linear(transformer output)                 (ipa.py:359-360)
+      v.push_back(chain_step(c, x_sp, 320, c->P(tk + "linear_" + s + ".weight"), 320, c->P(tk + "linear_" + s + ".bias"), 256, 0, c->node, 256, c->node, 256, node_sp));
+      // node transition + mask                              (layers.py:138-145, ipa.py:363-365)
+      v.push_back(chain_step(c, node_sp, 256, c->P(nt + "linear_1.weight"), 256, c->P(nt + "linear_1.bias"), 256, 1, nullptr, 0, nullptr, 0, a_sp));
+      v.push_back(chain_step(c, a_sp, 256, c->P(nt + "linear_2.weight"), 256, c->P(nt + "linear_2.bias"), 256, 1, nullptr, 0, nullptr, 0, b_sp));
+      ChainStep l3 = chain_step(c, b_sp, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), 256, 0, c->a256, 256, c->node, 256);
+      chain_ln(l3, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, node_sp);
+      v.push_back(l3);
+      if (b < N_BLK - 1 && c->opt_pair >= 1) {
+        // per-residue terms of the EdgeTransition (layers.py:170-176): n' = initial_embed(node), u = W1[:,128:256] n' + b1, p = Wf[:,128:256] n' + bf
+        const std::string e = tk + "edge_transition_" + s + ".";
+        const Split np{c->nprime_hi, c->nprime_lo};
+        v.push_back(chain_step(c, node_sp, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), 128, 0, c->nprime, 128, nullptr, 0, np));
+        v.push_back(chain_step(c, np, 128, c->P(e + "trunk.0.weight") + 128, 384, c->P(e + "trunk.0.bias"), 384, 0, c->u384, 384));
+        v.push_back(chain_step(c, np, 128, c->P(e + "final_layer.weight") + 128, 384, c->P(e + "final_layer.bias"), 128, 0, c->p128, 128));
+      } else if (b == N_BLK - 1) {
+        // torsion head (layers.py:199-213) up to its exact-fp32 last layer
+        v.push_back(chain_step(c, node_sp, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), 256, 1, nullptr, 0, nullptr, 0, a_sp));
+        v.push_back(chain_step(c, a_sp, 256, c->P(tp + "linear_2.weight"), 256, c->P(tp + "linear_2.bias"), 256, 0, c->b256, 256, c->node, 256));
+      }
+      gemm_chain(v.data(), (int)v.size(), R, st);
+    } else {
+      layernorm(c->a256, nullptr, c->P(tk + "ipa_ln_" + s + ".weight"), c->P(tk + "ipa_ln_" + s + ".bias"), nullptr, c->node, R, 256, st);
+      // sequence transformer on [node | skip(init_node)]   (ipa.py:353-360)
+      linear(c, c->init_node, 256, c->P(tk + "skip_embed_" + s + ".weight"), 256, c->P(tk + "skip_embed_" + s + ".bias"), c->skip64, 64, R, 64, 256, st, 0,
+             nullptr, 0, nullptr, nullptr, -1, init_sp);
+      concat_skip(c->node, c->skip64, c->x320, R, st, x_sp.hi, x_sp.lo);
+      do_tfm_attention(c, t0, B, L, st);
+      do_tfm_tail(c, t0, B, L, st);
+      do_tfm_attention(c, t1, B, L, st);
+      do_tfm_tail(c, t1, B, L, st);
+      linear(c, c->x320, 320, c->P(tk + "linear_" + s + ".weight"), 320, c->P(tk + "linear_" + s + ".bias"), c->node, 256, R, 256, 320, st, 0, c->node, 256,
+             nullptr, nullptr, -1, x_sp, node_sp);
+      // node transition + mask                              (layers.py:138-145, ipa.py:363-365)
+      linear(c, c->node, 256, c->P(nt + "linear_1.weight"), 256, c->P(nt + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, node_sp, a_sp);
+      linear(c, c->a256, 256, c->P(nt + "linear_2.weight"), 256, c->P(nt + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, a_sp, b_sp);
+      linear(c, c->b256, 256, c->P(nt + "linear_3.weight"), 256, c->P(nt + "linear_3.bias"), c->a256, 256, R, 256, 256, st, 0, c->node, 256, nullptr, nullptr, -1, b_sp);
+      layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, R, 256, st, node_sp.hi, node_sp.lo);
+    }
     // backbone update on node * diffuse_mask, exact fp32    (ipa.py:367-369)
     bb_update_frame(c->node, c->P(tk + "bb_update_" + s + ".linear.weight"), c->P(tk + "bb_update_" + s + ".linear.bias"), c->quat, c->trans, c->diffuse, R, st);
-    if (b < N_BLK - 1) do_edge_transition(c, b, B, L, c->node, c->z, rmask, c->z, st, node_sp);
+    if (b < N_BLK - 1) do_edge_transition(c, b, B, L, c->node, c->z, rmask, c->z, st, node_sp, chain && c->opt_pair >= 1);
   }
-  const std::string tp = "translator.torsion_pred.";
-  linear(c, c->node, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, node_sp, a_sp);
-  linear(c, c->a256, 256, c->P(tp + "linear_2.weight"), 256, c->P(tp + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 0, c->node, 256, nullptr, nullptr, -1, a_sp);
+  if (!chain) {
+    linear(c, c->node, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, node_sp, a_sp);
+    linear(c, c->a256, 256, c->P(tp + "linear_2.weight"), 256, c->P(tp + "linear_2.bias"), c->b256, 256, R, 256, 256, st, 0, c->node, 256, nullptr, nullptr, -1, a_sp);
+  }
   linear(c, c->b256, 256, c->P(tp + "linear_final.weight"), 256, c->P(tp + "linear_final.bias"), c->psi_u, 2, R, 2, 256, st, 0, nullptr, 0, nullptr, nullptr, EXACT);
   c->cur_prec = EXACT;
   psi_finalize(c->psi_u, gt_psi, fixed, out_psi, R, st);
@@ -824,6 +932,7 @@ s2s_ctx* s2s_create(const float* tfreq, const float* pdenom, const float* bin_lo
     if (const char* e = getenv("S2S_WIMG_COPIES")) c->wimg_copies = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("S2S_TFM_PASSES")) c->tfm_passes = atoi(e) == 3 ? 3 : 1;
     if (const char* e = getenv("S2S_ET_PAIR")) c->opt_et_pair = atoi(e) != 0;
+    if (const char* e = getenv("S2S_CHAIN")) c->opt_chain = std::max(0, std::min(2, atoi(e)));  // A/B timing; s2s_set_option("chain") overrides
     auto up = [&](const float* h, size_t n) {
       float* d;
       S2S_CUDA(cudaMalloc(&d, n * 4));
@@ -863,6 +972,7 @@ int s2s_set_option(s2s_ctx* c, const char* key, int value) {
     else if (k == "node_gemm") { S2S_CHECK(value == 0 || value == 1, "node_gemm: 0|1"); c->opt_node = value; }
     else if (k == "ipa_kernels") { S2S_CHECK(value == 0 || value == 1, "ipa_kernels: 0|1"); c->opt_ipa = value; }
     else if (k == "et_pair") { S2S_CHECK(value == 0 || value == 1, "et_pair: 0|1"); c->opt_et_pair = value; }
+    else if (k == "chain") { S2S_CHECK(value >= 0 && value <= 2, "chain: 0|1|2"); c->opt_chain = value; }
     else if (k == "embed_table") { S2S_CHECK(value == 0 || value == 1, "embed_table: 0|1"); c->opt_table = value; }
     else S2S_CHECK(false, "unknown option " + k);
   });

@@ -1,63 +1,35 @@
 // Row-wise kernels of the node track: LayerNorm(+residual,+mask), key-biased softmax, input features,
 // psi head normalisation.  One warp per row; rows are 128..512 floats so everything stays in registers.
+#include "row_ops.cuh"
 #include "s2s_internal.cuh"
 
 namespace s2s {
 
 namespace {
 
-// y[r] = LN(x[r] (+ res[r])) * w + b, then * rowscale[r]
+// y[r] = LN(x[r] (+ res[r])) * w + b, then * rowscale[r]   (one warp per row: layernorm_rows in row_ops.cuh)
+// y has pitch D; the optional second copy y2 and the split-bf16 image (y_hi, y_lo) share the pitch ld2, and columns
+// [D, D + tail_w) of THOSE rows receive a copy of tail[row][0 .. tail_w) (pitch tail_ld) — the sequence transformer's input
+// cat([node, skip_embed(init_node)]) of ipa.py:353-356 written by the LayerNorm that produces node.
 template <int D>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         const float* __restrict__ rowscale, float* __restrict__ y,
-                                                        int rows, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo) {
+                                                        int rows, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, int ld2,
+                                                        float* __restrict__ y2, const float* __restrict__ tail, int tail_ld, int tail_w) {
   pdl_sync();
-  // one warp per row; a lane owns groups of 4 consecutive channels (16-byte loads and stores, 8-byte bf16 image stores)
-  constexpr int G4 = D / 4, PER = (G4 + 31) / 32;
   const int row = blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
-  float4 v[PER];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int g = lane + 32 * i;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g < G4) {
-      v[i] = *reinterpret_cast<const float4*>(x + (long)row * D + g * 4);
-      if (res) {
-        const float4 r4 = *reinterpret_cast<const float4*>(res + (long)row * D + g * 4);
-        v[i].x += r4.x; v[i].y += r4.y; v[i].z += r4.z; v[i].w += r4.w;
-      }
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-  }
-  const float mean = warp_sum(s) * (1.f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    if (lane + 32 * i < G4) {
-      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
-      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
-  const float sc = rowscale ? rowscale[row] : 1.f;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int g = lane + 32 * i;
-    if (g < G4) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + g * 4)), b4 = __ldg(reinterpret_cast<const float4*>(b + g * 4));
-      float4 o;
-      o.x = ((v[i].x - mean) * rstd * w4.x + b4.x) * sc;
-      o.y = ((v[i].y - mean) * rstd * w4.y + b4.y) * sc;
-      o.z = ((v[i].z - mean) * rstd * w4.z + b4.z) * sc;
-      o.w = ((v[i].w - mean) * rstd * w4.w + b4.w) * sc;
-      *reinterpret_cast<float4*>(y + (long)row * D + g * 4) = o;
-      if (y_hi) {  // split-bf16 image for a following tensor-core GEMM
-        *reinterpret_cast<uint2*>(y_hi + (long)row * D + g * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
-        *reinterpret_cast<uint2*>(y_lo + (long)row * D + g * 4) =
+  layernorm_rows<D, 1>(x + (long)row * D, res ? res + (long)row * D : nullptr, D, w, b, rowscale ? rowscale + row : nullptr, y + (long)row * D, D,
+                       y_hi ? y_hi + (long)row * ld2 : nullptr, y_lo ? y_lo + (long)row * ld2 : nullptr, y2 ? y2 + (long)row * ld2 : nullptr, ld2, lane, 1);
+  if (tail) {
+    for (int g = lane; g < tail_w / 4; g += 32) {
+      const float4 o = *reinterpret_cast<const float4*>(tail + (long)row * tail_ld + g * 4);
+      if (y2) *reinterpret_cast<float4*>(y2 + (long)row * ld2 + D + g * 4) = o;
+      if (y_hi) {
+        *reinterpret_cast<uint2*>(y_hi + (long)row * ld2 + D + g * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        *reinterpret_cast<uint2*>(y_lo + (long)row * ld2 + D + g * 4) =
             make_uint2(pack_bf16(o.x - bf16_round(o.x), o.y - bf16_round(o.y)), pack_bf16(o.z - bf16_round(o.z), o.w - bf16_round(o.w)));
       }
     }
@@ -289,15 +261,18 @@ __global__ void repitch_pair_kernel(const uint4* __restrict__ src, uint4* __rest
 }  // namespace
 
 void layernorm(const float* x, const float* res, const float* w, const float* b, const float* rowscale, float* y,
-               int rows, int D, cudaStream_t st, bf16* y_hi, bf16* y_lo) {
+               int rows, int D, cudaStream_t st, bf16* y_hi, bf16* y_lo, const LnExtra& ex) {
   S2S_PROF("layernorm", st);
   const int grid = ceil_div(rows, 8);
+  const int ld2 = ex.ld2 > 0 ? ex.ld2 : D;
+  S2S_CHECK(ld2 % 4 == 0 && ex.tail_w % 4 == 0 && ex.tail_ld % 4 == 0 && (!ex.tail || D + ex.tail_w <= ld2), "layernorm: bad pitch / tail width");
+  S2S_CHECK(!y_hi || y_lo, "layernorm: a hi image needs a lo image");
   if (D == 128)
-    launch_pdl(layernorm_kernel<128>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo);
+    launch_pdl(layernorm_kernel<128>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo, ld2, ex.y2, ex.tail, ex.tail_ld, ex.tail_w);
   else if (D == 256)
-    launch_pdl(layernorm_kernel<256>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo);
+    launch_pdl(layernorm_kernel<256>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo, ld2, ex.y2, ex.tail, ex.tail_ld, ex.tail_w);
   else if (D == 320)
-    launch_pdl(layernorm_kernel<320>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo);
+    launch_pdl(layernorm_kernel<320>, grid, 256, 0, st, x, res, w, b, rowscale, y, rows, y_hi, y_lo, ld2, ex.y2, ex.tail, ex.tail_ld, ex.tail_w);
   else
     S2S_CHECK(false, "layernorm: unsupported width");
   S2S_LAUNCH_CHECK();

@@ -48,9 +48,34 @@ struct TcGemm {
 void gemm_tc(const TcGemm& g, cudaStream_t st);
 void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st);
 
+// ---- gemm_chain.cu: consecutive row-local linear layers (split-bf16, 3 passes) in one launch ----------------------------
+// step:  y = act(A W^T + bias) * row_post + res  ->  C (fp32) and / or its split-bf16 image (out_hi, out_lo);
+//        with ln_w set, C is a scratch and LayerNorm(C) * ln_w + ln_b, times ln_scale[row], goes to ln_out (+ ln_hi / ln_lo).
+// A of every step is a split-bf16 image [M][K] (pitch lda, 0 = K): the caller's for step 0, an earlier step's output after.
+constexpr int CHAIN_MAX_STEPS = 10;
+struct ChainStep {
+  const bf16 *A_hi = nullptr, *A_lo = nullptr; long lda = 0;
+  const bf16 *W_hi = nullptr, *W_lo = nullptr; long ldw = 0;  // [N][K] (nn.Linear weight), row pitch ldw
+  int N = 0, K = 0, relu = 0;
+  const float *bias = nullptr, *res = nullptr, *row_post = nullptr; long ldres = 0;
+  float* C = nullptr; long ldc = 0;
+  bf16 *out_hi = nullptr, *out_lo = nullptr; long ldo = 0;
+  const float *ln_w = nullptr, *ln_b = nullptr, *ln_scale = nullptr;
+  float* ln_out = nullptr; bf16 *ln_hi = nullptr, *ln_lo = nullptr; long ld_ln = 0;  // one pitch for ln_out and its images
+};
+void gemm_chain(const ChainStep* steps, int n_steps, int M, cudaStream_t st);
+
 // ---- rows.cu ------------------------------------------------------------------------------------------
+// y has pitch D.  LnExtra: the image (y_hi, y_lo) and an optional second fp32 copy y2 share the pitch ld2 (0 = D); `tail`
+// ([rows][tail_w], pitch tail_ld) is copied into columns [D, D + tail_w) of y2 and of the image.
+struct LnExtra {
+  int ld2 = 0;
+  float* y2 = nullptr;
+  const float* tail = nullptr;
+  int tail_ld = 0, tail_w = 0;
+};
 void layernorm(const float* x, const float* res, const float* w, const float* b, const float* rowscale, float* y,
-               int rows, int D, cudaStream_t st, bf16* y_hi = nullptr, bf16* y_lo = nullptr);
+               int rows, int D, cudaStream_t st, bf16* y_hi = nullptr, bf16* y_lo = nullptr, const LnExtra& ex = LnExtra());
 void softmax_keybias(float* S, const float* keybias, int nb, int nh, int L, cudaStream_t st, bf16* P_hi = nullptr,
                      bf16* P_lo = nullptr);
 void node_features(const float* t, const long long* ridx, const float* fixed, const float* tfreq,

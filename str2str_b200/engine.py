@@ -42,7 +42,7 @@ _ENGINE_UIDS = itertools.count(1)
 class NativeEngine:
     """One s2s_ctx bound to one CUDA device."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device, pair_kernels: int = 1, node_gemm: int = 1):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device, pair_kernels: int = 1, node_gemm: int = 1, **options: int):
         self.uid = next(_ENGINE_UIDS)  # process-wide unique: (uid, generation) identifies one workspace allocation
         self.lib = _lib.load()
         self.device = torch.device(device)
@@ -60,6 +60,8 @@ class NativeEngine:
             _lib.check(self.lib.s2s_finalize(self.ctx, _lib.stream(self.device)))
             self.set_option("pair_kernels", pair_kernels)
             self.set_option("node_gemm", node_gemm)
+            for key, value in options.items():  # further s2s_set_option keys (et_pair, embed_table, chain, ...)
+                self.set_option(key, value)
         self.shape = None
         self.generation = 0  # bumped whenever the workspace is (re)allocated: invalidates captured CUDA graphs
 

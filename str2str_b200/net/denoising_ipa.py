@@ -67,6 +67,8 @@ class DenoisingNet(nn.Module):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("str2str_b200.DenoisingNet runs on CUDA only: move the module and the batch to a GPU")
+        if device.index is None:  # "cuda" and "cuda:<current>" are one device: one engine (and one set of options) for both spellings
+            device = torch.device("cuda", torch.cuda.current_device())
         key = str(device)
         if key not in self._native:
             self._native[key] = NativeEngine(self.state_dict(), device, **self._opts)

@@ -575,3 +575,32 @@ def test_trajectory_scheduler_vs_oracle(params, sde):
         _, rig_ref, _ = smp.forward_backward(batch, r0, delta, rigids_t=start[delta], return_rigids=True, seed=seed, first_decoy=first)
         assert rel(rig[delta][..., 4:], rig_ref[..., 4:]) < 2e-5
         first += n
+
+
+# ---- node-track chains (gemm_chain.cu): row-local layers fused into one launch ----------------------------------------------
+@pytest.mark.parametrize("L,B", [(64, 1), (57, 2), (128, 3), (256, 2), (300, 1)])
+def test_node_track_chain_is_bit_identical_to_separate_launches(params, L, B):
+    """The chained node track (sequence-transformer tails, post-transformer linear, NodeTransition, the per-residue terms of the
+    EdgeTransition and the torsion head as gemm_chain launches; LayerNorm as a step epilogue; the four skip connections as one
+    stacked GEMM) performs the same arithmetic in the same order as one launch per layer: outputs must agree BIT FOR BIT, and
+    the chained forward is compared with the oracle as well."""
+    f = synthetic.make_features(B, L, seed=900 + L, n_pad=3 if L > 8 else 0, n_fixed=1, random_aatype=True)
+    q, x = synthetic.make_backbone(L, seed=900 + L)
+    g = torch.Generator().manual_seed(L)
+    f["rigids_t"] = (torch.cat([q, x], -1)[None].repeat(B, 1, 1) + 0.2 * torch.randn(B, L, 7, generator=g)).float()
+    f["sc_ca_t"] = (x[None] + torch.randn(B, L, 3, generator=g)).float()
+    f["t"] = torch.linspace(0.3, 0.7, B)
+    net = make_net(params)
+    outs, launches = [], []
+    for chain in (0, 2):  # 2 = always (the default, 1, chains from 8192 residue rows up)
+        net.set_option("chain", chain)  # every engine of the module, present and future
+        with torch.no_grad(), kernel_log() as kl:
+            out = net(cuda(f), as_tensor_7=True)
+        outs.append((out["rigids"].clone(), out["psi"].clone()))
+        launches.append(sum(kl.names.values()))
+        assert sum(v for k, v in kl.names.items() if k.startswith("gemm_chain")) == (8 if chain else 0), kl.names
+    print(f"chain L={L} B={B}: profiled launches {launches[0]} -> {launches[1]}")
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = O.denoising_net(params, f)
+    valid = f["residue_mask"].bool()
+    assert rel(outs[1][0].cpu()[valid][:, 4:], ref["rigids"][valid][:, 4:]) < 1e-4
