@@ -58,7 +58,8 @@ int s2s_finalize(s2s_ctx* ctx, void* stream);
  *                         norm1 / linear1 / linear2 / norm2, the next in_proj or the post-transformer linear, NodeTransition,
  *                         the per-residue terms of the EdgeTransition, the torsion head) as ONE launch each (gemm_chain.cu,
  *                         LayerNorm as a step epilogue; 162 -> 88 launches per forward, same values bit for bit):
- *                         1 = from 8192 residue rows up (default: below that separate launches are faster), 2 = always, 0 = never. */
+ *                         1 = when the 128-row panels outnumber half the SMs (default: below that separate launches, which then split their output
+ *                         columns over the idle SMs, are faster), 2 = always, 0 = never. */
 int s2s_set_option(s2s_ctx* ctx, const char* key, int value);
 /* Size the workspace for (B, L) and build the relative-position table for residue-index offsets in
  * [d_min, d_max] (= min/max of residue_idx[i] - residue_idx[j]); d_max < d_min keeps the table already planned

@@ -9,6 +9,7 @@
 
 #include "../../include/str2str_b200.h"
 #include "s2s_internal.cuh"
+#include "tc_common.cuh"
 
 namespace s2s {
 
@@ -117,7 +118,7 @@ struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
   int opt_pair = 1, opt_node = 1, opt_ipa = 1, opt_table = 1, opt_et_pair = 1;
-  int opt_chain = 1;  // row-local layers of the node track fused into gemm_chain launches: 0 never, 1 from 8192 rows up, 2 always (do_trunk)
+  int opt_chain = 1;  // row-local layers of the node track fused into gemm_chain launches: 0 never, 1 when the row panels outnumber half the SMs, 2 always (do_trunk)
   int tfm_passes = 1;  // sequence-transformer in_proj + attention GEMMs: 1 = single bf16 (default; trajectory error unchanged, tools/traj_parity.py), 3 = split-bf16 (S2S_TFM_PASSES=3)
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
   int cur_prec = 0;  // default precision class of linear() calls (0 exact, 3 split-bf16, 1 bf16); set per stage
@@ -762,8 +763,9 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
   // conformations/s at cfg2 (16384 residue rows, 162 -> 88 launches per forward), but 130.4 -> 122.1 at L = 64 x 32 decoys and
   // 46.7 -> 44.2 at L = 64 x 1: with fewer row panels than SMs a layer is bound by its own load -> stage -> MMA -> epilogue
   // latency chain, which a step of the chain does not shorten, while separate launches overlap their prologues on idle SMs.
-  // So option "chain" = 1 (default) chains from 8192 rows up, 2 always (tests), 0 never.
-  const bool chain = img && (c->opt_chain == 2 || (c->opt_chain == 1 && R >= 8192));
+  // So option "chain" = 1 (default) chains when there are more 128-row panels than half the SMs — below that the separate panel
+  // GEMMs split their output columns over the idle SMs instead (gemm_tc.cu: n_split) —, 2 always (tests), 0 never.
+  const bool chain = img && (c->opt_chain == 2 || (c->opt_chain == 1 && 2 * ceil_div(R, 128) > sm_count()));
   auto sp = [&](bf16* hi, bf16* lo) { return img ? Split{hi, lo} : Split(); };
   const Split node_sp = sp(c->node_hi, c->node_lo), init_sp = sp(c->init_hi, c->init_lo), a_sp = sp(c->a256_hi, c->a256_lo),
               b_sp = sp(c->b256_hi, c->b256_lo), x_sp = sp(c->x320_hi, c->x320_lo);

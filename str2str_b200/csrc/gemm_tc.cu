@@ -6,6 +6,7 @@
 // passes = 1: plain bf16 product (IPA q/k/v projections, q.k^T, P.V — tools/precision_probe.py shows these tolerate it)
 // passes = 3: split-bf16 product  A_hi B_hi + A_lo B_hi + A_hi B_lo  accumulated in fp32 (≈16 mantissa bits per operand)
 //             for the layers of the residual stream that do not tolerate single bf16 rounding.
+#include <algorithm>
 #include <cstdlib>
 
 #include "s2s_internal.cuh"
@@ -42,6 +43,7 @@ struct TcKernelArgs {
   long bias_sb, bias_sh;  // batch strides of `bias` (0: one bias vector for every batch)
   int coalesced;          // 1: outputs / residual go through the per-warp transposition buffer (all pitches and N % 4 == 0)
   int b_mn;               // B operand is MN-major ([K][N] source), see TcGemm
+  int n_split, n_per;     // panel kernel: CTAs per row panel and output columns per CTA (a multiple of 64), see gemm_tc()
 };
 
 // EPI >= 0: coalesced epilogue specialised at compile time on what leaves the kernel (bit 0: fp32 C, 1: bf16 hi image,
@@ -522,12 +524,17 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
   const int NP = a.nb * a.nh * MT;                            // panels: (batch, head, 128-row tile)
   auto ksteps_of = [&](int kb) { return (min(KBLK, kb < KB ? a.K - kb * KBLK : a.K2 - (kb - KB) * KBLK) + 15) / 16; };
   // chunk ci of the whole CTA run uses accumulator buffer ci & 1; its width follows from the buffer and what is left of N
-  auto chunk_width = [&](uint32_t ci, int n_done) { return min((ci & 1) ? pg.w1 : 128, a.N - n_done); };
+  auto chunk_width = [&](uint32_t ci, int n_done, int n_hi) { return min((ci & 1) ? pg.w1 : 128, n_hi - n_done); };
+  // With fewer panels than SMs the output columns of a panel are split over n_split CTAs (work item pp = panel * n_split + part):
+  // each stages the panel once and walks its own column range [n_lo, n_hi), so a small-M GEMM is not bound by one SM streaming
+  // the whole weight matrix and issuing every MMA.
+  const int NW = NP * a.n_split;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t cnt = 0, ci = 0;
-      for (int p = blockIdx.x; p < NP; p += gridDim.x) {
+      for (int pp = blockIdx.x; pp < NW; pp += gridDim.x) {
+        const int p = pp / a.n_split, n_lo = (pp % a.n_split) * a.n_per, n_hi = min(a.N, n_lo + a.n_per);
         const int mt = p % MT, bz = p / MT, ib = bz / a.nh, ih = bz % a.nh;
         const int arow = ib * a.a_rb + ih * a.a_rh + mt * TM, acol = ib * a.a_cb + ih * a.a_ch;
         const int brow = ib * a.b_rb + ih * a.b_rh, bcol = ib * a.b_cb + ih * a.b_ch;
@@ -543,8 +550,8 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
           tma_load_2d(st, &mAh, acol + kb * KBLK, arow, &s_full[s]);
           if (bps == 2) tma_load_2d(st + TILE_BYTES, &mAl, acol + kb * KBLK, arow, &s_full[s]);
         }
-        for (int n = 0; n < a.N; ++ci) {  // weight blocks: 128 rows of W from row n (rows past the end read as zeros), one K block
-          const int w = chunk_width(ci, n);
+        for (int n = n_lo; n < n_hi; ++ci) {  // weight blocks: 128 rows of W from row n (rows past the end read as zeros), one K block
+          const int w = chunk_width(ci, n, n_hi);
           for (int kb = 0; kb < KBT; ++kb, ++cnt) {
             const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
             mbar_wait(&s_empty[s], ph ^ 1);
@@ -576,12 +583,13 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     constexpr uint32_t BLK = TILE_BYTES >> 4;
     const uint32_t stage_units = bps * BLK;
     const uint32_t bmn_fix = ((uint32_t)(TILE_BYTES / 2) >> 4 << 16) - (1u << 16);  // MN-major B: LBO field 1 -> 512 (8 KB between halves)
-    for (int p = blockIdx.x; p < NP; p += gridDim.x, ++pi) {
+    for (int pp = blockIdx.x; pp < NW; pp += gridDim.x, ++pi) {
+      const int n_lo = (pp % a.n_split) * a.n_per, n_hi = min(a.N, n_lo + a.n_per);
       cnt += KBT;  // the ring stages that carried A
       mbar_wait(a_ready, pi & 1);
       tc_fence_after();
-      for (int n = 0; n < a.N; ++ci) {
-        const int w = chunk_width(ci, n);
+      for (int n = n_lo; n < n_hi; ++ci) {
+        const int w = chunk_width(ci, n, n_hi);
         const uint32_t ab = ci & 1, aph = (ci >> 1) & 1;
         mbar_wait(&acc_empty[ab], aph ^ 1);
         tc_fence_after();
@@ -625,7 +633,8 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
     constexpr bool kC = (EPI & 1) != 0, kHi = (EPI & 2) != 0, kLo = (EPI & 4) != 0, kRes = (EPI & 8) != 0, kWide = (EPI & 16) != 0;
     const int xj = lane & 7;
     uint32_t cnt = 0, ci = 0, pi = 0;
-    for (int p = blockIdx.x; p < NP; p += gridDim.x, ++pi) {
+    for (int pp = blockIdx.x; pp < NW; pp += gridDim.x, ++pi) {
+      const int p = pp / a.n_split, n_lo = (pp % a.n_split) * a.n_per, n_hi = min(a.N, n_lo + a.n_per);
       const int mt = p % MT, bz = p / MT, ib = bz / a.nh, ih = bz % a.nh;
       const long boff = ib * a.sCb + ih * a.sCh;
       const float* bias = a.bias ? a.bias + ib * a.bias_sb + ih * a.bias_sh : nullptr;
@@ -657,8 +666,8 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
       const float pre = (row_ok && a.row_pre) ? a.row_pre[m] * a.alpha : a.alpha;
       const float post = (row_ok && a.row_post) ? a.row_post[m] : 1.f;
       const long row0 = (long)mt * TM + q * 32 + (lane >> 3);  // first of the 8 rows (stride 4) this lane stores
-      for (int n = 0; n < a.N; ++ci) {
-        const int w = chunk_width(ci, n);
+      for (int n = n_lo; n < n_hi; ++ci) {
+        const int w = chunk_width(ci, n, n_hi);
         const uint32_t ab = ci & 1, aph = (ci >> 1) & 1;
         const int nw0 = n + hf * 64;                 // first column of this warp's 64-column share of the chunk
         const bool has_cols = hf * 64 < w;           // warp-uniform
@@ -851,6 +860,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   k.b2_cb = g.b2_cb; k.b2_ch = g.b2_ch; k.b2_rb = g.b2_rb; k.b2_rh = g.b2_rh;
   k.bias_sb = g.bias_sb; k.bias_sh = g.bias_sh;
   k.b_mn = g.b_mn;
+  k.n_split = 1; k.n_per = 0;
   k.coalesced = g.N % 4 == 0 && g.ldc % 4 == 0 && g.ldres % 4 == 0 && g.ldo % 4 == 0 && g.sCb % 4 == 0 && g.sCh % 4 == 0 && !g.out_vt;
   if (const char* e = getenv("S2S_GEMM_COALESCED")) k.coalesced = k.coalesced && atoi(e) != 0;  // A/B timing only
   k.a_cb = g.a_cb; k.a_ch = g.a_ch; k.a_rb = g.a_rb; k.a_rh = g.a_rh;
@@ -895,7 +905,20 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
     pg.acc1 = a_cols + 128;
     pg.w1 = 512 - a_cols - 128 >= 128 ? 128 : 64;
     const int n_panels = g.nb * g.nh * ceil_div(g.M, TM);
-    const int pgrid = n_panels < sm_count() ? n_panels : sm_count();
+    // fewer panels than half the SMs: split every panel's output columns over several CTAs (at least 128 columns each, in units
+    // of 64).  Measured at L = 64 x 32 decoys (16 panels): the q|k|v projection (N = 6144) took 55 us on 16 SMs, each streaming
+    // the whole 3 MB weight matrix (profiles/r02d_launch_summary_L64_B32_separate.txt).
+    k.n_split = 1; k.n_per = (g.N + 63) / 64 * 64;
+    static const int split_env = [] { const char* e = getenv("S2S_GEMM_NSPLIT"); return e ? atoi(e) : 1; }();  // 0: A/B timing
+    if (split_env && n_panels * 2 <= sm_count()) {
+      const int units = ceil_div(g.N, 64), want = std::min(sm_count() / n_panels, units / 2);
+      if (want > 1) {
+        k.n_per = ceil_div(units, want) * 64;
+        k.n_split = ceil_div(g.N, k.n_per);
+      }
+    }
+    const int n_work = n_panels * k.n_split;
+    const int pgrid = n_work < sm_count() ? n_work : sm_count();
     static bool pconf[24] = {};
     auto plaunch = [&](auto kern) {
       if (!pconf[epi]) {
