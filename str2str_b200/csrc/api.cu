@@ -611,6 +611,19 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
     gemm_f32(g, st);
   }
   ipa_finalize_points(c->opt, quat, trans, c->feats, R, st, fused ? c->sa_hi : nullptr, fused ? c->sa_lo : nullptr);
+  static const int splitk_env = [] { const char* e = getenv("S2S_SPLITK"); return e ? atoi(e) : 1; }();  // 0: A/B timing
+  if (fused && splitk_env && 2 * ceil_div(R, 128) <= sm_count()) {
+    // few residue rows: linear_out's reduction over the 2688 features is cut into nine slices that run on different SMs
+    // (c->proj, the projection buffer, is dead by now and serves as the partial-sum scratch: 9 x R x 256 of its R x 6816 floats)
+    const auto w = weight_split(c, c->P(ip + "linear_out.weight"));
+    TcGemm g;
+    g.A_hi = c->sa_hi; g.A_lo = c->sa_lo; g.a_rows = R; g.a_cols = IPA_FEAT; g.a_pitch = IPA_FEAT;
+    g.B_hi = w.first; g.B_lo = w.second; g.b_rows = 256; g.b_cols = IPA_FEAT; g.b_pitch = IPA_FEAT;
+    g.M = R; g.N = 256; g.K = IPA_FEAT; g.passes = 3;
+    g.bias = c->P(ip + "linear_out.bias"); g.row_post = row_post; g.res = res; g.ldres = 256; g.C = out; g.ldc = 256;
+    gemm_tc_splitk(g, c->proj, st);
+    return;
+  }
   linear(c, c->feats, IPA_FEAT, c->P(ip + "linear_out.weight"), IPA_FEAT, c->P(ip + "linear_out.bias"), out, 256, R, 256,
          IPA_FEAT, st, 0, res, 256, nullptr, row_post, TC3, fused ? Split{c->sa_hi, c->sa_lo} : Split());
 }
@@ -769,26 +782,34 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
   auto sp = [&](bf16* hi, bf16* lo) { return img ? Split{hi, lo} : Split(); };
   const Split node_sp = sp(c->node_hi, c->node_lo), init_sp = sp(c->init_hi, c->init_lo), a_sp = sp(c->a256_hi, c->a256_lo),
               b_sp = sp(c->b256_hi, c->b256_lo), x_sp = sp(c->x320_hi, c->x320_lo);
-  S2S_CUDA(cudaMemcpyAsync(c->init_node, c->node, (size_t)R * 256 * 4, cudaMemcpyDeviceToDevice, st));
   if (img) {
+    // every block's skip connection reads the same initial node embedding (ipa.py:333,353-356): one stacked GEMM serves the
+    // four of them, here, while c->node still IS that embedding (so no copy of it is kept)
     split_bf16(c->node, 256, R, 256, c->node_hi, c->node_lo, st);
-    S2S_CUDA(cudaMemcpyAsync(c->init_hi, c->node_hi, (size_t)R * 256 * 2, cudaMemcpyDeviceToDevice, st));
-    S2S_CUDA(cudaMemcpyAsync(c->init_lo, c->node_lo, (size_t)R * 256 * 2, cudaMemcpyDeviceToDevice, st));
+    linear(c, c->node, 256, c->skip_w_all, 256, c->skip_b_all, c->skip_all, N_BLK * D_SKIP, R, N_BLK * D_SKIP, 256, st, 0, nullptr, 0, nullptr, nullptr, -1, node_sp);
+  } else {
+    S2S_CUDA(cudaMemcpyAsync(c->init_node, c->node, (size_t)R * 256 * 4, cudaMemcpyDeviceToDevice, st));
   }
   split_rigids(rigids_t, c->quat, c->trans, R, st);
-  // every block's skip connection reads the same init_node (ipa.py:353-356): one stacked GEMM for the four of them
-  if (chain) linear(c, c->init_node, 256, c->skip_w_all, 256, c->skip_b_all, c->skip_all, N_BLK * D_SKIP, R, N_BLK * D_SKIP, 256, st, 0, nullptr, 0, nullptr, nullptr, -1, init_sp);
   const std::string tp = "translator.torsion_pred.";
   for (int b = 0; b < N_BLK; ++b) {
     const std::string s = std::to_string(b);
     const std::string nt = tk + "node_transition_" + s + ".", t0 = tk + "transformer_" + s + ".layers.0.", t1 = tk + "transformer_" + s + ".layers.1.";
     // node = LN(node + ipa(node, z, T) * mask)          (ipa.py:344-351)
     do_ipa(c, b, B, L, c->node, c->z, c->quat, c->trans, rmask, c->a256, c->node, rmask, st, node_sp);
-    if (chain) {
+    if (img) {
       // ... and the sequence transformer's input [node | skip(init_node)] (ipa.py:353-356) from the same LayerNorm launch
       LnExtra ex;
       ex.ld2 = D_TFM; ex.y2 = c->x320; ex.tail = c->skip_all + b * D_SKIP; ex.tail_ld = N_BLK * D_SKIP; ex.tail_w = D_SKIP;
       layernorm(c->a256, nullptr, c->P(tk + "ipa_ln_" + s + ".weight"), c->P(tk + "ipa_ln_" + s + ".bias"), nullptr, c->node, R, 256, st, x_sp.hi, x_sp.lo, ex);
+    } else {
+      layernorm(c->a256, nullptr, c->P(tk + "ipa_ln_" + s + ".weight"), c->P(tk + "ipa_ln_" + s + ".bias"), nullptr, c->node, R, 256, st);
+      // sequence transformer on [node | skip(init_node)]   (ipa.py:353-360)
+      linear(c, c->init_node, 256, c->P(tk + "skip_embed_" + s + ".weight"), 256, c->P(tk + "skip_embed_" + s + ".bias"), c->skip64, 64, R, 64, 256, st, 0,
+             nullptr, 0, nullptr, nullptr, -1, init_sp);
+      concat_skip(c->node, c->skip64, c->x320, R, st, x_sp.hi, x_sp.lo);
+    }
+    if (chain) {
       const bool sp3 = c->tfm_passes == 3;
       std::vector<ChainStep> v;
       // layer 0: attention, then its row-local tail and layer 1's in_proj in one launch
@@ -823,11 +844,6 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
       }
       gemm_chain(v.data(), (int)v.size(), R, st);
     } else {
-      layernorm(c->a256, nullptr, c->P(tk + "ipa_ln_" + s + ".weight"), c->P(tk + "ipa_ln_" + s + ".bias"), nullptr, c->node, R, 256, st);
-      // sequence transformer on [node | skip(init_node)]   (ipa.py:353-360)
-      linear(c, c->init_node, 256, c->P(tk + "skip_embed_" + s + ".weight"), 256, c->P(tk + "skip_embed_" + s + ".bias"), c->skip64, 64, R, 64, 256, st, 0,
-             nullptr, 0, nullptr, nullptr, -1, init_sp);
-      concat_skip(c->node, c->skip64, c->x320, R, st, x_sp.hi, x_sp.lo);
       do_tfm_attention(c, t0, B, L, st);
       do_tfm_tail(c, t0, B, L, st);
       do_tfm_attention(c, t1, B, L, st);

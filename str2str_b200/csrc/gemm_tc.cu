@@ -831,7 +831,55 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, long ld, int ro
   if (lo) *reinterpret_cast<uint2*>(lo + (long)r * cols + c) = make_uint2(l[0], l[1]);
 }
 
+// C[m][n] = (sum_s part[s][m][n] + bias[n]) * row_post[m] + res[m][n]: the fixed-order reduction of a split-K GEMM's partial sums
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int S, long stride, const float* __restrict__ bias,
+                                     const float* __restrict__ row_post, const float* res, long ldres, float* C, long ldc, int M, int N) {
+  pdl_sync();
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n4 = N / 4;
+  if (i >= (long)M * n4) return;
+  const int m = (int)(i / n4), n = (int)(i % n4) * 4;
+  float4 acc = *reinterpret_cast<const float4*>(part + (long)m * N + n);
+  for (int s = 1; s < S; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(part + s * stride + (long)m * N + n);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  if (row_post) {
+    const float p = row_post[m];
+    acc.x *= p; acc.y *= p; acc.z *= p; acc.w *= p;
+  }
+  if (res) {
+    const float4 r = *reinterpret_cast<const float4*>(res + (long)m * ldres + n);
+    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+  }
+  *reinterpret_cast<float4*>(C + (long)m * ldc + n) = acc;
+}
+
 }  // namespace
+
+// C = (A W^T + bias) * row_post + res with a long reduction (K a few thousand) on FEW rows: the K range is cut into slices of 320,
+// every (row panel, slice) pair is one work item of the panel kernel (A slice resident in tensor memory, TS-mode MMAs) writing
+// its partial sum to `scratch` ([slices][M][N] fp32), and one small kernel adds the partials in slice order.  With M / 128 row
+// panels well below the SM count the tile kernel would leave most SMs idle, each of the busy ones walking the whole K range.
+void gemm_tc_splitk(const TcGemm& g0, float* scratch, cudaStream_t st) {
+  S2S_CHECK(g0.nb * g0.nh == 1 && g0.passes == 3 && !g0.K2 && !g0.b_mn && !g0.out_hi && g0.C && g0.N % 4 == 0 && g0.ldc % 4 == 0 && g0.ldres % 4 == 0 &&
+                !g0.relu && !g0.row_pre && g0.alpha == 1.f, "gemm_tc_splitk: unsupported variant");
+  const int S = ceil_div(g0.K, 320);
+  TcGemm g = g0;
+  g.nh = S; g.a_ch = 320; g.b_ch = 320; g.K = 320;  // columns past K read as zeros (TMA out-of-bounds fill): the last slice may be partial
+  g.bias = nullptr; g.row_post = nullptr; g.res = nullptr; g.ldres = 0;
+  g.C = scratch; g.ldc = g0.N; g.sCb = 0; g.sCh = (long)g0.M * g0.N;
+  g.force_panel = 1;
+  gemm_tc(g, st);
+  S2S_PROF("splitk_reduce", st);
+  launch_pdl(splitk_reduce_kernel, ceil_div((long)g0.M * (g0.N / 4), 256), 256, 0, st, (const float*)scratch, S, (long)g0.M * g0.N, g0.bias, g0.row_post,
+             g0.res, g0.ldres, g0.C, g0.ldc, g0.M, g0.N);
+  S2S_LAUNCH_CHECK();
+}
 
 void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st) {
   S2S_CHECK(cols % 4 == 0 && ld % 4 == 0, "split_bf16: width must be a multiple of 4");
@@ -897,7 +945,7 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
   // staging -> MMA -> epilogue chain of a panel is not overlapped with the next panel.  Off by default (S2S_GEMM_PANEL_BATCHED=1: A/B).
   static const int panel_batched = [] { const char* e = getenv("S2S_GEMM_PANEL_BATCHED"); return e ? atoi(e) : 0; }();
   const bool plain = g.nb * g.nh == 1 && g.K2 == 0 && !g.b_mn;
-  if (use_panel && epi >= 0 && (plain || panel_batched) && g.K % 64 == 0 && a_cols <= 320 && (g.K2 == 0 || g.passes == 1) &&
+  if (use_panel && epi >= 0 && (plain || panel_batched || g.force_panel) && g.K % 64 == 0 && a_cols <= 320 && (g.K2 == 0 || g.passes == 1) &&
       (!g.b_mn || g.K2 == 0)) {
     PanelGeom pg;
     pg.acol_lo = kbt * 32;

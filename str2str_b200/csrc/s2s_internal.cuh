@@ -44,8 +44,10 @@ struct TcGemm {
   // b_mn = 1: B is given as [K rows][N columns] (N contiguous, e.g. the v columns of a row-major q|k|v buffer) and is read
   // as an MN-major UMMA operand: box row = ib*b_rb + ih*b_rh + kb*64, box column = ib*b_cb + ih*b_ch + n0 (+64).
   int b_mn = 0;
+  int force_panel = 0;  // batched call that must take the panel kernel (gemm_tc_splitk)
 };
 void gemm_tc(const TcGemm& g, cudaStream_t st);
+void gemm_tc_splitk(const TcGemm& g, float* scratch, cudaStream_t st);  // scratch: ceil(K / 320) * M * N floats
 void split_bf16(const float* src, long ld, int rows, int cols, bf16* hi, bf16* lo, cudaStream_t st);
 
 // ---- gemm_chain.cu: consecutive row-local linear layers (split-bf16, 3 passes) in one launch ----------------------------
