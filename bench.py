@@ -169,29 +169,36 @@ def algorithmic(B, L):
                 edge_embed=("tensor", ee_flops, rows * 128 * 2, {}))
 
 
+NCU_CAPTURE = "r02e_ncu_full_summary.csv"  # `ncu --set full --clock-control none` of tools/profile_forward.py 64 256 1, condensed by tools/ncu_summary.py
+
+
 def ncu_traffic(B, L):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-    (profiles/r01c_ncu_full_pair_kernels.csv, made with tools/ncu_summary.py at cfg2).  None for any other shape."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture at cfg2
+    (profiles/NCU_CAPTURE): the average over a kernel's launches, summed over the kernels one profiled stage consists of
+    (the edge embedder = table MLP + expansion).  Empty for any other shape."""
     if (B, L) != (64, 256):
         return {}
     import csv
 
+    stages = {"edge_transition_pair_kernel": "edge_transition", "edge_transition_tc3_kernel": "edge_transition", "ipa_pair_tc_kernel": "ipa_pair_attention",
+              "edge_embed_pipe_kernel<2>": "edge_embed", "edge_embed_expand_kernel": "edge_embed", "embed_table_setup_kernel": "edge_embed"}
+    path = os.path.join(ROOT, "profiles", NCU_CAPTURE)
+    if not os.path.exists(path):
+        return {}
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    ir = next(i for i, h in enumerate(hdr) if h.startswith("dram_read"))
+    iw = next(i for i, h in enumerate(hdr) if h.startswith("dram_write"))
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    ur, uw = hdr[ir].split("[")[1].rstrip("]"), hdr[iw].split("[")[1].rstrip("]")
+    per_kernel = {}
+    for r in rows[1:]:
+        kern = next((k for k in stages if r[0].startswith(k)), None)
+        if kern:
+            per_kernel.setdefault(kern, []).append(float(r[ir]) * scale[ur] + float(r[iw]) * scale[uw])
     out = {}
-    for fn, names in (("r01c_ncu_full_pair_kernels.csv", {"edge_transition_tc": "edge_transition", "ipa_pair_tc_kernel": "ipa_pair_attention",
-                                                          "edge_embed_pipe_kernel": "edge_embed"}),):
-        path = os.path.join(ROOT, "profiles", fn)
-        if not os.path.exists(path):
-            continue
-        rows = list(csv.reader(open(path)))
-        hdr = rows[0]
-        ir = next(i for i, h in enumerate(hdr) if h.startswith("dram_read"))
-        iw = next(i for i, h in enumerate(hdr) if h.startswith("dram_write"))
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        ur, uw = hdr[ir].split("[")[1].rstrip("]"), hdr[iw].split("[")[1].rstrip("]")
-        for r in rows[1:]:
-            key = next((v for k, v in names.items() if r[0].startswith(k)), None)
-            if key:
-                out[key] = float(r[ir]) * scale[ur] + float(r[iw]) * scale[uw]
+    for kern, vals in per_kernel.items():
+        out[stages[kern]] = out.get(stages[kern], 0.0) + sum(vals) / len(vals)
     return out
 
 
@@ -226,7 +233,7 @@ def roofline_records(per, B, L):
         roof = {k: extra[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
         roof.update({k: extra[dom][k] for k in ("executed_tflops", "moved_gbs", "moved_frac") if k in extra[dom]})
         roof.update(kernel=dom, algorithmic="SURVEY.md 8(d) per-unit figure x units per launch (bench.py: algorithmic())",
-                    traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/r01c_ncu_full_pair_kernels.csv (dram read + write per launch)",
+                    traffic=traffic.get(dom), traffic_source="ncu --set full, profiles/" + NCU_CAPTURE + " (dram read + write per launch)",
                     peak_source=src, timing="CUDA events around each launch, one eager step")
     return roof, extra
 
