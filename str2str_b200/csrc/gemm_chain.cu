@@ -88,7 +88,7 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 32 * 8);
     }
-    mbar_init(a_ready, 128);
+    mbar_init(a_ready, 32 * 8);
     mbar_init(a_free, 1);
     mbar_init(step_done, 32 * 8);
     fence_barrier_init();
@@ -194,11 +194,13 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       for (int si = 0; si < a.n_steps; ++si, ++g) {
         const ChainK& s = a.s[si];
         const int KB = s.K / KBLK;
-        if (hf == 0) {
-          // ---- stage the panel of A into tensor memory: this thread copies row r of every K block (128 bytes = 32 columns)
+        {
+          // ---- stage the panel of A into tensor memory: this thread copies row r of every other K block (128 bytes = 32 columns);
+          // the two warps of a lane quarter (hf = 0 / 1) take the even / odd K blocks
           if (g > 0) mbar_wait(a_free, (g - 1) & 1);
           tc_fence_after();
           for (int kb = 0; kb < KB; ++kb, ++cnt) {
+            if ((kb & 1) != hf) continue;
             const uint32_t st_i = cnt % C_STAGES, ph = (cnt / C_STAGES) & 1;
             mbar_wait(&s_full[st_i], ph);
             const unsigned char* st = smem + st_i * stage_bytes;
@@ -212,8 +214,8 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
               }
               tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + (img ? s.acol_lo : 0) + kb * 32, pk);
             }
-            named_bar_sync(1, 128);  // all four staging warps have read the blocks
-            if (threadIdx.x == 64) mbar_arrive(&s_empty[st_i]);
+            named_bar_sync(hf ? 3 : 1, 128);  // all four warps staging this K block have read it
+            if (threadIdx.x == 64 + hf * 128) mbar_arrive(&s_empty[st_i]);
           }
           tc_fence_before();
           mbar_arrive(a_ready);

@@ -509,7 +509,7 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 32 * 8);
     }
-    mbar_init(a_ready, 128);
+    mbar_init(a_ready, 32 * 8);
     mbar_init(a_free, 1);
     fence_barrier_init();
   }
@@ -638,11 +638,13 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
       const int mt = p % MT, bz = p / MT, ib = bz / a.nh, ih = bz % a.nh;
       const long boff = ib * a.sCb + ih * a.sCh;
       const float* bias = a.bias ? a.bias + ib * a.bias_sb + ih * a.bias_sh : nullptr;
-      if (hf == 0) {
-        // ---- stage the panel of A into tensor memory: this thread copies row r of every K block (128 bytes = 32 columns)
+      {
+        // ---- stage the panel of A into tensor memory: this thread copies row r of every other K block (128 bytes = 32 columns);
+        // the two warps of a lane quarter (hf = 0 / 1) take the even / odd K blocks
         if (pi > 0) mbar_wait(a_free, (pi - 1) & 1);
         tc_fence_after();
         for (int kb = 0; kb < KBT; ++kb, ++cnt) {
+          if ((kb & 1) != hf) continue;
           const uint32_t s = cnt % n_stages, ph = (cnt / n_stages) & 1;
           mbar_wait(&s_full[s], ph);
           const unsigned char* st = smem + s * stage_bytes;
@@ -655,8 +657,8 @@ gemm_panel_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant
             }
             tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + (img ? pg.acol_lo : 0) + kb * 32, pk);
           }
-          named_bar_sync(1, 128);  // all four staging warps have read the blocks
-          if (threadIdx.x == 64) mbar_arrive(&s_empty[s]);
+          named_bar_sync(1 + hf, 128);  // all four warps staging this K block have read it
+          if (threadIdx.x == 64 + hf * 128) mbar_arrive(&s_empty[s]);
         }
         tc_fence_before();
         mbar_arrive(a_ready);
@@ -953,13 +955,14 @@ void gemm_tc(const TcGemm& g, cudaStream_t st) {
     pg.acc1 = a_cols + 128;
     pg.w1 = 512 - a_cols - 128 >= 128 ? 128 : 64;
     const int n_panels = g.nb * g.nh * ceil_div(g.M, TM);
-    // fewer panels than half the SMs: split every panel's output columns over several CTAs (at least 128 columns each, in units
-    // of 64).  Measured at L = 64 x 32 decoys (16 panels): the q|k|v projection (N = 6144) took 55 us on 16 SMs, each streaming
-    // the whole 3 MB weight matrix (profiles/r02d_launch_summary_L64_B32_separate.txt).
+    // fewer panels than half the SMs: split every panel's output columns over several CTAs, in units of 64 columns.  Measured at
+    // L = 64 x 32 decoys (16 panels): the q|k|v projection (N = 6144) took 55 us on 16 SMs, each streaming the whole 3 MB weight
+    // matrix (profiles/r02d_launch_summary_L64_B32_separate.txt); whole-step effect of the split with at least 128 / 64 columns
+    // per CTA: 130 -> 183 -> 216 conformations/s at L = 64 x 32, 46.7 -> 74.4 -> 98.0 at cfg1 (L = 64, 1 decoy).
     k.n_split = 1; k.n_per = (g.N + 63) / 64 * 64;
-    static const int split_env = [] { const char* e = getenv("S2S_GEMM_NSPLIT"); return e ? atoi(e) : 1; }();  // 0: A/B timing
+    static const int split_env = [] { const char* e = getenv("S2S_GEMM_NSPLIT"); return e ? atoi(e) : 1; }();  // minimum 64-column units per CTA; 0: no split (A/B timing)
     if (split_env && n_panels * 2 <= sm_count()) {
-      const int units = ceil_div(g.N, 64), want = std::min(sm_count() / n_panels, units / 2);
+      const int units = ceil_div(g.N, 64), want = std::min(sm_count() / n_panels, units / split_env);
       if (want > 1) {
         k.n_per = ceil_div(units, want) * 64;
         k.n_split = ceil_div(g.N, k.n_per);
