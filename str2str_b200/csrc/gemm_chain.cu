@@ -35,7 +35,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int C_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (the first four also stage A into tensor memory)
+constexpr int C_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (which also stage A into tensor memory)
 constexpr int C_RING = 12 * TILE_BYTES;
 constexpr int C_OFF_BAR = C_RING;
 constexpr int C_OFF_BIAS = C_OFF_BAR + 32 * 8 + 16;  // per-epilogue-warp bias slice, [8][64] fp32

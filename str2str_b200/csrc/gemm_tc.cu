@@ -473,8 +473,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
 // output columns in chunks of <= 128, streaming only the weight blocks through the shared-memory ring.  A_hi serves two
 // of the three split-bf16 passes; A is read from L2 once per panel instead of once per 128 output columns.
 // Tensor memory: [A_hi | A_lo] (K/2 columns each) + two accumulator buffers (128 + 128, or 128 + 64 when K = 320 leaves
-// only 192 columns).  Roles: TMA producer warp, MMA warp, 8 epilogue warps of which the first four (one per TMEM lane
-// quarter) also stage A at the start of a panel.  Coalesced compile-time-specialised epilogue as above (EPI >= 0 only).
+// only 192 columns).  Roles: TMA producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter) that also stage A at
+// the start of a panel, the two warps of a quarter taking the even / odd K blocks.  Coalesced compile-time-specialised
+// epilogue as above (EPI >= 0 only).  With few panels the output columns of a panel are split over several CTAs (n_split).
 struct PanelGeom {
   int acol_lo;     // first TMEM column of A_lo (A_hi starts at column 0)
   int acc0, acc1;  // first TMEM column of the two accumulator buffers
