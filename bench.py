@@ -502,14 +502,22 @@ def run_cfg5(a, world, rank, dev):
                 my_first.append(base[L] + used[L])
             used[L] += b
 
+    busy_marks = []
+
     def run_all(e2e):
         outs = []
+        start_ev = torch.cuda.Event(enable_timing=True)
+        start_ev.record()
+        busy_marks.append(start_ev)
         for (L, b), fd in zip(mine, my_first):
             batch = {k: v.to(dev, non_blocking=True) for k, v in hosts[L].items()} if e2e else resident[L]
             r0 = Rigid.from_tensor_4x4(batch["rigidgroups_gt_frames"][..., 0, :, :].repeat(b, 1, 1, 1))
             o = smp.forward_backward(batch, r0, 0.5, return_numpy=False, seed=a.seed, first_decoy=fd)
             outs.append(o[:, :, 1, :].reshape(-1, 3))   # C-alpha, packed [b * L, 3]
         packed = torch.cat(outs, 0) if outs else torch.zeros(0, 3, device=dev)
+        done_ev = torch.cuda.Event(enable_timing=True)  # this rank's own work ends here; the collective below waits for the slowest rank
+        done_ev.record()
+        busy_marks.append(done_ev)
         if world > 1:  # one collective: packed coordinates, padded to the largest rank share (cu_seqlens are the plan itself)
             sizes = [sum(b * L for L, b in plan[r]) for r in range(world)]
             buf = torch.zeros(max(sizes), 3, device=dev)
@@ -531,23 +539,29 @@ def run_cfg5(a, world, rank, dev):
     for mode in ("value", "e2e"):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        del busy_marks[:]
         e0.record()
         for _ in range(a.steps):
             run_all(mode == "e2e")
         e1.record()
         torch.cuda.synchronize(dev)
-        busy = torch.tensor([e0.elapsed_time(e1)], device=dev)   # this rank's own time, before waiting for the others
+        total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        # this rank's own work: from the start of every pass to its last kernel before the collective
+        own = torch.tensor([sum(busy_marks[i].elapsed_time(busy_marks[i + 1]) for i in range(0, len(busy_marks), 2))], device=dev)
         barrier()
-        mx, mn = busy.clone(), busy.clone()
+        mx, bmx, bmn = total.clone(), own.clone(), own.clone()
         if world > 1:
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-        res[mode] = (float(mx), float(mn))
+            dist.all_reduce(bmx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bmn, op=dist.ReduceOp.MIN)
+        res[mode] = (float(mx), float(bmx), float(bmn))
     clk = clocks.stop() if clocks else None
     if rank == 0:
         tot = sum(counts.values())
-        ms, ms_min = res["value"]
-        cost = [sum(b * L * L for L, b in plan[r]) for r in range(world)]
+        from str2str_b200.sampler import batch_cost
+
+        ms, busy_max, busy_min = res["value"]
+        cost = [sum(batch_cost(L, b) for L, b in plan[r]) for r in range(world)]
         line = {
             "metric": "conformations/sec (mixed lengths, 100 denoise steps)", "value": round(tot * a.steps / (ms / 1e3), 3), "unit": "conformations/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(1, a.warmup), "ms_per_step": round(ms / a.steps, 2), "higher_is_better": True,
@@ -557,8 +571,9 @@ def run_cfg5(a, world, rank, dev):
                     "h2d_bytes_per_step": int(sum(sum(v.numel() * v.element_size() for v in hosts[L].values()) for L, _ in mine)),
                     "d2h_bytes_per_step": int(sum(b * L for L, b in mine) * 12 * (world if world > 1 else 1))},
             "gpu_launches": int(smp.launches * len(mine) * a.steps), "clocks": clk,
-            "imbalance": {"busy_ms_max": round(ms / a.steps, 1), "busy_ms_min": round(ms_min / a.steps, 1),
-                          "min_over_max": round(ms_min / ms, 3), "planned_cost_min_over_max": round(min(cost) / max(cost), 3)},
+            "imbalance": {"busy_ms_max": round(busy_max / a.steps, 1), "busy_ms_min": round(busy_min / a.steps, 1),
+                          "min_over_max": round(busy_min / busy_max, 3), "planned_cost_min_over_max": round(min(cost) / max(cost), 3),
+                          "planned_ms_per_rank": [round(c, 1) for c in cost]},
         }
         print(json.dumps(line))
 

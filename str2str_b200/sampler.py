@@ -236,28 +236,68 @@ class ForwardBackwardSampler:
         return all_gather_decoys(torch.as_tensor(local), share).numpy()
 
 
-def plan_mixed_lengths(counts: Dict[int, int], world: int, replica_per_batch: int = 64):
-    """Mixed-length workload (BASELINE cfg 5): split every (length, n_decoys) request into batches of at most
-    `replica_per_batch` decoys (and no more than an even share per rank, so that one long chain cannot unbalance the
-    plan) and assign the batches to ranks by longest-processing-time-first on the cost model
-    cost(L, B) = B * L^2 (the pair track dominates).  Returns one list of (L, B) batches per rank.
+def batch_cost(L: int, b: int) -> float:
+    """Modelled device time (ms) of one 100-step trajectory batch of b decoys of length L on one B200: a per-decoy slope with a
+    pair-track term (L^2) and a node-track term, plus a per-batch floor — the dependent-launch latency of 101 iterations, which
+    is what makes many small batches expensive.  Fitted (all within 5 %) to bench.py --length L --decoys b, ms per batch:
+    (64, 8) 103, (64, 64) 227, (128, 8) 130, (128, 64) 464, (256, 8) 218, (256, 32) 696, (256, 64) 1328, (384, 8) 396,
+    (384, 13) 614, (384, 32) 1437.  Only ratios matter to the planner."""
+    return b * (2.8885e-4 * L * L - 7.86e-4 * L + 1.177) + max(40.0, 92.0 - 0.12 * L)
+
+
+def plan_mixed_lengths(counts: Dict[int, int], world: int, replica_per_batch: int = 64, cost=batch_cost):
+    """Mixed-length workload (BASELINE cfg 5): every (length, n_decoys) request is cut into k_L nearly equal batches of at most
+    `replica_per_batch` decoys and the batches are assigned to ranks by longest-processing-time-first on `cost(L, b)`.  The
+    piece counts k_L are chosen to minimise the plan's makespan (every combination for a handful of length classes, one class
+    at a time otherwise): a long class is spread over as many ranks as its share of the work, a short one stays in ONE large
+    batch instead of an even (and inefficiently small) share per rank.  Returns one list of (L, B) batches per rank.
     Lengths are never padded against each other: each batch runs un-padded at its own L, which is also what defines
     the reference result for this configuration."""
-    batches = []
-    for L, n in counts.items():
-        share = max(1, -(-n // world))
-        while n > 0:
-            b = min(replica_per_batch, share, n)
-            batches.append((L, b))
-            n -= b
-    batches.sort(key=lambda lb: -(lb[1] * lb[0] ** 2))
-    load = [0] * world
-    plan = [[] for _ in range(world)]
-    for L, b in batches:
-        r = min(range(world), key=lambda k: load[k])
-        plan[r].append((L, b))
-        load[r] += b * L * L
-    return plan
+    def pieces(k):
+        out = []
+        for L, n in counts.items():
+            base, rem = divmod(n, k[L])
+            out += [(L, base + (1 if i < rem else 0)) for i in range(k[L]) if base + (1 if i < rem else 0) > 0]
+        return out
+
+    def lpt(batches):
+        load = [0.0] * world
+        plan = [[] for _ in range(world)]
+        for L, b in sorted(batches, key=lambda lb: -cost(*lb)):
+            r = min(range(world), key=lambda q: load[q])
+            plan[r].append((L, b))
+            load[r] += cost(L, b)
+        return max(load), plan
+
+    counts = {L: n for L, n in counts.items() if n > 0}
+    kmin = {L: max(1, -(-n // replica_per_batch)) for L, n in counts.items()}
+    kmax = {L: min(n, kmin[L] + world - 1) for L, n in counts.items()}
+    n_combos = 1
+    for L in counts:
+        n_combos *= kmax[L] - kmin[L] + 1
+    if n_combos <= 20000:  # few length classes (cfg 5 has four): try every combination of piece counts
+        import itertools
+
+        best, plan = None, None
+        for ks in itertools.product(*[range(kmin[L], kmax[L] + 1) for L in counts]):
+            m, p = lpt(pieces(dict(zip(counts, ks))))
+            if best is None or m < best * (1.0 - 1e-9):
+                best, plan = m, p
+        return plan
+    k = dict(kmin)  # many classes: raise one piece count at a time while that shortens the makespan
+    best, plan = lpt(pieces(k))
+    while True:
+        cand = None
+        for L in counts:
+            if k[L] < kmax[L]:
+                k2 = dict(k)
+                k2[L] += 1
+                m, p = lpt(pieces(k2))
+                if m < best * (1.0 - 1e-9) and (cand is None or m < cand[0]):
+                    cand = (m, p, k2)
+        if cand is None:
+            return plan
+        best, plan, k = cand
 
 
 def shard_bounds(n: int, world: int):

@@ -98,14 +98,24 @@ def test_shard_bounds():
 
 
 def test_mixed_length_plan_is_balanced():
-    from str2str_b200.sampler import plan_mixed_lengths
+    from str2str_b200.sampler import batch_cost, plan_mixed_lengths
 
-    plan = plan_mixed_lengths({64: 64, 128: 64, 256: 64, 384: 64}, world=8, replica_per_batch=16)  # BASELINE cfg 5
-    assert len(plan) == 8
-    flat = [lb for r in plan for lb in r]
-    assert sum(b for L, b in flat if L == 384) == 64 and sum(b for _, b in flat) == 256
-    loads = [sum(b * L * L for L, b in r) for r in plan]
-    assert max(loads) <= 1.25 * (sum(loads) / 8)  # LPT keeps ranks within 25 % of the mean cost
+    counts = {64: 64, 128: 64, 256: 64, 384: 64}  # BASELINE cfg 5
+    for world, cap in ((8, 64), (8, 16), (4, 64), (2, 64), (1, 64)):
+        plan = plan_mixed_lengths(counts, world=world, replica_per_batch=cap)
+        assert len(plan) == world
+        flat = [lb for r in plan for lb in r]
+        for L, n in counts.items():
+            assert sum(b for l2, b in flat if l2 == L) == n
+        assert all(0 < b <= cap for _, b in flat)
+        loads = [sum(batch_cost(L, b) for L, b in r) for r in plan]
+        assert max(loads) <= 1.15 * (sum(loads) / world), (world, cap, plan)  # within 15 % of the mean modelled time
+    # one GPU: a class is never cut below the batch cap (every extra batch pays the per-iteration latency floor again)
+    assert plan_mixed_lengths(counts, world=1) == [[(384, 64), (256, 64), (128, 64), (64, 64)]]
+    # eight GPUs: the long class is spread over several ranks, the short ones stay whole (an even share per rank would be
+    # 8 decoys of each class per rank: measured 851 ms per job on 8 B200s against 696 ms for this plan's slowest rank)
+    p8 = plan_mixed_lengths(counts, world=8)
+    assert sorted(b for r in p8 for L, b in r if L == 64) == [64] and len([1 for r in p8 for L, b in r if L == 384]) >= 4
     assert plan_mixed_lengths({64: 3}, world=2, replica_per_batch=2) in ([[(64, 2)], [(64, 1)]], [[(64, 1)], [(64, 2)]])
 
 
