@@ -118,6 +118,9 @@ struct s2s_ctx {
   std::map<std::string, std::pair<const float*, int64_t>> params;
   bool finalized = false;
   int opt_pair = 1, opt_node = 1, opt_ipa = 1, opt_table = 1, opt_et_pair = 1;
+  int opt_fork = 1;   // few residue rows: independent kernels of a block run on a side stream (Fork below); S2S_FORK=0 disables
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork[4] = {}, ev_join[4] = {};
   int opt_chain = 1;  // row-local layers of the node track fused into gemm_chain launches: 0 never, 1 when the row panels outnumber half the SMs, 2 always (do_trunk)
   int tfm_passes = 1;  // sequence-transformer in_proj + attention GEMMs: 1 = single bf16 (default; trajectory error unchanged, tools/traj_parity.py), 3 = split-bf16 (S2S_TFM_PASSES=3)
   int wimg_copies = 8;  // replicated EdgeTransition weight images (set S2S_WIMG_COPIES to override)
@@ -180,6 +183,38 @@ struct PrecScope {
 };
 
 struct Split { bf16* hi = nullptr; bf16* lo = nullptr; };  // split-bf16 image of an fp32 activation (dense, pitch = width)
+
+// A few launches on the context's side stream, concurrent with what follows on `st` until join().  With few residue rows a kernel
+// occupies a fraction of the SMs and the forward is a chain of launch latencies (~10 us per dependent tensor-core GEMM), so kernels
+// that do not depend on each other — the q|k|v projection and the point projection, P.v and P.v_pts, the per-residue
+// EdgeTransition terms, the frame update — overlap instead.  Event record / wait pairs: legal under CUDA-graph capture, where
+// they become parallel branches of the graph.  Off (everything on `st`) when the kernels fill the GPU anyway.
+struct Fork {
+  s2s_ctx* c;
+  cudaStream_t st;
+  int slot;
+  bool on;
+  Fork(s2s_ctx* ctx, cudaStream_t main, int slot_, bool enable) : c(ctx), st(main), slot(slot_), on(enable && ctx->opt_fork && ctx->side && !g_profile_on) {
+    if (on) {
+      S2S_CUDA(cudaEventRecord(c->ev_fork[slot], st));
+      S2S_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork[slot], 0));
+    }
+  }
+  cudaStream_t stream() const { return on ? c->side : st; }
+  void join() {
+    if (!on) return;
+    on = false;
+    S2S_CUDA(cudaEventRecord(c->ev_join[slot], c->side));
+    S2S_CUDA(cudaStreamWaitEvent(st, c->ev_join[slot], 0));
+  }
+  ~Fork() {
+    if (on) {  // error path: never leave the side stream detached from a capture
+      cudaEventRecord(c->ev_join[slot], c->side);
+      cudaStreamWaitEvent(st, c->ev_join[slot], 0);
+    }
+  }
+};
+bool few_rows(int R) { return 2 * ceil_div(R, 128) <= sm_count(); }
 
 // bf16 (hi, lo) image of a weight (or of a sub-block of one) registered at finalize
 std::pair<const bf16*, const bf16*> weight_split(const s2s_ctx* c, const float* W) {
@@ -514,13 +549,22 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   const std::string ip = "translator.trunk.ipa_" + std::to_string(blk) + ".";
   const bool tc = c->opt_node == 1 && L % 16 == 0;
   const float qk_scale = 0.03608439182435161f;  // sqrt(1 / (3 * 256))   (ipa.py:187)
+  // second-generation path: point term folded into the logits GEMM, tcgen05 pair kernel, split-bf16 P
+  const bool fused = tc && c->opt_ipa == 1 && ipa_pair_attention_tc_supported(L);
+  IpaPointsAug aug;
+  if (fused) {
+    aug.qp_aug = c->qp_aug; aug.kp_aug = c->kp_aug; aug.colbias = c->colbias; aug.vp_hi = c->vp_hi; aug.vp_lo = c->vp_lo;
+    aug.pt_w = w.pt_w; aug.inv_alpha = 1.f / qk_scale; aug.L = L;
+  }
+  if (tc && !node_sp.hi) {
+    split_bf16(node, 256, R, 256, c->sa_hi, c->sa_lo, st);
+    node_sp.hi = c->sa_hi; node_sp.lo = c->sa_lo;
+  }
+  // few rows: the point projection and the rigid apply run beside the q | k | v projection (they meet at the logits GEMM)
+  Fork pts(c, st, 0, fused && few_rows(R));
   if (tc) {
     // q | k | v projection in one bf16 tensor-core GEMM whose epilogue writes the attention operands directly:
     // row-major bf16 q,k (K-major for q.k^T) and the transposed v (K-major for P.v); no fp32 copy is needed.
-    if (!node_sp.hi) {
-      split_bf16(node, 256, R, 256, c->sa_hi, c->sa_lo, st);
-      node_sp.hi = c->sa_hi; node_sp.lo = c->sa_lo;
-    }
     const auto ws = weight_split(c, w.proj_w);
     TcGemm g;
     g.A_hi = node_sp.hi; g.a_rows = R; g.a_cols = 256; g.a_pitch = 256;
@@ -534,18 +578,12 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
     p.B_hi = ws.first + (size_t)6144 * 256; p.B_lo = ws.second + (size_t)6144 * 256; p.b_rows = 672; p.b_cols = 256; p.b_pitch = 256;
     p.M = R; p.N = 672; p.K = 256; p.passes = 3; p.bias = w.proj_b + 6144;
     p.C = c->proj + 6144; p.ldc = 6816;
-    gemm_tc(p, st);
+    gemm_tc(p, pts.stream());
   } else {
     linear(c, node, 256, w.proj_w, 256, w.proj_b, c->proj, 6816, R, 6816, 256, st, 0, nullptr, 0, nullptr, nullptr, EXACT);
   }
-  // second-generation path: point term folded into the logits GEMM, tcgen05 pair kernel, split-bf16 P
-  const bool fused = tc && c->opt_ipa == 1 && ipa_pair_attention_tc_supported(L);
-  IpaPointsAug aug;
-  if (fused) {
-    aug.qp_aug = c->qp_aug; aug.kp_aug = c->kp_aug; aug.colbias = c->colbias; aug.vp_hi = c->vp_hi; aug.vp_lo = c->vp_lo;
-    aug.pt_w = w.pt_w; aug.inv_alpha = 1.f / qk_scale; aug.L = L;
-  }
-  ipa_points(c->proj + 6144, 6816, c->proj + 6336, 6816, quat, trans, c->q_pts, c->k_pts, c->v_pts, R, st, aug);
+  ipa_points(c->proj + 6144, 6816, c->proj + 6336, 6816, quat, trans, c->q_pts, c->k_pts, c->v_pts, R, pts.stream(), aug);
+  pts.join();
   if (tc) {  // S = scale * q.k^T, batched over (decoy, head)
     TcGemm g;
     g.A_hi = c->qkv_bf16; g.a_rows = R; g.a_cols = 6144; g.a_pitch = 6144; g.a_rb = L; g.a_ch = 256;
@@ -579,6 +617,8 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
   const long pair_col = N_H * C_H + 4 * N_H * P_V;
   if (fused) { p.opair_hi = c->sa_hi + pair_col; p.opair_lo = c->sa_lo + pair_col; }
   if (fused) ipa_pair_attention_tc(p, st); else ipa_pair_attention(p, st);
+  // few rows: P.v_pts and the back-rotation of its result run beside P.v (they meet at linear_out)
+  Fork vpts(c, st, 1, fused && few_rows(R));
   if (tc) {  // o = P v -> feats[:, h*256 + c]
     TcGemm g;
     g.A_hi = c->P_bf16; g.a_rows = (size_t)B * N_H * L; g.a_cols = L; g.a_pitch = L; g.a_rb = N_H * L; g.a_rh = L;
@@ -594,7 +634,7 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
     g.B_hi = c->vp_hi; g.B_lo = c->vp_lo; g.b_rows = R; g.b_cols = N_H * VP_PITCH; g.b_pitch = N_H * VP_PITCH; g.b_rb = L; g.b_ch = VP_PITCH; g.b_mn = 1;  // row-major value points
     g.M = L; g.N = P_V * 3; g.K = L; g.nb = B; g.nh = N_H; g.passes = 3;
     g.C = c->opt; g.ldc = N_H * P_V * 3; g.sCb = (long)L * N_H * P_V * 3; g.sCh = P_V * 3;
-    gemm_tc(g, st);
+    gemm_tc(g, vpts.stream());
   } else {
     GemmArgs g;
     g.A = c->S; g.lda = L; g.sAb = (long)N_H * L * L; g.sAh = (long)L * L;
@@ -610,7 +650,8 @@ void do_ipa(s2s_ctx* c, int blk, int B, int L, const float* node, const bf16* z,
     g.N = P_V * 3;
     gemm_f32(g, st);
   }
-  ipa_finalize_points(c->opt, quat, trans, c->feats, R, st, fused ? c->sa_hi : nullptr, fused ? c->sa_lo : nullptr);
+  ipa_finalize_points(c->opt, quat, trans, c->feats, R, vpts.stream(), fused ? c->sa_hi : nullptr, fused ? c->sa_lo : nullptr);
+  vpts.join();
   static const int splitk_env = [] { const char* e = getenv("S2S_SPLITK"); return e ? atoi(e) : 1; }();  // 0: A/B timing
   if (fused && splitk_env && 2 * ceil_div(R, 128) <= sm_count()) {
     // few residue rows: linear_out's reduction over the 2688 features is cut into nine slices that run on different SMs
@@ -643,8 +684,10 @@ void do_edge_transition(s2s_ctx* c, int blk, int B, int L, const float* node, co
   if (!prep_done) {
     linear(c, node, 256, c->P(e + "initial_embed.weight"), 256, c->P(e + "initial_embed.bias"), c->nprime, 128, R, 128, 256, st, 0,
            nullptr, 0, nullptr, nullptr, -1, node_sp, np);
+    Fork pf(c, st, 3, np.hi != nullptr && few_rows(R));  // few rows: the two per-residue terms side by side
+    linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, pf.stream(), 0, nullptr, 0, nullptr, nullptr, -1, np);
     linear(c, c->nprime, 128, W1 + 128, 384, c->P(e + "trunk.0.bias"), c->u384, 384, R, 384, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
-    linear(c, c->nprime, 128, Wf + 128, 384, c->P(e + "final_layer.bias"), c->p128, 128, R, 128, 128, st, 0, nullptr, 0, nullptr, nullptr, -1, np);
+    pf.join();
   }
   if (tc) {  // the n'_j terms ride along as extra K columns of the MMAs: they need n' in bf16 (= the hi image)
     if (!np.hi) f32_to_bf16(c->nprime, c->nprime_bf16, (long)R * 128, st);
@@ -857,8 +900,11 @@ void do_trunk(s2s_ctx* c, int B, int L, const float* rigids_t, const float* rmas
       layernorm(c->a256, nullptr, c->P(nt + "ln.weight"), c->P(nt + "ln.bias"), rmask, c->node, R, 256, st, node_sp.hi, node_sp.lo);
     }
     // backbone update on node * diffuse_mask, exact fp32    (ipa.py:367-369)
-    bb_update_frame(c->node, c->P(tk + "bb_update_" + s + ".linear.weight"), c->P(tk + "bb_update_" + s + ".linear.bias"), c->quat, c->trans, c->diffuse, R, st);
+    // (few rows: beside the EdgeTransition's per-residue GEMMs, which read the same node rows and nothing the update writes)
+    Fork bb(c, st, 2, img && few_rows(R) && b < N_BLK - 1);
+    bb_update_frame(c->node, c->P(tk + "bb_update_" + s + ".linear.weight"), c->P(tk + "bb_update_" + s + ".linear.bias"), c->quat, c->trans, c->diffuse, R, bb.stream());
     if (b < N_BLK - 1) do_edge_transition(c, b, B, L, c->node, c->z, rmask, c->z, st, node_sp, chain && c->opt_pair >= 1);
+    bb.join();
   }
   if (!chain) {
     linear(c, c->node, 256, c->P(tp + "linear_1.weight"), 256, c->P(tp + "linear_1.bias"), c->a256, 256, R, 256, 256, st, 1, nullptr, 0, nullptr, nullptr, -1, node_sp, a_sp);
@@ -951,6 +997,12 @@ s2s_ctx* s2s_create(const float* tfreq, const float* pdenom, const float* bin_lo
     if (const char* e = getenv("S2S_TFM_PASSES")) c->tfm_passes = atoi(e) == 3 ? 3 : 1;
     if (const char* e = getenv("S2S_ET_PAIR")) c->opt_et_pair = atoi(e) != 0;
     if (const char* e = getenv("S2S_CHAIN")) c->opt_chain = std::max(0, std::min(2, atoi(e)));  // A/B timing; s2s_set_option("chain") overrides
+    if (const char* e = getenv("S2S_FORK")) c->opt_fork = atoi(e) != 0;
+    S2S_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; ++k) {
+      S2S_CUDA(cudaEventCreateWithFlags(&c->ev_fork[k], cudaEventDisableTiming));
+      S2S_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
     auto up = [&](const float* h, size_t n) {
       float* d;
       S2S_CUDA(cudaMalloc(&d, n * 4));
@@ -966,6 +1018,11 @@ s2s_ctx* s2s_create(const float* tfreq, const float* pdenom, const float* bin_lo
 void s2s_destroy(s2s_ctx* c) {
   if (!c) return;
   c->ws.release(); c->wslab.release();
+  if (c->side) cudaStreamDestroy(c->side);
+  for (int k = 0; k < 4; ++k) {
+    if (c->ev_fork[k]) cudaEventDestroy(c->ev_fork[k]);
+    if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+  }
   cudaFree(c->tfreq); cudaFree(c->pdenom); cudaFree(c->bin_lower); cudaFree(c->backbone);
   delete c;
 }
