@@ -40,7 +40,7 @@ constexpr int NPART = NEW / 4;
 constexpr int CW = 128 / NPART;
 constexpr int ET5_THREADS = 64 + 32 * NEW;
 constexpr int NSEG = 4;
-constexpr int VEC_FLOATS = NSEG * (D_ET + C_Z) + D_ET + C_Z + C_Z + 2 * NPART * 128;
+constexpr int VEC_FLOATS = 2 * NSEG * (D_ET + C_Z) + D_ET + C_Z + C_Z + 2 * NPART * 128;  // u / p vectors double-buffered by tile parity
 constexpr int OFF_BAR = OFF_VEC + VEC_FLOATS * 4;
 // barriers: w_full[NSTAGE] w_empty[NSTAGE] a0_full a0_empty fullE full2 fullF emptyE empty2 h1p[3] h2p[3]
 // (w_full, a0_full, emptyE, empty2, h1p, h2p are used in the leader CTA only)
@@ -142,9 +142,9 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
                             const __grid_constant__ CUtensorMap tmap_w, Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
-  float* u_s = reinterpret_cast<float*>(smem + OFF_VEC);  // [NSEG][D_ET]
-  float* p_s = u_s + NSEG * D_ET;                         // [NSEG][C_Z]
-  float* b2_s = p_s + NSEG * C_Z;
+  float* u_s = reinterpret_cast<float*>(smem + OFF_VEC);  // [2][NSEG][D_ET]: per-residue layer-1 terms of this / the next tile
+  float* p_s = u_s + 2 * NSEG * D_ET;                     // [2][NSEG][C_Z]: per-residue final-layer terms
+  float* b2_s = p_s + 2 * NSEG * C_Z;
   float* lnw_s = b2_s + D_ET;
   float* lnb_s = lnw_s + C_Z;
   float* red_s = lnb_s + C_Z;  // [2 stats][NPART column parts][128 rows]
@@ -351,36 +351,64 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
         mbar_arrive_cluster(bar_b);
       }
     };
-    for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid) {
-      const int tile = 2 * pt + (int)crank;
+    // The per-residue vectors u_i / p_i and the row's edge mask of tile t + 1 are fetched from global memory while tile t is
+    // being processed and parked in the other half of u_s / p_s: between two tiles the epilogue warps then meet on ONE named
+    // barrier and start on the (already finished) first accumulator at once.  Before, every tile began with barrier - global
+    // loads - barrier, ~1.5 k cycles of exposed latency per tile with the tensor pipe waiting for its accumulators to drain
+    // (ncu source page: 13 % of the kernel's stall samples on the index arithmetic and loads of that prologue).
+    constexpr int NU = FLAT ? (NSEG * D_ET + 32 * NEW - 1) / (32 * NEW) : 1;
+    float un[NU], pn = 0.f, m_next = 0.f;
+    auto fetch = [&](int tile) {  // this thread's share of the vectors of `tile`, and its row's mask, into registers
       int bi, jr;
       if constexpr (FLAT) {
         const long f = (long)tile * TM + r;
         bi = (int)(f / a.L);
         jr = (int)(f - (long)bi * a.L);
+#pragma unroll
+        for (int k = 0; k < NU; ++k) {
+          const int c = et + k * 32 * NEW;
+          const int sg = c / D_ET;
+          un[k] = c < NSEG * D_ET ? a.u[(size_t)(((long)tile * TM + sg * 32) / a.L) * D_ET + (c - sg * D_ET)] : 0.f;
+        }
+        const int sg = et / C_Z;
+        pn = a.p[(size_t)(((long)tile * TM + sg * 32) / a.L) * C_Z + (et - sg * C_Z)];
       } else {
         bi = tile / tiles_per_i;
         jr = (tile % tiles_per_i) * TM + r;
+        un[0] = et < D_ET ? a.u[(size_t)bi * D_ET + et] : 0.f;
+        pn = et < C_Z ? a.p[(size_t)bi * C_Z + et] : 0.f;
       }
       const int b = bi / a.L;
-      named_bar_sync(1, 32 * NEW);
+      m_next = a.mask[bi] * a.mask[(size_t)b * a.L + jr];
+    };
+    auto stash = [&](uint32_t buf) {  // ... and from the registers into half `buf` of the shared-memory vectors
+      float* ud = u_s + buf * NSEG * D_ET;
+      float* pd = p_s + buf * NSEG * C_Z;
       if constexpr (FLAT) {
-        for (int c = et; c < NSEG * D_ET; c += 32 * NEW) {
-          const int sg = c / D_ET;
-          u_s[c] = a.u[(size_t)(((long)tile * TM + sg * 32) / a.L) * D_ET + (c - sg * D_ET)];
-        }
-        {
-          const int sg = et / C_Z;
-          p_s[et] = a.p[(size_t)(((long)tile * TM + sg * 32) / a.L) * C_Z + (et - sg * C_Z)];
-        }
+#pragma unroll
+        for (int k = 0; k < NU; ++k)
+          if (et + k * 32 * NEW < NSEG * D_ET) ud[et + k * 32 * NEW] = un[k];
+        pd[et] = pn;
       } else {
-        for (int c = et; c < D_ET; c += 32 * NEW) u_s[c] = a.u[(size_t)bi * D_ET + c];
-        if (et < C_Z) p_s[et] = a.p[(size_t)bi * C_Z + et];
+        if (et < D_ET) ud[et] = un[0];
+        if (et < C_Z) pd[et] = pn;
       }
+    };
+    if (pair_id < n_pair_tiles) {
+      fetch(2 * pair_id + (int)crank);
+      stash(0);
+    }
+    uint32_t it = 0;
+    for (int pt = pair_id; pt < n_pair_tiles; pt += n_pairs_grid, ++it) {
+      const int tile = 2 * pt + (int)crank;
+      // half it & 1 is complete (written during the previous tile or just above) and every warp has left the previous tile,
+      // whose half may now be overwritten
       named_bar_sync(1, 32 * NEW);
-      const float* u_q = FLAT ? u_s + q * D_ET : u_s;
-      const float* p_q = FLAT ? p_s + q * C_Z : p_s;
-      const float m = a.mask[bi] * a.mask[(size_t)b * a.L + jr];
+      const float m = m_next;
+      const bool more = pt + n_pairs_grid < n_pair_tiles;
+      if (more) fetch(2 * (pt + n_pairs_grid) + (int)crank);  // in flight during layer 1
+      const float* u_q = u_s + (it & 1) * NSEG * D_ET + (FLAT ? q * D_ET : 0);
+      const float* p_q = p_s + (it & 1) * NSEG * C_Z + (FLAT ? q * C_Z : 0);
       float y[CW];
       auto wait_full = [&](uint64_t* bar, uint32_t& n) {
         mbar_wait(bar, n & 1);
@@ -413,6 +441,7 @@ edge_transition_pair_kernel(const __grid_constant__ CUtensorMap tmap_z, const __
         store_packed(COL_H1 + nc * 64 + part * (CW / 2));
         hand_over(nc == 1 ? empty2_l : emptyE_l, h1p_l + nc * 8);
       }
+      if (more) stash((it + 1) & 1);
       // ---- layer 2: + b2, relu, pack, in place (chunks 1, 2) or into the spare strip (chunk 0) ----
       for (int c = 0; c < 3; ++c) {
         const uint32_t base = c == 1 ? 0u : 128u;
