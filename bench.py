@@ -169,7 +169,7 @@ def algorithmic(B, L):
                 edge_embed=("tensor", ee_flops, rows * 128 * 2, {}))
 
 
-NCU_CAPTURE = "r02g_ncu_full_summary.csv"  # `ncu --set full --clock-control none` of tools/profile_forward.py 64 256 1, condensed by tools/ncu_summary.py
+NCU_CAPTURE = "r02h_ncu_full_summary.csv"  # `ncu --set full --clock-control none` of tools/profile_forward.py 64 256 1, condensed by tools/ncu_summary.py
 
 
 def ncu_traffic(B, L):
