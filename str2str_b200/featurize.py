@@ -228,19 +228,20 @@ def atom37_to_frames(aatype: torch.Tensor, pos: torch.Tensor, mask: torch.Tensor
     The reference's two composes with sign-flip rotations are column sign flips: group 0 negates the x and z axes
     (:840-846), an ambiguous group's alternative frame negates y and z (:859-880)."""
     aatype = aatype.clamp(max=20)
-    base = torch.as_tensor(GROUP_BASE_ATOMS)[aatype]                                  # [L,8,3] atom37 indices
+    dev = pos.device  # every table lookup / index below lives on the device of the inputs: the same code featurises on the GPU
+    base = torch.as_tensor(GROUP_BASE_ATOMS, device=dev)[aatype]                      # [L,8,3] atom37 indices
     L = aatype.shape[0]
-    ar = torch.arange(L)[:, None, None]
+    ar = torch.arange(L, device=dev)[:, None, None]
     p = pos[ar, base]                                                                  # [L,8,3,3]
     R, t = _frames_from_3_points(p[..., 0, :], p[..., 1, :], p[..., 2, :], eps)
     R, t = R.float(), t.float()                                                        # Rigid forces fp32
-    flip0 = torch.ones(8, 3)
+    flip0 = torch.ones(8, 3, device=dev)
     flip0[0, 0] = flip0[0, 2] = -1.0
     R = R * flip0[None, :, None, :]
-    group_exists = torch.as_tensor(GROUP_MASK, dtype=mask.dtype)[aatype]
+    group_exists = torch.as_tensor(GROUP_MASK, dtype=mask.dtype, device=dev)[aatype]
     gt_exists = mask[ar, base].min(-1)[0] * group_exists
-    amb = torch.as_tensor(GROUP_AMBIGUOUS, dtype=mask.dtype)[aatype]                  # [L,8]
-    alt_sign = torch.ones(L, 8, 3)
+    amb = torch.as_tensor(GROUP_AMBIGUOUS, dtype=mask.dtype, device=dev)[aatype]      # [L,8]
+    alt_sign = torch.ones(L, 8, 3, device=dev)
     alt_sign[..., 1:] = (1.0 - 2.0 * amb.float())[..., None]
     return {"rigidgroups_gt_frames": _to_4x4(R, t), "rigidgroups_gt_exists": gt_exists, "rigidgroups_group_exists": group_exists,
             "rigidgroups_group_is_ambiguous": amb, "rigidgroups_alt_gt_frames": _to_4x4(R * alt_sign[..., None, :], t)}
@@ -253,18 +254,19 @@ def atom37_to_torsion_angles(aatype: torch.Tensor, pos: torch.Tensor, mask: torc
     L = aatype.shape[0]
     prev_pos = torch.cat([pos.new_zeros(1, 37, 3), pos[:-1]], 0)
     prev_mask = torch.cat([mask.new_zeros(1, 37), mask[:-1]], 0)
-    quad = torch.empty(L, 7, 4, 3, dtype=pos.dtype)
+    dev = pos.device
+    quad = torch.empty(L, 7, 4, 3, dtype=pos.dtype, device=dev)
     quad[:, 0] = torch.cat([prev_pos[:, 1:3], pos[:, :2]], 1)                          # CA-, C-, N, CA
     quad[:, 1] = torch.cat([prev_pos[:, 2:3], pos[:, :3]], 1)                          # C-, N, CA, C
     quad[:, 2] = torch.cat([pos[:, :3], pos[:, 4:5]], 1)                               # N, CA, C, O
-    chi_idx = torch.as_tensor(CHI_ATOM_IDX)[aatype]                                    # [L,4,4]
-    ar = torch.arange(L)[:, None, None]
+    chi_idx = torch.as_tensor(CHI_ATOM_IDX, device=dev)[aatype]                        # [L,4,4]
+    ar = torch.arange(L, device=dev)[:, None, None]
     quad[:, 3:] = pos[ar, chi_idx]
-    tmask = torch.empty(L, 7, dtype=mask.dtype)
+    tmask = torch.empty(L, 7, dtype=mask.dtype, device=dev)
     tmask[:, 0] = prev_mask[:, 1] * prev_mask[:, 2] * mask[:, 0] * mask[:, 1]
     tmask[:, 1] = prev_mask[:, 2] * (mask[:, 0] * mask[:, 1] * mask[:, 2])
     tmask[:, 2] = (mask[:, 0] * mask[:, 1] * mask[:, 2]) * mask[:, 4]
-    tmask[:, 3:] = torch.as_tensor(CHI_MASK, dtype=mask.dtype)[aatype] * mask[ar, chi_idx].prod(-1)
+    tmask[:, 3:] = torch.as_tensor(CHI_MASK, dtype=mask.dtype, device=dev)[aatype] * mask[ar, chi_idx].prod(-1)
     R, t = _frames_from_3_points(quad[..., 1, :], quad[..., 2, :], quad[..., 0, :], 1e-8)
     R, t = R.float(), t.float()
     # Rigid.invert() in fp32 (R^T, -(R^T t)), applied to the fp64 fourth atom (promotion), rigid_utils.py:1135-1145
@@ -275,28 +277,28 @@ def atom37_to_torsion_angles(aatype: torch.Tensor, pos: torch.Tensor, mask: torc
     sc = torch.stack([rel[..., 2], rel[..., 1]], -1)
     sc = sc / torch.sqrt((sc * sc).sum(-1, keepdim=True) + 1e-8)
     sc = sc * sc.new_tensor([1.0, 1.0, -1.0, 1.0, 1.0, 1.0, 1.0])[None, :, None]
-    mirror = torch.cat([mask.new_ones(L, 3), 1.0 - 2.0 * torch.as_tensor(CHI_PI_PERIODIC, dtype=sc.dtype)[aatype]], -1)
+    mirror = torch.cat([mask.new_ones(L, 3), 1.0 - 2.0 * torch.as_tensor(CHI_PI_PERIODIC, dtype=sc.dtype, device=dev)[aatype]], -1)
     return {"torsion_angles_sin_cos": sc, "alt_torsion_angles_sin_cos": sc * mirror[..., None], "torsion_angles_mask": tmask}
 
 
 def pseudo_beta_and_atom14(aatype: torch.Tensor, pos: torch.Tensor, mask: torch.Tensor) -> Dict[str, torch.Tensor]:
     """Pseudo-beta (CB, CA for glycine; data_transforms.py:370-387) and the dense 14-atom view of the atom37 arrays with its
     renamed alternative for the residues whose atom names are interchangeable (:575-757)."""
-    L = aatype.shape[0]
+    L, dev = aatype.shape[0], pos.device
     is_gly = aatype == RESNAME_TO_IDX["GLY"]
     ca, cb = ATOM_ORDER["CA"], ATOM_ORDER["CB"]
     out = {"pseudo_beta": torch.where(is_gly[:, None], pos[:, ca], pos[:, cb]), "pseudo_beta_mask": torch.where(is_gly, mask[:, ca], mask[:, cb])}
-    a14_to_37 = torch.as_tensor(ATOM14_TO_37)[aatype]
-    exists14 = torch.as_tensor(ATOM14_MASK)[aatype]
-    ar = torch.arange(L)[:, None]
+    a14_to_37 = torch.as_tensor(ATOM14_TO_37, device=dev)[aatype]
+    exists14 = torch.as_tensor(ATOM14_MASK, device=dev)[aatype]
+    ar = torch.arange(L, device=dev)[:, None]
     gt_exists = exists14 * mask[ar, a14_to_37]
     gt_pos = gt_exists[..., None] * pos[ar, a14_to_37]
-    rename = torch.as_tensor(ATOM14_RENAME, dtype=mask.dtype)[aatype]
+    rename = torch.as_tensor(ATOM14_RENAME, dtype=mask.dtype, device=dev)[aatype]
     out.update({
-        "atom14_atom_exists": exists14, "residx_atom14_to_atom37": a14_to_37, "residx_atom37_to_atom14": torch.as_tensor(ATOM37_TO_14)[aatype],
-        "atom37_atom_exists": torch.as_tensor(ATOM37_MASK)[aatype], "atom14_gt_exists": gt_exists, "atom14_gt_positions": gt_pos,
+        "atom14_atom_exists": exists14, "residx_atom14_to_atom37": a14_to_37, "residx_atom37_to_atom14": torch.as_tensor(ATOM37_TO_14, device=dev)[aatype],
+        "atom37_atom_exists": torch.as_tensor(ATOM37_MASK, device=dev)[aatype], "atom14_gt_exists": gt_exists, "atom14_gt_positions": gt_pos,
         "atom14_alt_gt_positions": torch.einsum("rac,rab->rbc", gt_pos, rename), "atom14_alt_gt_exists": torch.einsum("ra,rab->rb", gt_exists, rename),
-        "atom14_atom_is_ambiguous": torch.as_tensor(ATOM14_AMBIGUOUS, dtype=mask.dtype)[aatype],
+        "atom14_atom_is_ambiguous": torch.as_tensor(ATOM14_AMBIGUOUS, dtype=mask.dtype, device=dev)[aatype],
     })
     return out
 
@@ -306,7 +308,10 @@ class ProteinFeatureTransform:
     order of operations in `__call__` (:49-68)."""
 
     def __init__(self, unit: Optional[str] = "angstrom", truncate_length: Optional[int] = None, strip_missing_residues: bool = True,
-                 recenter_and_scale: bool = True, eps: float = 1e-8):
+                 recenter_and_scale: bool = True, eps: float = 1e-8, device=None):
+        """`device` (not a reference key): where the geometric features (frames, torsions, pseudo-beta, atom14 views) are
+        computed and returned, e.g. "cuda" to featurise straight into the sampler's device; None = CPU like the reference."""
+        self.device = device
         if unit == "angstrom":
             self.coordinate_scale = 1.0
         elif unit in ("nm", "nanometer"):
@@ -335,6 +340,8 @@ class ProteinFeatureTransform:
             centre = np.sum(f["atom_positions"][:, CA_IDX], axis=0) / (np.sum(f["seq_mask"]) + self.eps)
             f["atom_positions"] = (f["atom_positions"] - centre[None, None, :]) * self.coordinate_scale * f["atom_mask"][..., None]
         t = {k: torch.as_tensor(v) for k, v in f.items()}
+        if self.device is not None:
+            t = {k: v.to(self.device) for k, v in t.items()}
         t["aatype"] = t["aatype"].long()
         t["atom_positions"] = t["atom_positions"].double()
         t["atom_mask"] = t["atom_mask"].double()

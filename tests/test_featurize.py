@@ -46,6 +46,26 @@ def test_transform_matches_reference(path):
             assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= TOL, k
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[10:-4] for p in CASES])
+def test_transform_on_device_matches_reference(path):
+    """The same transform with device="cuda": every geometric feature is computed by batched torch ops on the GPU and lands
+    where the sampler needs it; same goldens of the unmodified reference, same tolerances."""
+    g = np.load(path)
+    kw = ast.literal_eval(str(g["transform_kwargs"]))
+    out = F.ProteinFeatureTransform(device="cuda", **kw)(F.parse_pdb_string(str(g["pdb_text"])))
+    keys = [k[4:] for k in g.files if k.startswith("out_")]
+    assert len(keys) == 34
+    for k in keys:
+        assert out[k].is_cuda, k
+        ref, got = g[f"out_{k}"], out[k].cpu().numpy()
+        assert got.shape == ref.shape and got.dtype == ref.dtype, (k, got.shape, ref.shape, got.dtype, ref.dtype)
+        if np.issubdtype(ref.dtype, np.integer) or k.endswith("mask") or k.endswith("exists") or k.endswith("ambiguous"):
+            assert np.array_equal(got, ref), k
+        else:
+            assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= TOL, k
+
+
 def _line(serial, name, resname, chain, resseq, xyz, icode=" ", altloc=" ", occ=1.0, rec="ATOM"):
     nm = name if len(name) == 4 else f" {name}"
     return (f"{rec:<6}{serial:>5} {nm:<4}{altloc}{resname:>3} {chain}{resseq:>4}{icode}   "
