@@ -175,6 +175,11 @@ def main():
         # BASELINE cfg 2's own size: L = 256, 100 denoising steps; two decoys with a padded tail
         trajectory(net, diffuser, "traj_L256_n100.npz", 2, 256, 100, 6, 0, 11)
         return
+    if mode == "traj512":
+        # BASELINE cfg 4's chain length (the long-chain IPA pair kernel, the unfused sequence-transformer attention): L = 512, one
+        # decoy with a padded tail, 6 denoising steps
+        trajectory(net, diffuser, "traj_L512_n6.npz", 1, 512, 6, 7, 0, 23)
+        return
     if mode == "prior":
         # FrameDiffuser.sample_prior (backward_only: true) with the draws it consumes captured: randn [B,L,3] (axis),
         # rand [B,L] (CPU generator, so3.py:262), randn [B,L,3] (translation, r3.py:37-38)

@@ -252,6 +252,13 @@ def test_trajectory_cfg2_size_vs_reference_golden(golden_dir, params):
     _run_traj(golden_dir, params, "traj_L256_n100.npz")
 
 
+def test_trajectory_cfg4_length_vs_reference_golden(golden_dir, params):
+    """BASELINE.json configs[3]'s chain length: 512 residues (the long-chain IPA pair kernel with its ring of key blocks, the
+    GEMM + softmax + GEMM sequence-transformer attention, flattened EdgeTransition tiles of 4 per i row), 6 denoise steps from the
+    trajectory of the UNMODIFIED reference (tests/golden/make_golden.py traj512)."""
+    _run_traj(golden_dir, params, "traj_L512_n6.npz")
+
+
 # ---- (c) stress fixture, teacher-forced --------------------------------------------------------------------------------
 def test_stress_fixture_teacher_forced_per_step(golden_dir):
     """final_scale = 0.1 (the reference's own fp32 noise floor exceeds 1e-4 on long trajectories there, so full
