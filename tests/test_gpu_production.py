@@ -671,3 +671,48 @@ def test_pdb_file_to_ensemble_pdb_pipeline_vs_oracle(params, tmp_path):
     err = np.abs(back["atom_positions"][:, :5] - a37_ref[0, :, :5].numpy()).max()
     print(f"PDB -> features -> sampler -> PDB: max |file - oracle| over N, CA, C, CB, O = {err:.2e} A")
     assert err < 3e-3
+
+
+# ---- mixed-length jobs on one rank (BASELINE cfg 5's execution path) ------------------------------------------------------
+def test_mixed_length_jobs_on_one_rank_vs_oracle(params):
+    """`plan_mixed_lengths` cuts a mixed-length request into (length, batch) jobs; one sampler (one engine, one CUDA graph per shape)
+    runs them back to back un-padded, as bench.py --workload cfg5 does on every rank.  Each job is compared with the CPU oracle's
+    trajectory from the same perturbed start, and the first job is repeated at the end: same bits as the first time, whatever
+    shapes the workspace and the graph cache have seen in between."""
+    from str2str_b200.rigid import Rigid
+    from str2str_b200.sampler import ForwardBackwardSampler, InferenceConfig, plan_mixed_lengths
+
+    n = 4
+    plan = plan_mixed_lengths({64: 3, 100: 2, 24: 2}, world=1, replica_per_batch=2)
+    jobs = plan[0]
+    assert sorted(jobs) == sorted([(64, 2), (64, 1), (100, 2), (24, 2)])
+    net = make_net(params)
+    d = make_diffuser()
+    smp = ForwardBackwardSampler(net, d, InferenceConfig(num_timesteps=2 * n, min_t=0.01), use_cuda_graph=True)
+
+    def run(L, b, seed):
+        feats = synthetic.make_features(1, L, seed=seed, n_pad=2, random_aatype=True)
+        q, x = synthetic.make_backbone(L, seed=seed)
+        g = torch.Generator().manual_seed(seed)
+        noise = (torch.randn(b, L, 3, generator=g), torch.rand(b, L, generator=g), torch.randn(b, L, 3, generator=g))
+        rt_ref = O.forward_marginal(O.quat_to_rotmat(q[None].repeat(b, 1, 1)), x[None].repeat(b, 1, 1), 0.5 * torch.ones(b),
+                                    synthetic.make_features(b, L, seed=seed, n_pad=2)["residue_mask"], *noise)
+        r0 = Rigid.from_tensor_7(torch.cat([q, x], -1)[None].repeat(b, 1, 1).cuda(), normalize_quats=True)
+        _, fin, _ = smp.forward_backward(cuda(feats), r0, 0.5, rigids_t=rt_ref.cuda(), return_rigids=True)
+        return fin.cpu(), rt_ref
+
+    first = None
+    for k, (L, b) in enumerate(jobs + [jobs[0]]):
+        seed = 50 + (k % len(jobs))
+        fin, rt_ref = run(L, b, seed)
+        if k == 0:
+            first = fin.clone()
+        if k == len(jobs):
+            assert torch.equal(fin, first), "a repeated job must reproduce its first run bit for bit"
+            continue
+        featsB = synthetic.make_features(b, L, seed=seed, n_pad=2, random_aatype=True)
+        fin_ref, _, _ = O.forward_backward(params, featsB, rt_ref, 0.5, 2 * n)
+        valid = featsB["residue_mask"].bool()
+        r = rel(fin[..., 4:][valid], fin_ref[..., 4:][valid])
+        print(f"mixed-length job L={L} B={b}: C-alpha rel vs oracle {r:.2e}")
+        assert r < 1e-4
