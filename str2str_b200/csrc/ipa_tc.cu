@@ -34,8 +34,8 @@ struct P2Layout {
   static constexpr int STAGE = Z_BYTES + SP_BYTES;
   static constexpr int OFF_WB = 2 * STAGE;                // linear_b image: 2 blocks [16 rows x 64 ch]
   static constexpr int OFF_WDZ = OFF_WB + 4096;           // down_z weight, [128][32] fp32
-  static constexpr int OFF_ZS = OFF_WDZ + C_Z * 32 * 4;   // [2 groups][8][ZS_PITCH] fp32
-  static constexpr int OFF_RED = OFF_ZS + 2 * 8 * ZS_PITCH * 4;  // [2 groups][2][4 warps][8]
+  static constexpr int OFF_ZS = OFF_WDZ + C_Z * 32 * 4;   // [2 groups][2 queries of a slab][8][ZS_PITCH] fp32
+  static constexpr int OFF_RED = OFF_ZS + 2 * 2 * 8 * ZS_PITCH * 4;  // [2 groups][2][4 warps][8]
   static constexpr int OFF_BAR = OFF_RED + 2 * 2 * 4 * 8 * 4;
   static constexpr int BYTES = OFF_BAR + 8 * 8 + 16;
 };
@@ -78,9 +78,15 @@ __device__ __forceinline__ void umma_desc(uint32_t d_tmem, uint32_t a_lo, uint32
       : "memory");
 }
 
-template <int NKB>
+// QPS = queries per slab.  A slab is NKB blocks of 128 pair rows; at L = 64 one block holds the keys of TWO consecutive queries
+// (their rows are adjacent in memory), and with QPS = 1 half of every block — loaded, multiplied and carried through the softmax
+// by half-idle warps — belonged to the next query and was thrown away: the kernel ran at 1.2 TB/s there (one ~2 us slab step
+// per 16 KB of useful data).  QPS = 2 (L = 64 only) keeps both: per-query softmax reductions over the two warps that own the
+// query's keys, one zsum accumulator per query (the K range of the MMA split at the query boundary), down_z once per query.
+template <int NKB, int QPS>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
+  static_assert(QPS == 1 || (QPS == 2 && NKB == 1), "two queries per slab: L = 64, one key block");
   using LY = P2Layout<NKB>;
   constexpr int KP = LY::KP;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -118,18 +124,19 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
       for (int n = 0; n < n_local; ++n) {
         const int g = n & 1, k = n >> 1;
         const int slab = blockIdx.x + n * gridDim.x;
-        const int b = slab / L, i = slab - b * L;
+        const int q0 = slab * QPS;  // first query of the slab
+        const int b = q0 / L, i = q0 - b * L;
         mbar_wait(&empty[g], (k & 1) ^ 1);
         unsigned char* st = smem + g * LY::STAGE;
-        mbar_expect_tx(&full[g], LY::Z_BYTES + 8 * L * 4);
+        mbar_expect_tx(&full[g], LY::Z_BYTES + 8 * QPS * L * 4);
 #pragma unroll
         for (int rb = 0; rb < NKB; ++rb)
 #pragma unroll
           for (int cb = 0; cb < 2; ++cb)
-            tma_load_2d(st + (rb * 2 + cb) * TILE_BYTES, &tmap_z, cb * KBLK, slab * L + rb * 128, &full[g]);
+            tma_load_2d(st + (rb * 2 + cb) * TILE_BYTES, &tmap_z, cb * KBLK, q0 * L + rb * 128, &full[g]);
         const float* Srow = a.S + ((long)b * N_H * L + i) * L;
-        for (int h = 0; h < N_H; ++h)
-          tma_bulk_1d(st + LY::Z_BYTES + h * KP * 4, Srow + (long)h * L * L, L * 4, &full[g]);
+        for (int h = 0; h < N_H; ++h)  // the logits rows of consecutive queries are adjacent: one copy of QPS * L floats per head
+          tma_bulk_1d(st + LY::Z_BYTES + h * KP * 4, Srow + (long)h * L * L, QPS * L * 4, &full[g]);
       }
     }
   } else {
@@ -138,7 +145,7 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
     unsigned char* st = smem + g * LY::STAGE;
     float* S_s = reinterpret_cast<float*>(st + LY::Z_BYTES);
     unsigned char* P_s = st + LY::Z_BYTES;
-    float* zs = reinterpret_cast<float*>(smem + LY::OFF_ZS) + g * 8 * ZS_PITCH;
+    float* zs = reinterpret_cast<float*>(smem + LY::OFF_ZS) + g * 2 * 8 * ZS_PITCH;
     float* red = reinterpret_cast<float*>(smem + LY::OFF_RED) + g * 64;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const uint32_t d1 = tmem + g * 64, d2 = tmem + g * 64 + 32;
@@ -161,11 +168,13 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
       const int n = 2 * k + g;
       if (n >= n_local) break;
       const int slab = blockIdx.x + n * gridDim.x;
-      const int b = slab / L, i = slab - b * L;
+      const int q0 = slab * QPS;
+      const int tq = QPS == 2 ? (t >> 6) : 0;  // which query of the slab this thread's key belongs to
+      const int b = q0 / L, i = q0 - b * L + tq;
       float mk[NKB];
 #pragma unroll
       for (int rb = 0; rb < NKB; ++rb) {
-        const int j = rb * 128 + t;
+        const int j = QPS == 2 ? (t & 63) : rb * 128 + t;
         mk[rb] = j < L ? __ldg(a.mask + (long)b * L + j) : 0.f;
       }
       const float m_i = __ldg(a.mask + (long)b * L + i);
@@ -200,7 +209,7 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
       for (int rb = 0; rb < NKB; ++rb) {
         float d[16];
         tmem_ld16(d1 + lane_off + rb * 16, d);
-        const bool ok = rb * 128 + t < L;
+        const bool ok = QPS == 2 || rb * 128 + t < L;
         const float mterm = 1e5f * (m_i * mk[rb] - 1.f);
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
@@ -220,7 +229,8 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
       float sum[8];
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
-        mx[h] = fmaxf(fmaxf(red[h], red[8 + h]), fmaxf(red[16 + h], red[24 + h]));
+        if constexpr (QPS == 2) mx[h] = fmaxf(red[(wq & 2) * 8 + h], red[((wq & 2) + 1) * 8 + h]);  // the two warps of this query
+        else mx[h] = fmaxf(fmaxf(red[h], red[8 + h]), fmaxf(red[16 + h], red[24 + h]));
         sum[h] = 0.f;
       }
 #pragma unroll
@@ -239,12 +249,15 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
       }
       named_bar_sync(1 + g, 128);
 #pragma unroll
-      for (int h = 0; h < 8; ++h) sum[h] = 1.f / ((red[32 + h] + red[40 + h]) + (red[48 + h] + red[56 + h]));
+      for (int h = 0; h < 8; ++h) {
+        if constexpr (QPS == 2) sum[h] = 1.f / (red[32 + (wq & 2) * 8 + h] + red[32 + ((wq & 2) + 1) * 8 + h]);
+        else sum[h] = 1.f / ((red[32 + h] + red[40 + h]) + (red[48 + h] + red[56 + h]));
+      }
       // attention weights: split bf16 to HBM (A operands of P.v / P.v_pts) and into the stage as the zsum B operand
       // (rows 0-7 hi, 8-15 lo; K-major SWIZZLE_128B blocks of 64 keys), overwriting the logits rows (all read above)
 #pragma unroll
       for (int rb = 0; rb < NKB; ++rb) {
-        const int j = rb * 128 + t;
+        const int j = QPS == 2 ? (t & 63) : rb * 128 + t;
         unsigned char* blk = P_s + (rb * 2 + (t >> 6)) * 2048;
         const int jj = t & 63;
         bf16* gh = a.P_hi + ((long)b * N_H * L + i) * L + j;
@@ -273,8 +286,14 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
             for (int ks = 0; ks < 8; ++ks) {
               const uint32_t al = z_mn + rb * 2 * BLK + ks * (2048 >> 4);
               const uint32_t bl = p_lo + (rb * 2 + (ks >> 2)) * (2048 >> 4) + (ks & 3) * 2;
-              if (rb | ks) umma_desc<true>(d2, al, mn_hi, bl, DESC_HI_SW128, IDESC_Z);
-              else umma_desc<false>(d2, al, mn_hi, bl, DESC_HI_SW128, IDESC_Z);
+              if constexpr (QPS == 2) {  // keys 0-63 (k-steps 0-3) are query 0, keys 64-127 query 1: one accumulator each
+                const uint32_t dq = d2 + (ks >> 2) * 16;
+                if (ks & 3) umma_desc<true>(dq, al, mn_hi, bl, DESC_HI_SW128, IDESC_Z);
+                else umma_desc<false>(dq, al, mn_hi, bl, DESC_HI_SW128, IDESC_Z);
+              } else {
+                if (rb | ks) umma_desc<true>(d2, al, mn_hi, bl, DESC_HI_SW128, IDESC_Z);
+                else umma_desc<false>(d2, al, mn_hi, bl, DESC_HI_SW128, IDESC_Z);
+              }
             }
           umma_commit(&zsum_bar[g]);
           umma_commit(&empty[g]);  // slab and P operand consumed: the producer may refill this stage
@@ -283,36 +302,40 @@ ipa_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, P2Args a) {
       }
       mbar_wait(&zsum_bar[g], k & 1);
       tc_fence_after();
-      {
-        float d[16];
-        tmem_ld16(d2 + lane_off, d);  // lane = channel t
 #pragma unroll
-        for (int h = 0; h < 8; ++h) zs[h * ZS_PITCH + t] = d[h] + d[8 + h];
+      for (int qq = 0; qq < QPS; ++qq) {
+        float d[16];
+        tmem_ld16(d2 + qq * 16 + lane_off, d);  // lane = channel t
+#pragma unroll
+        for (int h = 0; h < 8; ++h) zs[(qq * 8 + h) * ZS_PITCH + t] = d[h] + d[8 + h];
       }
       tc_fence_before();
       named_bar_sync(1 + g, 128);
       // o_pair[h][d] = down_z(sum_j P z) : sum_j P = 1, so the bias passes through (ipa.py:253-254)
-      float acc0 = bdz, acc1 = bdz;
-      const float* z0 = zs + hq * ZS_PITCH;
-      const float* z1 = zs + (hq + 4) * ZS_PITCH;
+#pragma unroll
+      for (int qq = 0; qq < QPS; ++qq) {
+        float acc0 = bdz, acc1 = bdz;
+        const float* z0 = zs + (qq * 8 + hq) * ZS_PITCH;
+        const float* z1 = zs + (qq * 8 + hq + 4) * ZS_PITCH;
 #pragma unroll 4
-      for (int c = 0; c < C_Z; c += 4) {
-        const float4 u0 = *reinterpret_cast<const float4*>(z0 + c);
-        const float4 u1 = *reinterpret_cast<const float4*>(z1 + c);
-        const float w0 = wdz_s[c * 32 + dd], w1 = wdz_s[(c + 1) * 32 + dd], w2 = wdz_s[(c + 2) * 32 + dd], w3 = wdz_s[(c + 3) * 32 + dd];
-        acc0 = fmaf(w0, u0.x, acc0); acc0 = fmaf(w1, u0.y, acc0); acc0 = fmaf(w2, u0.z, acc0); acc0 = fmaf(w3, u0.w, acc0);
-        acc1 = fmaf(w0, u1.x, acc1); acc1 = fmaf(w1, u1.y, acc1); acc1 = fmaf(w2, u1.z, acc1); acc1 = fmaf(w3, u1.w, acc1);
-      }
-      const long o0 = ((long)b * L + i) * a.ld_opair + hq * 32 + dd;
-      if (a.opair_hi) {
-        const bf16 h0 = __float2bfloat16_rn(acc0), h1 = __float2bfloat16_rn(acc1);
-        a.opair_hi[o0] = h0;
-        a.opair_hi[o0 + 128] = h1;
-        a.opair_lo[o0] = __float2bfloat16_rn(acc0 - __bfloat162float(h0));
-        a.opair_lo[o0 + 128] = __float2bfloat16_rn(acc1 - __bfloat162float(h1));
-      } else {
-        a.o_pair[o0] = acc0;
-        a.o_pair[o0 + 128] = acc1;
+        for (int c = 0; c < C_Z; c += 4) {
+          const float4 u0 = *reinterpret_cast<const float4*>(z0 + c);
+          const float4 u1 = *reinterpret_cast<const float4*>(z1 + c);
+          const float w0 = wdz_s[c * 32 + dd], w1 = wdz_s[(c + 1) * 32 + dd], w2 = wdz_s[(c + 2) * 32 + dd], w3 = wdz_s[(c + 3) * 32 + dd];
+          acc0 = fmaf(w0, u0.x, acc0); acc0 = fmaf(w1, u0.y, acc0); acc0 = fmaf(w2, u0.z, acc0); acc0 = fmaf(w3, u0.w, acc0);
+          acc1 = fmaf(w0, u1.x, acc1); acc1 = fmaf(w1, u1.y, acc1); acc1 = fmaf(w2, u1.z, acc1); acc1 = fmaf(w3, u1.w, acc1);
+        }
+        const long o0 = ((long)q0 + qq) * a.ld_opair + hq * 32 + dd;  // row of query q0 + qq = b * L + its index
+        if (a.opair_hi) {
+          const bf16 h0 = __float2bfloat16_rn(acc0), h1 = __float2bfloat16_rn(acc1);
+          a.opair_hi[o0] = h0;
+          a.opair_hi[o0 + 128] = h1;
+          a.opair_lo[o0] = __float2bfloat16_rn(acc0 - __bfloat162float(h0));
+          a.opair_lo[o0 + 128] = __float2bfloat16_rn(acc1 - __bfloat162float(h1));
+        } else {
+          a.o_pair[o0] = acc0;
+          a.o_pair[o0 + 128] = acc1;
+        }
       }
     }
   }
@@ -627,17 +650,17 @@ __global__ void build_ipa_wb_kernel(const float* __restrict__ Wb, unsigned char*
   *reinterpret_cast<bf16*>(dst + (c / KBLK) * 2048 + sw128_offset(r, c % KBLK)) = v;
 }
 
-template <int NKB>
+template <int NKB, int QPS>
 void launch_pair_tc(const IpaPairArgs& a, const CUtensorMap& mz, const P2Args& k, cudaStream_t st) {
   using LY = P2Layout<NKB>;
   static bool configured = false;
   const int smem = LY::BYTES + 1024;
   if (!configured) {
-    S2S_CUDA(cudaFuncSetAttribute(ipa_pair_tc_kernel<NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S2S_CUDA(cudaFuncSetAttribute(ipa_pair_tc_kernel<NKB, QPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int cap = sm_count() * (NKB == 1 ? 2 : 1);
-  launch_pdl(ipa_pair_tc_kernel<NKB>, k.n_slabs < cap ? k.n_slabs : cap, P2_THREADS, smem, st, mz, k);
+  launch_pdl(ipa_pair_tc_kernel<NKB, QPS>, k.n_slabs < cap ? k.n_slabs : cap, P2_THREADS, smem, st, mz, k);
   S2S_LAUNCH_CHECK();
 }
 
@@ -681,8 +704,12 @@ void ipa_pair_attention_tc(const IpaPairArgs& a, cudaStream_t st) {
     if (atoi(e) & 1) { const uint32_t tmp = k.a2_lbo; k.a2_lbo = k.a2_sbo; k.a2_sbo = tmp; }
   }
   S2S_PROF("ipa_pair_attention", st);
-  if (a.L <= 128) launch_pair_tc<1>(a, mz, k, st);
-  else if (a.L <= 256) launch_pair_tc<2>(a, mz, k, st);
+  static const int qps_env = [] { const char* e = getenv("S2S_IPA_QPS"); return e ? atoi(e) : 2; }();  // 1: A/B timing
+  if (a.L == 64 && qps_env == 2) {  // two queries per slab (see the kernel)
+    k.n_slabs = a.B * a.L / 2;
+    launch_pair_tc<1, 2>(a, mz, k, st);
+  } else if (a.L <= 128) launch_pair_tc<1, 1>(a, mz, k, st);
+  else if (a.L <= 256) launch_pair_tc<2, 1>(a, mz, k, st);
   else if (a.L <= 384) launch_pair_tc_long<3>(mz, k, st);
   else launch_pair_tc_long<4>(mz, k, st);
 }
